@@ -1,0 +1,174 @@
+/* otvm_b200 — C ABI of the B200 (sm_100a) kernels behind the OTVM per-frame inference hot path.
+ *
+ * The reference (Hongje/OTVM) is pure Python/PyTorch and defines no FFI; its "operator interface" is the
+ * set of torch.nn / torch.nn.functional calls on the path (SURVEY.md §2.3, §8(b) last row).  Each entry
+ * point below replaces the reference call sites it cites (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: raw device pointers + sizes, no torch types.  The caller owns every buffer (inputs,
+ *     outputs, workspaces); the library never allocates, frees or retains device memory.
+ *   - activations are NHWC ("pixel-major"): element (n,y,x,c) of a tensor lives at
+ *     base[((n*H + y)*W + x) * ld + c]; `ld` >= C lets a producer write straight into a channel slice of a
+ *     wider concat buffer (torch.cat is never materialised by a copy).
+ *   - dtype: OTVM_F32 (strict fp32 arithmetic, FFMA) or OTVM_BF16 (bf16 storage, tcgen05 tensor cores with
+ *     fp32 accumulation).  Statistics, softmax state and biases are always fp32.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream, and
+ *     returns 0 on success or a negative code (see otvm_strerror); it never throws.
+ */
+#ifndef OTVM_B200_H
+#define OTVM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OTVM_ABI_VERSION 1
+
+enum { OTVM_F32 = 0, OTVM_BF16 = 1 };
+enum { OTVM_ACT_NONE = 0, OTVM_ACT_RELU = 1, OTVM_ACT_LEAKY = 2 };     /* LeakyReLU slope 0.01 (nn default) */
+enum {
+  OTVM_OK = 0, OTVM_ERR_ARG = -1, OTVM_ERR_CUDA = -2, OTVM_ERR_UNSUPPORTED = -3, OTVM_ERR_WORKSPACE = -4
+};
+
+int otvm_version(void);
+const char* otvm_strerror(int code);
+/* last CUDA error string seen by this library on the calling thread (for OTVM_ERR_CUDA) */
+const char* otvm_last_cuda_error(void);
+/* 1 when the device is compute capability 10.x (tcgen05 / TMA paths usable) */
+int otvm_device_is_sm100(int device);
+
+/* ---- convolution ------------------------------------------------------------------------------------
+ * Replaces every nn.Conv2d / F.conv2d on the path: models/trimap/STM.py:17-19,37-43,107,122-127,169-170;
+ * models/alpha/FBA/layers_WS.py:22 (weights arrive already standardised, layers_WS.py:15-21 is folded at
+ * load time because weights are constant in eval); models/alpha/FBA/models.py:303-347,399-415.
+ * Eval-mode BatchNorm (STM.py:44,80 and torchvision Bottleneck) is folded into weight/bias by the host.
+ *
+ *   out[p, co] = act( sum_{ky,kx,ci} w[co,ky,kx,ci] * pre(in[p*stride - pad + (ky,kx)*dil, ci]) + bias[co]
+ *                     + res[p, co] )                  pre = ReLU when relu_in (STM ResBlock, STM.py:24-25)
+ */
+typedef struct {
+  const void* in;      int64_t in_ld;             /* NHWC input, channel stride per pixel (elements)        */
+  int32_t N, H, W, Cin;
+  const void* weight;                             /* [Cout][KH][KW][Cin], same dtype as activations          */
+  const float* bias;                              /* [Cout] fp32 or NULL                                    */
+  int32_t Cout, KH, KW, stride, pad, dil;
+  void* out;           int64_t out_ps, out_cs;    /* out element (p,co) at out[p*out_ps + co*out_cs]        */
+  const void* res;     int64_t res_ld;            /* optional residual (NHWC, added before act) or NULL     */
+  void* out_relu;      int64_t out_relu_ld;       /* optional second NHWC output = ReLU(out) or NULL        */
+  int32_t act;                                    /* OTVM_ACT_*                                             */
+  int32_t relu_in;                                /* apply ReLU to the input while loading                  */
+  int32_t dtype;                                  /* OTVM_F32 / OTVM_BF16 for in, weight, out, res          */
+  int32_t out_f32;                                /* 1: `out` is fp32 even when dtype is bf16 (heads)       */
+  double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
+} otvm_conv_params;
+int otvm_conv2d(const otvm_conv_params* p, void* stream);
+/* 1 when otvm_conv2d would run this problem on the tcgen05 implicit-GEMM kernel (else the FFMA kernel) */
+int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);
+
+/* ---- GroupNorm(32, C) -------------------------------------------------------------------------------
+ * Replaces nn.GroupNorm(32,C) (models/alpha/FBA/layers_WS.py:26-27; FBA/models.py:272-276) together with
+ * the ReLU/LeakyReLU and residual add that follow it (resnet_GN_WS.py:32-48,69-88; FBA/models.py:305-336).
+ * stats: [N][32][2] doubles (sum, sum of squares), zeroed by otvm_gn_stats itself before accumulating.
+ *   y = act( (x - mean_g) * rstd_g * gamma[c] + beta[c] + res )           eps = 1e-5
+ */
+int otvm_gn_stats(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+                  double* stats, void* stream);
+int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+                  const double* stats, const float* gamma, const float* beta, float eps,
+                  const void* res, int64_t res_ld, int32_t act, void* out, int64_t out_ld, void* stream);
+
+/* ---- resampling / pooling ---------------------------------------------------------------------------
+ * F.interpolate(mode='bilinear', align_corners=False): STM.py:115,136; FBA/models.py:358-361,366,371,376.
+ * out[.., c] = (add ? add[.., c] : 0) + bilinear(in)[.., c]; output may be fp32 NCHW planes (out_nchw_f32)
+ * for the final STM logits. */
+int otvm_upsample_bilinear(const void* in, int64_t in_ld, int32_t N, int32_t Hi, int32_t Wi, int32_t C,
+                           int32_t Ho, int32_t Wo, const void* add, int64_t add_ld,
+                           void* out, int64_t out_ld, int32_t dtype, int32_t out_nchw_f32, void* stream);
+/* nn.MaxPool2d(3, 2, 1): STM.py:47,83; resnet_GN_WS.py:98 (indices are never used, FBA/models.py:338) */
+int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+                      void* out, int64_t out_ld, int32_t dtype, void* stream);
+/* nn.AdaptiveAvgPool2d(s), s in {1,2,3,6} in ONE pass over the input (FBA/models.py:302):
+ * out is [N][50][C] (1 + 4 + 9 + 36 cells, scale-major) */
+int otvm_ppm_pool(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+                  void* out, int32_t dtype, void* stream);
+
+/* ---- STM space-time memory read ---------------------------------------------------------------------
+ * Replaces Memory.forward, models/trimap/STM.py:144-163 (bmm :153, /sqrt(De) :154, softmax over THW :155,
+ * bmm :158; the torch.cat at :161 disappears because `out` is channels [0,Do) of the decoder input buffer
+ * whose channels [Do,2Do) the KV_Q value conv writes).  ONE fused kernel with online softmax per split of
+ * the memory axis + a log-sum-exp combine; the [THW x HW] affinity is never materialised.
+ *   keys  : [M][De]   pixel-major rows, M = T*h*w memory locations (ld = De)
+ *   vals  : [Do][ldv] channel-major, location m of channel c at vals[c*ldv + m]
+ *   query : [HW][q_ld] (first De channels used);   out : [HW][out_ld] (first Do channels written)
+ * workspace: fp32, at least otvm_memory_read_workspace(...) bytes.
+ */
+typedef struct {
+  const void* keys; const void* vals; int64_t ldv;
+  const void* query; int64_t q_ld;
+  void* out; int64_t out_ld;
+  int32_t M, HW, De, Do;
+  int32_t dtype;
+  void* workspace; int64_t workspace_bytes;
+  int32_t force_simt;                           /* 1: use the fp32 FFMA kernel even for bf16 inputs (tests) */
+} otvm_read_params;
+int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype);
+int otvm_memory_read(const otvm_read_params* p, void* stream);
+
+/* ---- frame glue (EvalModel.forward, models/alpha/model.py:391-512) ----------------------------------
+ * preprocess_gt + make_trimap_gt (models/alpha/model.py:342-362,380-389): BGR->RGB flip, 1/255, composite,
+ * unknown mask, (2r+1)^2 max-pool dilation, one-hot, centred pad to a multiple of 32 (:408-410).
+ *   a [H*W], fg/bg [3][H*W] fp32 planar (the eval.py tensors);  img: [Hp*Wp][4] fp32 RGB0 in [0,1];
+ *   scaled_img: [3][H*W] fp32 planar un-padded (first return value of EvalModel.forward);
+ *   tri3: [Hp*Wp][4] fp32 one-hot (bg, unknown, fg, 0), padding = bg. */
+int otvm_preprocess(const float* a, const float* fg, const float* bg, int32_t H, int32_t W,
+                    int32_t Hp, int32_t Wp, int32_t pad_top, int32_t pad_left, int32_t radius,
+                    float* img, float* scaled_img, float* tri3, uint8_t* scratch, void* stream);
+
+/* make_trimap + trimap_transform (models/alpha/model.py:40-53, utils/utils.py:12-39) and the 11-channel FBA
+ * input (models/alpha/model.py:414,445): optional softmax over the 3 logits, argmax classes, EXACT Euclidean
+ * distance transform of the bg and fg masks on the device (replaces cv2.distanceTransform on the host),
+ * three Gaussians per mask, soft bg/fg channels, ImageNet normalisation of the image.
+ *   tri_in : [Hp*Wp][tri_ld] fp32, 3 logits (is_logit=1) or 3 probabilities per pixel
+ *   x11    : [Hp*Wp][x11_ld] dtype — 3 normalised RGB + 6 distance channels + soft bg + soft fg
+ *   extras : [Hp*Wp][8] fp32 — RGB in [0,1] (3), soft bg, soft fg, 3 class probabilities (bg, un, fg)
+ *   d2     : [2][Hp*Wp] int32 squared distances (output, exposed for bit-exact tests); scratch: 2*Hp*Wp int32 */
+int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t is_logit, const float* img,
+                       int32_t Hp, int32_t Wp, void* x11, int64_t x11_ld, int32_t dtype,
+                       float* extras, int32_t* d2, int32_t* scratch, void* stream);
+
+/* Exact squared Euclidean distance transform on its own (utils/utils.py:21, cv2.distanceTransform with
+ * DIST_L2 / DIST_MASK_PRECISE before its sqrt): d2[p] = min over seed pixels q (seed[q] != 0) |p-q|^2,
+ * INT32_MAX/2 when there is no seed. */
+int otvm_edt_sq(const uint8_t* seed, int32_t H, int32_t W, int32_t* d2, int32_t* scratch, void* stream);
+
+/* clamp / sigmoid / fba_fusion (models/alpha/FBA/models.py:279-288,383-390,425-431).
+ *   raw  : [P][raw_ld] dtype, channels 0..6 = (alpha, F rgb, B rgb) pre-activation, 7..9 = trimap logits
+ *   img  : [P][8] fp32 extras (RGB first)
+ *   out7 : [P][8] fp32 fused (alpha, F, B, 0);  alpha_dst: optional dtype buffer, alpha written at
+ *   alpha_dst[p*alpha_ld] (channel slot of the refine input concat, FBA/models.py:418) */
+int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f32, const float* extras,
+                  int64_t P, float* out7, void* alpha_dst, int64_t alpha_ld, void* stream);
+
+/* softmax of the refined trimap logits (models/alpha/model.py:460), the 20-channel memorize input
+ * cat(tri3, alpha, hid16) + frame (models/trimap/model.py:231, STM.py:56-67: 22 = 3 normalised RGB + unknown
+ * + fg + alpha + 16 hidden, padded to mem_ld), and the cropped planar outputs eval.py reads (:495-508).
+ *   raw10 : [P][raw_ld] fp32 refine head (7 fused inputs ignored here, 7..9 trimap logits)
+ *   fused : [P][8] fp32 (alpha first);  hid: [P][hid_ld] dtype 16 channels;  extras: [P][8] fp32
+ *   mem_in: [P][mem_ld] dtype;  alpha_out [H*W] fp32;  trimap_out [3][H*W] fp32 (cropped, planar) */
+int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const float* fused, const void* hid,
+                       int64_t hid_ld, const float* extras, int32_t Hp, int32_t Wp, int32_t H, int32_t W,
+                       int32_t pad_top, int32_t pad_left, void* mem_in, int64_t mem_ld, int32_t dtype,
+                       float* alpha_out, float* trimap_out, void* stream);
+
+/* dtype conversion / layout helpers used at the boundary (NCHW fp32 <-> NHWC dtype) */
+int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
+                      int32_t dtype, void* stream);
+int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32_t C, int32_t HW, float* out,
+                      int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OTVM_B200_H */
