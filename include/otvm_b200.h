@@ -25,6 +25,11 @@ extern "C" {
 #endif
 
 #define OTVM_ABI_VERSION 1
+#if defined(__GNUC__)
+#define OTVM_API __attribute__((visibility("default")))
+#else
+#define OTVM_API
+#endif
 
 enum { OTVM_F32 = 0, OTVM_BF16 = 1 };
 enum { OTVM_ACT_NONE = 0, OTVM_ACT_RELU = 1, OTVM_ACT_LEAKY = 2 };     /* LeakyReLU slope 0.01 (nn default) */
@@ -32,12 +37,12 @@ enum {
   OTVM_OK = 0, OTVM_ERR_ARG = -1, OTVM_ERR_CUDA = -2, OTVM_ERR_UNSUPPORTED = -3, OTVM_ERR_WORKSPACE = -4
 };
 
-int otvm_version(void);
-const char* otvm_strerror(int code);
+OTVM_API int otvm_version(void);
+OTVM_API const char* otvm_strerror(int code);
 /* last CUDA error string seen by this library on the calling thread (for OTVM_ERR_CUDA) */
-const char* otvm_last_cuda_error(void);
+OTVM_API const char* otvm_last_cuda_error(void);
 /* 1 when the device is compute capability 10.x (tcgen05 / TMA paths usable) */
-int otvm_device_is_sm100(int device);
+OTVM_API int otvm_device_is_sm100(int device);
 
 /* ---- convolution ------------------------------------------------------------------------------------
  * Replaces every nn.Conv2d / F.conv2d on the path: models/trimap/STM.py:17-19,37-43,107,122-127,169-170;
@@ -63,9 +68,9 @@ typedef struct {
   int32_t out_f32;                                /* 1: `out` is fp32 even when dtype is bf16 (heads)       */
   double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
 } otvm_conv_params;
-int otvm_conv2d(const otvm_conv_params* p, void* stream);
+OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d would run this problem on the tcgen05 implicit-GEMM kernel (else the FFMA kernel) */
-int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);
+OTVM_API int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);
 
 /* ---- GroupNorm(32, C) -------------------------------------------------------------------------------
  * Replaces nn.GroupNorm(32,C) (models/alpha/FBA/layers_WS.py:26-27; FBA/models.py:272-276) together with
@@ -73,26 +78,27 @@ int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);
  * stats: [N][32][2] doubles (sum, sum of squares), zeroed by otvm_gn_stats itself before accumulating.
  *   y = act( (x - mean_g) * rstd_g * gamma[c] + beta[c] + res )           eps = 1e-5
  */
-int otvm_gn_stats(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+OTVM_API int otvm_gn_stats(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
                   double* stats, void* stream);
-int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+OTVM_API int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
                   const double* stats, const float* gamma, const float* beta, float eps,
                   const void* res, int64_t res_ld, int32_t act, void* out, int64_t out_ld, void* stream);
 
 /* ---- resampling / pooling ---------------------------------------------------------------------------
  * F.interpolate(mode='bilinear', align_corners=False): STM.py:115,136; FBA/models.py:358-361,366,371,376.
- * out[.., c] = (add ? add[.., c] : 0) + bilinear(in)[.., c]; output may be fp32 NCHW planes (out_nchw_f32)
- * for the final STM logits. */
-int otvm_upsample_bilinear(const void* in, int64_t in_ld, int32_t N, int32_t Hi, int32_t Wi, int32_t C,
+ * out[.., c] = (add ? add[.., c] : 0) + bilinear(in)[.., c]; out_relu (optional) = ReLU(out), the input of the
+ * ResBlock that follows (STM.py:24,116); output may be fp32 NCHW planes (out_nchw_f32) for the STM logits. */
+OTVM_API int otvm_upsample_bilinear(const void* in, int64_t in_ld, int32_t N, int32_t Hi, int32_t Wi, int32_t C,
                            int32_t Ho, int32_t Wo, const void* add, int64_t add_ld,
-                           void* out, int64_t out_ld, int32_t dtype, int32_t out_nchw_f32, void* stream);
+                           void* out, int64_t out_ld, void* out_relu, int64_t out_relu_ld,
+                           int32_t dtype, int32_t out_nchw_f32, void* stream);
 /* nn.MaxPool2d(3, 2, 1): STM.py:47,83; resnet_GN_WS.py:98 (indices are never used, FBA/models.py:338) */
-int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+OTVM_API int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
                       void* out, int64_t out_ld, int32_t dtype, void* stream);
 /* nn.AdaptiveAvgPool2d(s), s in {1,2,3,6} in ONE pass over the input (FBA/models.py:302):
- * out is [N][50][C] (1 + 4 + 9 + 36 cells, scale-major) */
-int otvm_ppm_pool(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
-                  void* out, int32_t dtype, void* stream);
+ * out is [N][50][C] (1 + 4 + 9 + 36 cells, scale-major); scratch: N*H*12*C floats (per-row column-bin sums) */
+OTVM_API int otvm_ppm_pool(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+                  void* out, float* scratch, int32_t dtype, void* stream);
 
 /* ---- STM space-time memory read ---------------------------------------------------------------------
  * Replaces Memory.forward, models/trimap/STM.py:144-163 (bmm :153, /sqrt(De) :154, softmax over THW :155,
@@ -113,42 +119,50 @@ typedef struct {
   void* workspace; int64_t workspace_bytes;
   int32_t force_simt;                           /* 1: use the fp32 FFMA kernel even for bf16 inputs (tests) */
 } otvm_read_params;
-int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype);
-int otvm_memory_read(const otvm_read_params* p, void* stream);
+OTVM_API int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype);
+OTVM_API int otvm_memory_read(const otvm_read_params* p, void* stream);
 
 /* ---- frame glue (EvalModel.forward, models/alpha/model.py:391-512) ----------------------------------
  * preprocess_gt + make_trimap_gt (models/alpha/model.py:342-362,380-389): BGR->RGB flip, 1/255, composite,
  * unknown mask, (2r+1)^2 max-pool dilation, one-hot, centred pad to a multiple of 32 (:408-410).
  *   a [H*W], fg/bg [3][H*W] fp32 planar (the eval.py tensors);  img: [Hp*Wp][4] fp32 RGB0 in [0,1];
  *   scaled_img: [3][H*W] fp32 planar un-padded (first return value of EvalModel.forward);
- *   tri3: [Hp*Wp][4] fp32 one-hot (bg, unknown, fg, 0), padding = bg. */
-int otvm_preprocess(const float* a, const float* fg, const float* bg, int32_t H, int32_t W,
+ *   tri3: [Hp*Wp][4] fp32 one-hot (bg, unknown, fg, 0), padding = bg;
+ *   imgn: [Hp*Wp][imgn_ld] dtype, (img - mean) / std + one zero channel: the STM query-encoder input
+ *   (STM.py:93); mean_std: HOST pointer, 3 means then 3 stds;  scratch: 2*H*W bytes. */
+OTVM_API int otvm_preprocess(const float* a, const float* fg, const float* bg, int32_t H, int32_t W,
                     int32_t Hp, int32_t Wp, int32_t pad_top, int32_t pad_left, int32_t radius,
-                    float* img, float* scaled_img, float* tri3, uint8_t* scratch, void* stream);
+                    const float* mean_std, float* img, float* scaled_img, float* tri3,
+                    void* imgn, int64_t imgn_ld, int32_t dtype, uint8_t* scratch, void* stream);
 
 /* make_trimap + trimap_transform (models/alpha/model.py:40-53, utils/utils.py:12-39) and the 11-channel FBA
  * input (models/alpha/model.py:414,445): optional softmax over the 3 logits, argmax classes, EXACT Euclidean
  * distance transform of the bg and fg masks on the device (replaces cv2.distanceTransform on the host),
  * three Gaussians per mask, soft bg/fg channels, ImageNet normalisation of the image.
  *   tri_in : [Hp*Wp][tri_ld] fp32, 3 logits (is_logit=1) or 3 probabilities per pixel
- *   x11    : [Hp*Wp][x11_ld] dtype — 3 normalised RGB + 6 distance channels + soft bg + soft fg
+ *   img    : [Hp*Wp][4] fp32 RGB0 in [0,1] (otvm_preprocess);  mean_std: HOST pointer, 3 means then 3 stds
+ *   x11    : [Hp*Wp][x11_ld>=16] dtype — 3 normalised RGB + 6 distance channels + soft bg + soft fg + 5 zeros
+ *   cat_dst: optional [Hp*Wp][cat_ld] dtype, 8 channels written per pixel: normalised RGB, RGB, soft bg, soft fg
+ *            (channels 64..71 of the conv_up4 / refine input concat, FBA/models.py:377-378,418)
  *   extras : [Hp*Wp][8] fp32 — RGB in [0,1] (3), soft bg, soft fg, 3 class probabilities (bg, un, fg)
- *   d2     : [2][Hp*Wp] int32 squared distances (output, exposed for bit-exact tests); scratch: 2*Hp*Wp int32 */
-int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t is_logit, const float* img,
-                       int32_t Hp, int32_t Wp, void* x11, int64_t x11_ld, int32_t dtype,
-                       float* extras, int32_t* d2, int32_t* scratch, void* stream);
+ *   d2     : [2][Hp*Wp] int32 squared distances to the nearest bg / fg pixel (exposed for bit-exact tests)
+ *   scratch: 2*Hp*Wp int32;  seeds: 2*Hp*Wp bytes */
+OTVM_API int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t is_logit, const float* img,
+                       int32_t Hp, int32_t Wp, const float* mean_std, void* x11, int64_t x11_ld,
+                       void* cat_dst, int64_t cat_ld, int32_t dtype,
+                       float* extras, int32_t* d2, int32_t* scratch, uint8_t* seeds, void* stream);
 
 /* Exact squared Euclidean distance transform on its own (utils/utils.py:21, cv2.distanceTransform with
  * DIST_L2 / DIST_MASK_PRECISE before its sqrt): d2[p] = min over seed pixels q (seed[q] != 0) |p-q|^2,
  * INT32_MAX/2 when there is no seed. */
-int otvm_edt_sq(const uint8_t* seed, int32_t H, int32_t W, int32_t* d2, int32_t* scratch, void* stream);
+OTVM_API int otvm_edt_sq(const uint8_t* seed, int32_t H, int32_t W, int32_t* d2, int32_t* scratch, void* stream);
 
 /* clamp / sigmoid / fba_fusion (models/alpha/FBA/models.py:279-288,383-390,425-431).
  *   raw  : [P][raw_ld] dtype, channels 0..6 = (alpha, F rgb, B rgb) pre-activation, 7..9 = trimap logits
  *   img  : [P][8] fp32 extras (RGB first)
  *   out7 : [P][8] fp32 fused (alpha, F, B, 0);  alpha_dst: optional dtype buffer, alpha written at
  *   alpha_dst[p*alpha_ld] (channel slot of the refine input concat, FBA/models.py:418) */
-int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f32, const float* extras,
+OTVM_API int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f32, const float* extras,
                   int64_t P, float* out7, void* alpha_dst, int64_t alpha_ld, void* stream);
 
 /* softmax of the refined trimap logits (models/alpha/model.py:460), the 20-channel memorize input
@@ -156,16 +170,17 @@ int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f3
  * + fg + alpha + 16 hidden, padded to mem_ld), and the cropped planar outputs eval.py reads (:495-508).
  *   raw10 : [P][raw_ld] fp32 refine head (7 fused inputs ignored here, 7..9 trimap logits)
  *   fused : [P][8] fp32 (alpha first);  hid: [P][hid_ld] dtype 16 channels;  extras: [P][8] fp32
- *   mem_in: [P][mem_ld] dtype;  alpha_out [H*W] fp32;  trimap_out [3][H*W] fp32 (cropped, planar) */
-int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const float* fused, const void* hid,
+ *   mem_in: [P][mem_ld>=24] dtype (22 channels + zeros), NULL on the last frame;  mean_std: HOST pointer;
+ *    alpha_out [H*W] fp32;  trimap_out [3][H*W] fp32 (cropped, planar) */
+OTVM_API int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const float* fused, const void* hid,
                        int64_t hid_ld, const float* extras, int32_t Hp, int32_t Wp, int32_t H, int32_t W,
-                       int32_t pad_top, int32_t pad_left, void* mem_in, int64_t mem_ld, int32_t dtype,
-                       float* alpha_out, float* trimap_out, void* stream);
+                       int32_t pad_top, int32_t pad_left, const float* mean_std, void* mem_in, int64_t mem_ld,
+                       int32_t dtype, float* alpha_out, float* trimap_out, void* stream);
 
 /* dtype conversion / layout helpers used at the boundary (NCHW fp32 <-> NHWC dtype) */
-int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
+OTVM_API int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
                       int32_t dtype, void* stream);
-int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32_t C, int32_t HW, float* out,
+OTVM_API int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32_t C, int32_t HW, float* out,
                       int32_t dtype, void* stream);
 
 #ifdef __cplusplus

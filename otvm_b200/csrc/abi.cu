@@ -1,0 +1,97 @@
+// C-ABI entry points that dispatch between the FFMA (strict fp32 / fallback) and tcgen05 kernels.
+#include <string.h>
+#include "common.cuh"
+
+namespace otvm {
+
+static thread_local char g_last_error[256] = "";
+
+void set_cuda_error(cudaError_t e) {
+  strncpy(g_last_error, cudaGetErrorString(e), sizeof(g_last_error) - 1);
+  g_last_error[sizeof(g_last_error) - 1] = 0;
+  cudaGetLastError();                          // clear the sticky-less error state
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+int conv2d_simt(const otvm_conv_params* p, cudaStream_t s);
+int conv2d_tc(const otvm_conv_params* p, cudaStream_t s);
+bool conv2d_tc_supported(const otvm_conv_params* p);
+int memory_read_simt(const otvm_read_params* p, cudaStream_t s);
+int memory_read_tc(const otvm_read_params* p, cudaStream_t s);
+bool memory_read_tc_supported(const otvm_read_params* p);
+int64_t memory_read_tc_workspace(int M, int HW, int De, int Do);
+int read_pick_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
+
+}  // namespace otvm
+
+using namespace otvm;
+
+extern "C" int otvm_version(void) { return OTVM_ABI_VERSION; }
+
+extern "C" const char* otvm_strerror(int code) {
+  switch (code) {
+    case OTVM_OK: return "ok";
+    case OTVM_ERR_ARG: return "invalid argument";
+    case OTVM_ERR_CUDA: return "CUDA error (see otvm_last_cuda_error)";
+    case OTVM_ERR_UNSUPPORTED: return "unsupported shape or dtype for this kernel";
+    case OTVM_ERR_WORKSPACE: return "workspace too small";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* otvm_last_cuda_error(void) { return g_last_error; }
+
+extern "C" int otvm_device_is_sm100(int device) {
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+static int conv_check(const otvm_conv_params* p) {
+  if (!p || !p->in || !p->weight || !p->out) return OTVM_ERR_ARG;
+  if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 ||
+      p->stride <= 0 || p->dil <= 0 || p->pad < 0 || p->in_ld < p->Cin)
+    return OTVM_ERR_ARG;
+  if (p->dtype != OTVM_F32 && p->dtype != OTVM_BF16) return OTVM_ERR_ARG;
+  return OTVM_OK;
+}
+
+extern "C" int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p) {
+  return conv_check(p) == OTVM_OK && conv2d_tc_supported(p) ? 1 : 0;
+}
+
+extern "C" int otvm_conv2d(const otvm_conv_params* p, void* stream) {
+  int rc = conv_check(p);
+  if (rc) return rc;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (conv2d_tc_supported(p)) return conv2d_tc(p, s);
+  return conv2d_simt(p, s);
+}
+
+extern "C" int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype) {
+  (void)dtype; (void)De;
+  // partial O (fp32) + (m, l) per split; both kernels use at most 64 splits and never more than M/64 blocks
+  int ns_simt = read_pick_splits(M, HW, Do, 64, 128, 64);
+  int64_t ns = ns_simt;
+  int64_t tc = memory_read_tc_workspace(M, HW, De, Do);
+  int64_t simt = ns * HW * ((int64_t)Do + 2) * (int64_t)sizeof(float);
+  return simt > tc ? simt : tc;
+}
+
+extern "C" int otvm_memory_read(const otvm_read_params* p, void* stream) {
+  if (!p || !p->keys || !p->vals || !p->query || !p->out || !p->workspace) return OTVM_ERR_ARG;
+  if (p->M <= 0 || p->HW <= 0 || p->De <= 0 || p->Do <= 0) return OTVM_ERR_ARG;
+  if (p->workspace_bytes < otvm_memory_read_workspace(p->M, p->HW, p->De, p->Do, p->dtype)) return OTVM_ERR_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!p->force_simt && memory_read_tc_supported(p)) return memory_read_tc(p, s);
+  return memory_read_simt(p, s);
+}

@@ -1,0 +1,380 @@
+// Per-frame glue of EvalModel.forward (reference models/alpha/model.py:391-512) as fused HBM kernels:
+// preprocessing + trimap dilation, the 8-channel trimap encoding with an EXACT on-device Euclidean distance
+// transform (replaces the three host round trips through cv2.distanceTransform, utils/utils.py:12-23),
+// the FBA fusion heads, and the output / memorize-input packing.
+#include "common.cuh"
+
+namespace otvm {
+
+constexpr int EDT_INF = 0x3fffffff;
+
+struct MeanStd { float mean[3], std[3]; };
+
+static inline int grid1d(int64_t n, int block) {
+  int64_t g = (n + block - 1) / block;
+  int64_t cap = (int64_t)sm_count() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// preprocess_gt: composite + unknown mask (models/alpha/model.py:380-389, 342-349)
+// ---------------------------------------------------------------------------------------------------
+__global__ void composite_kernel(const float* __restrict__ a, const float* __restrict__ fg,
+                                 const float* __restrict__ bg, int H, int W, int Wp, int pad_top, int pad_left,
+                                 float* __restrict__ img, float* __restrict__ scaled, uint8_t* __restrict__ unk) {
+  const int64_t P = (int64_t)H * W;
+  const float kScale = 1.f / 255;                     // IMG_SCALE, models/alpha/model.py:27
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const float al = a[p];
+    int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    float* o = img + ((int64_t)(y + pad_top) * Wp + x + pad_left) * 4;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {                     // flip([2]): BGR -> RGB
+      float f = fg[(2 - c) * P + p] * kScale, b = bg[(2 - c) * P + p] * kScale;
+      float v = f * al + b * (1.f - al);
+      o[c] = v; scaled[c * P + p] = v;
+    }
+    o[3] = 0.f;
+    unk[p] = (al > 0.f && al < 1.f) ? 1 : 0;
+  }
+}
+
+// separable (2r+1)^2 max filter == F.max_pool2d(k=2r+1, s=1, p=r) on a {0,1} mask (:353)
+__global__ void dilate_rows_kernel(const uint8_t* __restrict__ in, int H, int W, int r, uint8_t* __restrict__ out) {
+  const int64_t P = (int64_t)H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
+    int lo = max(0, x - r), hi = min(W - 1, x + r);
+    uint8_t m = 0;
+    for (int i = lo; i <= hi; ++i) m |= in[(int64_t)y * W + i];
+    out[p] = m;
+  }
+}
+
+template <typename T>
+__global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, const float* __restrict__ a, int H, int W,
+                                          int Hp, int Wp, int pad_top, int pad_left, int r,
+                                          float* __restrict__ img, float* __restrict__ tri3, MeanStd ms,
+                                          T* __restrict__ imgn, int64_t imgn_ld) {
+  const int64_t P = (int64_t)Hp * Wp;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    int yp = (int)(p / Wp), xp = (int)(p - (int64_t)yp * Wp);
+    int y = yp - pad_top, x = xp - pad_left;
+    float4 t = make_float4(1.f, 0.f, 0.f, 0.f);       // padding is background (:409-410)
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      int lo = max(0, y - r), hi = min(H - 1, y + r);
+      uint8_t m = 0;
+      for (int i = lo; i <= hi; ++i) m |= rows[(int64_t)i * W + x];
+      float al = a[(int64_t)y * W + x];
+      al = al < 0.f ? 0.f : (al > 1.f ? 1.f : al);
+      int cls = m ? 1 : (int)(2.f * al);              // torch.where(trimap>0.5, 1, 2*alpha).long()  (:360)
+      t = make_float4(cls == 0 ? 1.f : 0.f, cls == 1 ? 1.f : 0.f, cls == 2 ? 1.f : 0.f, 0.f);
+    } else {
+      *reinterpret_cast<float4*>(img + p * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    *reinterpret_cast<float4*>(tri3 + p * 4) = t;
+    // (f - mean) / std of the padded frame: the STM query encoder input (STM.py:93)
+    float4 im = *reinterpret_cast<const float4*>(img + p * 4);
+    float q[4] = {(im.x - ms.mean[0]) / ms.std[0], (im.y - ms.mean[1]) / ms.std[1], (im.z - ms.mean[2]) / ms.std[2], 0.f};
+    store4(imgn + p * imgn_ld, q);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact squared Euclidean distance transform (two passes, integer arithmetic)
+//   pass 1 (columns): g2[y][x] = squared distance to the nearest seed in column x
+//   pass 2 (rows)   : d2[y][x] = min_x' (x-x')^2 + g2[y][x']       (lower envelope by exhaustive search in smem)
+// ---------------------------------------------------------------------------------------------------
+__global__ void edt_cols_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask, int* __restrict__ g2) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= W * nmask) return;
+  int m = idx / W, x = idx - m * W;
+  const uint8_t* s = seed + (int64_t)m * H * W;
+  int* g = g2 + (int64_t)m * H * W;
+  int d = EDT_INF;                                    // distance (not squared) to the last seed above
+  for (int y = 0; y < H; ++y) {
+    d = s[(int64_t)y * W + x] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
+    g[(int64_t)y * W + x] = d;
+  }
+  d = EDT_INF;
+  for (int y = H - 1; y >= 0; --y) {
+    d = s[(int64_t)y * W + x] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
+    int up = g[(int64_t)y * W + x];
+    int best = min(up, d);
+    g[(int64_t)y * W + x] = best >= 32768 ? EDT_INF : best * best;
+  }
+}
+
+__global__ void edt_rows_kernel(const int* __restrict__ g2, int H, int W, int* __restrict__ d2) {
+  extern __shared__ int row[];
+  const int y = blockIdx.x, m = blockIdx.y;
+  const int* g = g2 + ((int64_t)m * H + y) * W;
+  for (int x = threadIdx.x; x < W; x += blockDim.x) row[x] = g[x];
+  __syncthreads();
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    int best = EDT_INF;
+    for (int xp = 0; xp < W; ++xp) {
+      int dx = x - xp;
+      int v = row[xp] + dx * dx;                      // EDT_INF + dx^2 stays below 2^31
+      best = min(best, v);
+    }
+    d2[((int64_t)m * H + y) * W + x] = best >= EDT_INF ? EDT_INF : best;
+  }
+}
+
+static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int* scratch, cudaStream_t s) {
+  edt_cols_kernel<<<ceil_div(W * nmask, 128), 128, 0, s>>>(seed, H, W, nmask, scratch);
+  OTVM_LAUNCH_CHECK();
+  int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
+  edt_rows_kernel<<<dim3(H, nmask), threads, W * sizeof(int), s>>>(scratch, H, W, d2);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// make_trimap (models/alpha/model.py:40-53): classes + seeds, then the 11-channel FBA input
+// ---------------------------------------------------------------------------------------------------
+
+__global__ void trimap_classes_kernel(const float* __restrict__ tri, int64_t tri_ld, int is_logit,
+                                      const float* __restrict__ img, int64_t P, float* __restrict__ extras,
+                                      uint8_t* __restrict__ seeds) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    float t0 = tri[p * tri_ld], t1 = tri[p * tri_ld + 1], t2 = tri[p * tri_ld + 2];
+    if (is_logit) {                                   // F.softmax(_logit_trimap, dim=1)  (:440)
+      float mx = fmaxf(t0, fmaxf(t1, t2));
+      float e0 = expf(t0 - mx), e1 = expf(t1 - mx), e2 = expf(t2 - mx);
+      float inv = 1.f / (e0 + e1 + e2);
+      t0 = e0 * inv; t1 = e1 * inv; t2 = e2 * inv;
+    }
+    int cls = 0; float best = t0;                     // tri.max(dim=2)[1]: first maximum wins
+    if (t1 > best) { best = t1; cls = 1; }
+    if (t2 > best) { cls = 2; }
+    seeds[p] = cls == 0;                              // trimap2b = (scaled == 0)
+    seeds[P + p] = cls == 2;                          // trimap2f = (scaled == 1)
+    float4 im = *reinterpret_cast<const float4*>(img + p * 4);
+    float* e = extras + p * 8;
+    *reinterpret_cast<float4*>(e) = make_float4(im.x, im.y, im.z, t0);
+    *reinterpret_cast<float4*>(e + 4) = make_float4(t2, t0, t1, t2);
+  }
+}
+
+template <typename T>
+__global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* __restrict__ d2, int64_t P,
+                                   MeanStd ms, T* __restrict__ x11, int64_t x11_ld, T* __restrict__ cat_dst,
+                                   int64_t cat_ld) {
+  // trimap_transform, utils/utils.py:25-39: exp(-d^2 / (2 (sigma L)^2)), sigma in {.02,.08,.16}, L = 320
+  const float den0 = (float)(2.0 * (0.02 * 320) * (0.02 * 320));
+  const float den1 = (float)(2.0 * (0.08 * 320) * (0.08 * 320));
+  const float den2 = (float)(2.0 * (0.16 * 320) * (0.16 * 320));
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const float* e = extras + p * 8;
+    float v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (e[c] - ms.mean[c]) / ms.std[c];       // (:414)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      int q = d2[(int64_t)k * P + p];
+      float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+      if (q < EDT_INF) {                              // no seed at all -> clicks stay 0 (utils/utils.py:31)
+        float d = sqrtf((float)q);                    // cv2 returns the float distance; the reference squares it
+        float dm = -(d * d);
+        g0 = expf(dm / den0); g1 = expf(dm / den1); g2 = expf(dm / den2);
+      }
+      v[3 + 3 * k] = g0; v[4 + 3 * k] = g1; v[5 + 3 * k] = g2;
+    }
+    v[9] = e[3]; v[10] = e[4];                        // soft bg, soft fg (:51)
+#pragma unroll
+    for (int c = 11; c < 16; ++c) v[c] = 0.f;
+    T* o = x11 + p * x11_ld;
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) { float q4[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]}; store4(o + c, q4); }
+    if (cat_dst) {                                    // cat(.., conv_out[-6][:, :3], img, two_chan_trimap) (:377-378)
+      float q0[4] = {v[0], v[1], v[2], e[0]}, q1[4] = {e[1], e[2], e[3], e[4]};
+      store4(cat_dst + p * cat_ld, q0); store4(cat_dst + p * cat_ld + 4, q1);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// clamp / sigmoid / fba_fusion (FBA/models.py:279-288)
+// ---------------------------------------------------------------------------------------------------
+template <typename TR, typename TA>
+__global__ void fba_head_kernel(const TR* __restrict__ raw, int64_t raw_ld, const float* __restrict__ extras,
+                                int64_t P, float* __restrict__ out7, TA* __restrict__ alpha_dst, int64_t alpha_ld) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const TR* r = raw + p * raw_ld;
+    float al = fminf(fmaxf(to_f(r[0]), 0.f), 1.f);
+    float F[3], B[3], img[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      F[c] = 1.f / (1.f + expf(-to_f(r[1 + c])));
+      B[c] = 1.f / (1.f + expf(-to_f(r[4 + c])));
+      img[c] = extras[p * 8 + c];
+    }
+    float num = 0.f, den = 0.f, Fo[3], Bo[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float f = al * img[c] + (1.f - al * al) * F[c] - al * (1.f - al) * B[c];
+      float b = (1.f - al) * img[c] + (2.f * al - al * al) * B[c] - al * (1.f - al) * f;   // uses updated F (:281)
+      f = fminf(fmaxf(f, 0.f), 1.f);
+      b = fminf(fmaxf(b, 0.f), 1.f);
+      Fo[c] = f; Bo[c] = b;
+      num += (img[c] - b) * (f - b);
+      den += (f - b) * (f - b);
+    }
+    float a2 = (al * 0.1f + num) / (den + 0.1f);
+    a2 = fminf(fmaxf(a2, 0.f), 1.f);
+    float* o = out7 + p * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(a2, Fo[0], Fo[1], Fo[2]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(Bo[0], Bo[1], Bo[2], 0.f);
+    if (alpha_dst) alpha_dst[p * alpha_ld] = from_f<TA>(a2);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// refined-trimap softmax, memorize input (22 channels), cropped planar outputs
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t raw_ld, const float* __restrict__ fused,
+                                     const T* __restrict__ hid, int64_t hid_ld, const float* __restrict__ extras,
+                                     int Hp, int Wp, int H, int W, int pad_top, int pad_left, MeanStd ms,
+                                     T* __restrict__ mem_in, int64_t mem_ld, float* __restrict__ alpha_out,
+                                     float* __restrict__ trimap_out) {
+  const int64_t P = (int64_t)Hp * Wp, Pc = (int64_t)H * W;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const float* r = raw10 + p * raw_ld;
+    float t0 = r[7], t1 = r[8], t2 = r[9];
+    float mx = fmaxf(t0, fmaxf(t1, t2));
+    float e0 = expf(t0 - mx), e1 = expf(t1 - mx), e2 = expf(t2 - mx);
+    float inv = 1.f / (e0 + e1 + e2);
+    t0 = e0 * inv; t1 = e1 * inv; t2 = e2 * inv;       // F.softmax(_logit_trimap_refine) (:460)
+    const float al = fused[p * 8];
+    if (mem_in) {
+      // Encoder_M input order (STM.py:56-67): frame(3, normalised), unknown, fg, alpha, hid(16)
+      T* o = mem_in + p * mem_ld;
+      float v[8];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = (extras[p * 8 + c] - ms.mean[c]) / ms.std[c];
+      v[3] = t1; v[4] = t2; v[5] = al;
+      const T* h = hid + p * hid_ld;
+      v[6] = to_f(h[0]); v[7] = to_f(h[1]);
+      { float q[4] = {v[0], v[1], v[2], v[3]}; store4(o, q); }
+      { float q[4] = {v[4], v[5], v[6], v[7]}; store4(o + 4, q); }
+      for (int c = 2; c < 14; c += 4) {
+        float q[4] = {to_f(h[c]), to_f(h[c + 1]), to_f(h[c + 2]), to_f(h[c + 3])};
+        store4(o + 6 + c, q);
+      }
+      { float q[4] = {to_f(h[14]), to_f(h[15]), 0.f, 0.f}; store4(o + 20, q); }
+    }
+    int yp = (int)(p / Wp), xp = (int)(p - (int64_t)yp * Wp);
+    int y = yp - pad_top, x = xp - pad_left;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      int64_t q = (int64_t)y * W + x;
+      alpha_out[q] = al;
+      trimap_out[q] = t0; trimap_out[Pc + q] = t1; trimap_out[2 * Pc + q] = t2;
+    }
+  }
+}
+
+}  // namespace otvm
+
+using namespace otvm;
+
+static MeanStd make_ms(const float* mean_std) {
+  MeanStd ms;
+  for (int c = 0; c < 3; ++c) { ms.mean[c] = mean_std[c]; ms.std[c] = mean_std[3 + c]; }
+  return ms;
+}
+
+extern "C" int otvm_preprocess(const float* a, const float* fg, const float* bg, int32_t H, int32_t W, int32_t Hp,
+                               int32_t Wp, int32_t pad_top, int32_t pad_left, int32_t radius, const float* mean_std,
+                               float* img, float* scaled_img, float* tri3, void* imgn, int64_t imgn_ld, int32_t dtype,
+                               uint8_t* scratch, void* stream) {
+  if (!a || !fg || !bg || !img || !scaled_img || !tri3 || !scratch || !imgn || !mean_std || imgn_ld % 4)
+    return OTVM_ERR_ARG;
+  MeanStd ms = make_ms(mean_std);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t P = (int64_t)H * W;
+  uint8_t* unk = scratch; uint8_t* rows = scratch + P;
+  composite_kernel<<<grid1d(P, 256), 256, 0, s>>>(a, fg, bg, H, W, Wp, pad_top, pad_left, img, scaled_img, unk);
+  OTVM_LAUNCH_CHECK();
+  dilate_rows_kernel<<<grid1d(P, 256), 256, 0, s>>>(unk, H, W, radius, rows);
+  OTVM_LAUNCH_CHECK();
+  if (dtype == OTVM_F32)
+    dilate_cols_onehot_kernel<float><<<grid1d((int64_t)Hp * Wp, 256), 256, 0, s>>>(
+        rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<float*>(imgn), imgn_ld);
+  else if (dtype == OTVM_BF16)
+    dilate_cols_onehot_kernel<bf16><<<grid1d((int64_t)Hp * Wp, 256), 256, 0, s>>>(
+        rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<bf16*>(imgn), imgn_ld);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_edt_sq(const uint8_t* seed, int32_t H, int32_t W, int32_t* d2, int32_t* scratch, void* stream) {
+  if (!seed || !d2 || !scratch || W > 8192) return OTVM_ERR_ARG;
+  return edt_launch(seed, H, W, 1, d2, scratch, static_cast<cudaStream_t>(stream));
+}
+
+
+extern "C" int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t is_logit, const float* img, int32_t Hp,
+                                  int32_t Wp, const float* mean_std, void* x11, int64_t x11_ld, void* cat_dst,
+                                  int64_t cat_ld, int32_t dtype, float* extras, int32_t* d2, int32_t* scratch,
+                                  uint8_t* seeds, void* stream) {
+  if (!tri_in || !img || !x11 || !extras || !d2 || !scratch || !seeds || !mean_std || x11_ld < 16 || x11_ld % 4 ||
+      Wp > 8192 || (cat_dst && cat_ld % 4))
+    return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int64_t P = (int64_t)Hp * Wp;
+  trimap_classes_kernel<<<grid1d(P, 256), 256, 0, s>>>(tri_in, tri_ld, is_logit, img, P, extras, seeds);
+  OTVM_LAUNCH_CHECK();
+  int rc = edt_launch(seeds, Hp, Wp, 2, d2, scratch, s);
+  if (rc) return rc;
+  MeanStd ms = make_ms(mean_std);
+  if (dtype == OTVM_F32)
+    trimap_pack_kernel<float><<<grid1d(P, 256), 256, 0, s>>>(extras, d2, P, ms, static_cast<float*>(x11), x11_ld,
+                                                             static_cast<float*>(cat_dst), cat_ld);
+  else if (dtype == OTVM_BF16)
+    trimap_pack_kernel<bf16><<<grid1d(P, 256), 256, 0, s>>>(extras, d2, P, ms, static_cast<bf16*>(x11), x11_ld,
+                                                            static_cast<bf16*>(cat_dst), cat_ld);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f32, const float* extras,
+                             int64_t P, float* out7, void* alpha_dst, int64_t alpha_ld, void* stream) {
+  if (!raw || !extras || !out7) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int g = grid1d(P, 256);
+  const bool rf = raw_f32 || dtype == OTVM_F32;
+  if (dtype == OTVM_F32)
+    fba_head_kernel<float, float><<<g, 256, 0, s>>>((const float*)raw, raw_ld, extras, P, out7, (float*)alpha_dst, alpha_ld);
+  else if (dtype == OTVM_BF16 && rf)
+    fba_head_kernel<float, bf16><<<g, 256, 0, s>>>((const float*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
+  else if (dtype == OTVM_BF16)
+    fba_head_kernel<bf16, bf16><<<g, 256, 0, s>>>((const bf16*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const float* fused, const void* hid,
+                                  int64_t hid_ld, const float* extras, int32_t Hp, int32_t Wp, int32_t H, int32_t W,
+                                  int32_t pad_top, int32_t pad_left, const float* mean_std, void* mem_in,
+                                  int64_t mem_ld, int32_t dtype, float* alpha_out, float* trimap_out, void* stream) {
+  if (!raw10 || !fused || !extras || !alpha_out || !trimap_out || !mean_std) return OTVM_ERR_ARG;
+  if (mem_in && (!hid || mem_ld < 24 || mem_ld % 4 || hid_ld % 2)) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MeanStd ms = make_ms(mean_std);
+  int g = grid1d((int64_t)Hp * Wp, 256);
+  if (dtype == OTVM_F32)
+    frame_outputs_kernel<float><<<g, 256, 0, s>>>(raw10, raw_ld, fused, (const float*)hid, hid_ld, extras, Hp, Wp, H, W,
+                                                  pad_top, pad_left, ms, (float*)mem_in, mem_ld, alpha_out, trimap_out);
+  else if (dtype == OTVM_BF16)
+    frame_outputs_kernel<bf16><<<g, 256, 0, s>>>(raw10, raw_ld, fused, (const bf16*)hid, hid_ld, extras, Hp, Wp, H, W,
+                                                 pad_top, pad_left, ms, (bf16*)mem_in, mem_ld, alpha_out, trimap_out);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}

@@ -1,0 +1,437 @@
+// HBM-bound kernels of the OTVM frame: GroupNorm(32,C) statistics/apply (+activation, +residual), bilinear
+// resampling, max/avg pooling, layout conversion.  All NHWC, 4 channels (16 B fp32 / 8 B bf16) per thread so
+// a warp touches 128..512 contiguous bytes; grids are sized from the SM count (grid-stride loops).
+#include "common.cuh"
+
+namespace otvm {
+
+static inline int grid_for(int64_t work_items, int block) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)sm_count() * 8;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// GroupNorm statistics: per (n, group) sum and sum of squares in fp64 (fp32 partials per thread/block).
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
+                                                       double* __restrict__ stats) {
+  __shared__ float part[32][2];
+  const int n = blockIdx.y;
+  const int c4n = C >> 2;                        // channel quads per pixel
+  const int64_t total = HW * c4n;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;       // multiple of c4n (host guarantees)
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cq = (int)(idx % c4n);
+  const int cg = C >> 5;                         // channels per group
+  if (threadIdx.x < 32) { part[threadIdx.x][0] = 0.f; part[threadIdx.x][1] = 0.f; }
+  __syncthreads();
+  float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+  const T* base = x + (int64_t)n * HW * ld + cq * 4;
+  for (; idx < total; idx += nthreads) {
+    int64_t pix = idx / c4n;
+    float v[4];
+    load4(base + pix * ld, v);
+    s1a += v[0] + v[1]; s2a += v[0] * v[0] + v[1] * v[1];
+    s1b += v[2] + v[3]; s2b += v[2] * v[2] + v[3] * v[3];
+  }
+  const int ga = (cq * 4) / cg, gb = (cq * 4 + 2) / cg;
+  atomicAdd(&part[ga][0], s1a); atomicAdd(&part[ga][1], s2a);
+  atomicAdd(&part[gb][0], s1b); atomicAdd(&part[gb][1], s2b);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    atomicAdd(&stats[(n * 32 + threadIdx.x) * 2 + 0], (double)part[threadIdx.x][0]);
+    atomicAdd(&stats[(n * 32 + threadIdx.x) * 2 + 1], (double)part[threadIdx.x][1]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
+                                                       const double* __restrict__ stats,
+                                                       const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float eps,
+                                                       const T* __restrict__ res, int64_t res_ld, int act,
+                                                       T* __restrict__ out, int64_t out_ld) {
+  extern __shared__ float sc_sh[];               // [C] scale, [C] shift
+  float* sc = sc_sh; float* sh = sc_sh + C;
+  const int n = blockIdx.y;
+  const int cg = C >> 5;
+  const double cnt = (double)HW * cg;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cg;
+    double mean = stats[(n * 32 + g) * 2] / cnt;
+    double var = stats[(n * 32 + g) * 2 + 1] / cnt - mean * mean;
+    float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+    float s = rstd * gamma[c];
+    sc[c] = s; sh[c] = beta[c] - (float)mean * s;
+  }
+  __syncthreads();
+  const int c4n = C >> 2;
+  const int64_t total = HW * c4n;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int64_t pix = idx / c4n; int c = (int)(idx - pix * c4n) * 4;
+    float v[4];
+    load4(x + ((int64_t)n * HW + pix) * ld + c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = fmaf(v[j], sc[c + j], sh[c + j]);
+    if (res) {
+      float r[4];
+      load4(res + ((int64_t)n * HW + pix) * res_ld + c, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], act);
+    store4(out + ((int64_t)n * HW + pix) * out_ld + c, v);
+  }
+}
+
+template <typename T>
+static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* stats, cudaStream_t s) {
+  OTVM_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
+  int c4n = C / 4;
+  int64_t total = (int64_t)HW * c4n;
+  int64_t lcm = c4n > 256 ? c4n : 256;           // c4n is a power of two times {1}: 16..512
+  if (lcm % 256 != 0 || lcm % c4n != 0) return OTVM_ERR_UNSUPPORTED;
+  int64_t want = (int64_t)sm_count() * 4 * 256;
+  int64_t threads = ((total < want ? total : want) + lcm - 1) / lcm * lcm;
+  dim3 grid((unsigned)(threads / 256), N);
+  gn_stats_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+template <typename T>
+static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const double* stats, const float* gamma,
+                      const float* beta, float eps, const void* res, int64_t res_ld, int act, void* out,
+                      int64_t out_ld, cudaStream_t s) {
+  int64_t total = (int64_t)HW * (C / 4);
+  dim3 grid(grid_for(total, 256), N);
+  gn_apply_kernel<T><<<grid, 256, 2 * C * sizeof(float), s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma,
+                                                             beta, eps, static_cast<const T*>(res), res_ld, act,
+                                                             static_cast<T*>(out), out_ld);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=False (ATen upsample_bilinear2d index rule), optional fused add
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index(float scale, int dst, int in_size, int& i0, int& i1, float& l1) {
+  float s = scale * (dst + 0.5f) - 0.5f;
+  s = s < 0.f ? 0.f : s;
+  i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = s - (float)i0;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in, int64_t in_ld, int Hi, int Wi,
+                                                       int C, int Ho, int Wo, float sy, float sx,
+                                                       const T* __restrict__ add, int64_t add_ld,
+                                                       T* __restrict__ out, int64_t out_ld,
+                                                       T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+  const int c4n = C >> 2;
+  const int64_t total = (int64_t)N * Ho * Wo * c4n;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int64_t pix = idx / c4n; int c = (int)(idx - pix * c4n) * 4;
+    int n = (int)(pix / ((int64_t)Ho * Wo));
+    int r = (int)(pix - (int64_t)n * Ho * Wo);
+    int oy = r / Wo, ox = r - oy * Wo;
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(sy, oy, Hi, y0, y1, ly);
+    src_index(sx, ox, Wi, x0, x1, lx);
+    const T* b = in + (int64_t)n * Hi * Wi * in_ld + c;
+    float v00[4], v01[4], v10[4], v11[4], o[4];
+    load4(b + ((int64_t)y0 * Wi + x0) * in_ld, v00);
+    load4(b + ((int64_t)y0 * Wi + x1) * in_ld, v01);
+    load4(b + ((int64_t)y1 * Wi + x0) * in_ld, v10);
+    load4(b + ((int64_t)y1 * Wi + x1) * in_ld, v11);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+    if (add) {
+      float a[4];
+      load4(add + pix * add_ld + c, a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = a[j] + o[j];
+    }
+    store4(out + pix * out_ld + c, o);
+    if (out_relu) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+      store4(out_relu + pix * out_relu_ld + c, o);
+    }
+  }
+}
+
+// scalar-channel variant writing fp32 (NHWC with out_ld, or NCHW planes): the 3-channel STM logits (STM.py:136)
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restrict__ in, int64_t in_ld, int Hi,
+                                                              int Wi, int C, int Ho, int Wo, float sy, float sx,
+                                                              float* __restrict__ out, int64_t out_ld, int nchw) {
+  const int64_t total = (int64_t)Ho * Wo;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += nthreads) {
+    int oy = (int)(pix / Wo), ox = (int)(pix - (int64_t)oy * Wo);
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(sy, oy, Hi, y0, y1, ly);
+    src_index(sx, ox, Wi, x0, x1, lx);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+    for (int c = 0; c < C; ++c) {
+      float v00 = to_f(in[((int64_t)y0 * Wi + x0) * in_ld + c]), v01 = to_f(in[((int64_t)y0 * Wi + x1) * in_ld + c]);
+      float v10 = to_f(in[((int64_t)y1 * Wi + x0) * in_ld + c]), v11 = to_f(in[((int64_t)y1 * Wi + x1) * in_ld + c]);
+      float o = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+      if (nchw) out[(int64_t)c * total + pix] = o; else out[pix * out_ld + c] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// MaxPool2d(3, 2, 1)
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, int64_t in_ld, int N, int H, int W,
+                                                      int C, int Ho, int Wo, T* __restrict__ out, int64_t out_ld) {
+  const int c4n = C >> 2;
+  const int64_t total = (int64_t)N * Ho * Wo * c4n;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int64_t pix = idx / c4n; int c = (int)(idx - pix * c4n) * 4;
+    int n = (int)(pix / ((int64_t)Ho * Wo));
+    int r = (int)(pix - (int64_t)n * Ho * Wo);
+    int oy = r / Wo, ox = r - oy * Wo;
+    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      int iy = oy * 2 - 1 + dy;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        int ix = ox * 2 - 1 + dx;
+        if (ix < 0 || ix >= W) continue;
+        float v[4];
+        load4(in + ((int64_t)(n * H + iy) * W + ix) * in_ld + c, v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
+      }
+    }
+    store4(out + pix * out_ld + c, m);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Pyramid pooling: AdaptiveAvgPool2d(s) for s in {1,2,3,6} from ONE read of the feature map.
+// pass 1: per row y, the 12 column-bin sums (1+2+3+6) for every channel; pass 2: the 50 cells from row sums.
+// bin b of scale s covers [floor(b*L/s), ceil((b+1)*L/s))  (ATen adaptive pooling).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int bin_start(int b, int s, int L) { return (b * L) / s; }
+__device__ __forceinline__ int bin_end(int b, int s, int L) { return ((b + 1) * L + s - 1) / s; }
+
+template <typename T>
+__global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in, int64_t in_ld, int H, int W, int C,
+                                                       float* __restrict__ rows) {
+  const int y = blockIdx.x, n = blockIdx.z;
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  float acc[12][4];
+#pragma unroll
+  for (int b = 0; b < 12; ++b)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
+  const T* row = in + ((int64_t)(n * H + y) * W) * in_ld + c;
+  for (int x = 0; x < W; ++x) {
+    float v[4];
+    load4(row + (int64_t)x * in_ld, v);
+    int bi = 0;
+#pragma unroll
+    for (int si = 0; si < 4; ++si) {
+      const int s = si == 0 ? 1 : si == 1 ? 2 : si == 2 ? 3 : 6;
+#pragma unroll
+      for (int b = 0; b < s; ++b, ++bi) {
+        if (x >= bin_start(b, s, W) && x < bin_end(b, s, W)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[bi][j] += v[j];
+        }
+      }
+    }
+  }
+  float* o = rows + (((int64_t)n * H + y) * 12) * C + c;
+#pragma unroll
+  for (int b = 0; b < 12; ++b) *reinterpret_cast<float4*>(o + (int64_t)b * C) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict__ rows, int H, int W, int C,
+                                                        T* __restrict__ out) {
+  const int cell = blockIdx.x, n = blockIdx.z;          // 0..49: scale-major, row-major inside a scale
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  int s, local, xoff;
+  if (cell < 1) { s = 1; local = cell; xoff = 0; }
+  else if (cell < 5) { s = 2; local = cell - 1; xoff = 1; }
+  else if (cell < 14) { s = 3; local = cell - 5; xoff = 3; }
+  else { s = 6; local = cell - 14; xoff = 6; }
+  const int by = local / s, bx = local - by * s;
+  const int y0 = bin_start(by, s, H), y1 = bin_end(by, s, H);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int y = y0; y < y1; ++y) {
+    float4 v = *reinterpret_cast<const float4*>(rows + (((int64_t)n * H + y) * 12 + xoff + bx) * C + c);
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+  const float inv = 1.f / (float)((y1 - y0) * (bin_end(bx, s, W) - bin_start(bx, s, W)));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] *= inv;
+  store4(out + ((int64_t)n * 50 + cell) * C + c, acc);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// layout conversion at the boundary
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t HW, T* __restrict__ out,
+                                    int64_t out_ld, int N) {
+  const int64_t total = (int64_t)N * HW * C;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int c = (int)(idx % C); int64_t pix = idx / C;             // pix = n*HW + p
+    int64_t n = pix / HW, p = pix - n * HW;
+    out[pix * out_ld + c] = from_f<T>(in[(n * C + c) * HW + p]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t in_ld, int C, int64_t HW,
+                                    float* __restrict__ out, int N) {
+  const int64_t total = (int64_t)N * HW * C;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int64_t p = idx % HW; int64_t r = idx / HW; int c = (int)(r % C); int64_t n = r / C;
+    out[idx] = to_f(in[(n * HW + p) * in_ld + c]);
+  }
+}
+
+}  // namespace otvm
+
+using namespace otvm;
+
+#define DISPATCH_DTYPE(dtype, CALL_F32, CALL_BF16) \
+  do { if ((dtype) == OTVM_F32) return CALL_F32; if ((dtype) == OTVM_BF16) return CALL_BF16; return OTVM_ERR_ARG; } while (0)
+
+extern "C" int otvm_gn_stats(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+                             double* stats, void* stream) {
+  if (!x || !stats || C % 32 != 0 || C % 4 != 0 || ld % 4 != 0) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, gn_stats_t<float>(x, ld, N, HW, C, stats, s), gn_stats_t<bf16>(x, ld, N, HW, C, stats, s));
+}
+
+extern "C" int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
+                             const double* stats, const float* gamma, const float* beta, float eps,
+                             const void* res, int64_t res_ld, int32_t act, void* out, int64_t out_ld,
+                             void* stream) {
+  if (!x || !stats || !out || C % 32 != 0 || ld % 4 != 0 || out_ld % 4 != 0 || (res && res_ld % 4 != 0))
+    return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype,
+                 gn_apply_t<float>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, s),
+                 gn_apply_t<bf16>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, s));
+}
+
+template <typename T>
+static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                      const void* add, int64_t add_ld, void* out, int64_t out_ld, void* out_relu,
+                      int64_t out_relu_ld, int out_nchw_f32, cudaStream_t s) {
+  // ATen: scale = in/out computed in float (F.interpolate with an integer scale_factor gives the same value)
+  float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
+  if (out_nchw_f32 || C % 4 != 0) {
+    if (add || out_relu || N != 1) return OTVM_ERR_UNSUPPORTED;
+    upsample_scalar_kernel<T><<<grid_for((int64_t)Ho * Wo, 256), 256, 0, s>>>(
+        static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo, sy, sx, static_cast<float*>(out), out_ld,
+        out_nchw_f32 == 1);
+  } else {
+    if (in_ld % 4 || out_ld % 4 || (add && add_ld % 4) || (out_relu && out_relu_ld % 4)) return OTVM_ERR_ARG;
+    int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+    upsample_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
+                                                           sy, sx, static_cast<const T*>(add), add_ld,
+                                                           static_cast<T*>(out), out_ld,
+                                                           static_cast<T*>(out_relu), out_relu_ld, N);
+  }
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_upsample_bilinear(const void* in, int64_t in_ld, int32_t N, int32_t Hi, int32_t Wi, int32_t C,
+                                      int32_t Ho, int32_t Wo, const void* add, int64_t add_ld, void* out,
+                                      int64_t out_ld, void* out_relu, int64_t out_relu_ld, int32_t dtype,
+                                      int32_t out_nchw_f32, void* stream) {
+  if (!in || !out) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype,
+                 upsample_t<float>(in, in_ld, N, Hi, Wi, C, Ho, Wo, add, add_ld, out, out_ld, out_relu, out_relu_ld,
+                                   out_nchw_f32, s),
+                 upsample_t<bf16>(in, in_ld, N, Hi, Wi, C, Ho, Wo, add, add_ld, out, out_ld, out_relu, out_relu_ld,
+                                  out_nchw_f32, s));
+}
+
+template <typename T>
+static int maxpool_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, int64_t out_ld,
+                     cudaStream_t s) {
+  int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  int64_t total = (int64_t)N * Ho * Wo * (C / 4);
+  maxpool_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, N, H, W, C, Ho, Wo,
+                                                        static_cast<T*>(out), out_ld);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C,
+                                 void* out, int64_t out_ld, int32_t dtype, void* stream) {
+  if (!in || !out || C % 4 || in_ld % 4 || out_ld % 4) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, maxpool_t<float>(in, in_ld, N, H, W, C, out, out_ld, s),
+                 maxpool_t<bf16>(in, in_ld, N, H, W, C, out, out_ld, s));
+}
+
+template <typename T>
+static int ppm_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, float* scratch,
+                 cudaStream_t s) {
+  dim3 g1(H, ceil_div(C / 4, 128), N), g2(50, ceil_div(C / 4, 128), N);
+  ppm_rows_kernel<T><<<g1, 128, 0, s>>>(static_cast<const T*>(in), in_ld, H, W, C, scratch);
+  OTVM_LAUNCH_CHECK();
+  ppm_cells_kernel<T><<<g2, 128, 0, s>>>(scratch, H, W, C, static_cast<T*>(out));
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_ppm_pool(const void* in, int64_t in_ld, int32_t N, int32_t H, int32_t W, int32_t C, void* out,
+                             float* scratch, int32_t dtype, void* stream) {
+  if (!in || !out || !scratch || C % 4 || in_ld % 4) return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DISPATCH_DTYPE(dtype, ppm_t<float>(in, in_ld, N, H, W, C, out, scratch, s),
+                 ppm_t<bf16>(in, in_ld, N, H, W, C, out, scratch, s));
+}
+
+extern "C" int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
+                                 int32_t dtype, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int g = grid_for((int64_t)N * HW * C, 256);
+  if (dtype == OTVM_F32) nchw_to_nhwc_kernel<float><<<g, 256, 0, s>>>(in, C, HW, static_cast<float*>(out), out_ld, N);
+  else if (dtype == OTVM_BF16) nchw_to_nhwc_kernel<bf16><<<g, 256, 0, s>>>(in, C, HW, static_cast<bf16*>(out), out_ld, N);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32_t C, int32_t HW, float* out,
+                                 int32_t dtype, void* stream) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int g = grid_for((int64_t)N * HW * C, 256);
+  if (dtype == OTVM_F32) nhwc_to_nchw_kernel<float><<<g, 256, 0, s>>>(static_cast<const float*>(in), in_ld, C, HW, out, N);
+  else if (dtype == OTVM_BF16) nhwc_to_nchw_kernel<bf16><<<g, 256, 0, s>>>(static_cast<const bf16*>(in), in_ld, C, HW, out, N);
+  else return OTVM_ERR_ARG;
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}

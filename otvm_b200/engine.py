@@ -1,0 +1,423 @@
+"""Per-frame OTVM inference engine over the sm_100a C ABI.
+
+Host-side mirror of the reference dataflow (paths relative to the reference root):
+
+* ``segment``  – STM.segment, models/trimap/STM.py:239-257 (Encoder_Q :92-102, KeyValue :173-174,
+  Memory.read :144-163, Decoder :129-137)
+* ``matting``  – MattingModule.forward, models/alpha/FBA/models.py:32-45 (ResnetDilated :251-269,
+  fba_decoder :351-392, RefinementModule :417-435)
+* ``memorize`` – STM.memorize, models/trimap/STM.py:201-228 (Encoder_M :56-74)
+* ``MemoryBank`` – the eviction policy of EvalModel.forward, models/alpha/model.py:472-493
+
+Everything numerical runs in the hand-written CUDA kernels of ``csrc/``; PyTorch only owns device memory and
+the stream.  Weights are prepared ONCE per ``load_state_dict`` (they are constant in eval): eval-mode
+BatchNorm is folded into the preceding convolution, weight standardisation (layers_WS.py:15-21) is applied
+to the weights themselves, the five 7x7 stems of Encoder_M (STM.py:63,67) become one 22-channel stem, and
+all filters are re-laid out [Cout][KH][KW][Cin] (K-major) in the activation dtype.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
+
+DE, DO = 128, 512          # key / value channels (STM.py:184-185)
+BN_EPS = 1e-5
+
+
+def _ws(w: torch.Tensor) -> torch.Tensor:
+    """layers_WS.py:15-21 in fp32 (same association order as the reference)."""
+    m = w.mean(dim=1, keepdim=True).mean(dim=2, keepdim=True).mean(dim=3, keepdim=True)
+    w = w - m
+    std = torch.sqrt(torch.var(w.view(w.size(0), -1), dim=1) + 1e-12).view(-1, 1, 1, 1) + 1e-5
+    return w / std
+
+
+class PackedWeights:
+    """state_dict -> kernel-ready tensors on ``device`` in ``dtype``."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device):
+        self.dtype, self.device = dtype, device
+        self.conv: Dict[str, tuple] = {}
+        self.norm: Dict[str, tuple] = {}
+        f = lambda k: sd[k].detach().to("cpu", torch.float32)
+
+        def put(name, w, b, cin_pad=None):
+            cout, cin, kh, kw = w.shape
+            if cin_pad and cin_pad > cin:
+                w = torch.cat([w, w.new_zeros(cout, cin_pad - cin, kh, kw)], dim=1)
+            wp = w.permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
+            bp = b.contiguous().to(device=device, dtype=torch.float32) if b is not None else None
+            self.conv[name] = (wp, bp)
+
+        def bn_fold(w, bn, b=None):
+            s = f(bn + ".weight") / torch.sqrt(f(bn + ".running_var") + BN_EPS)
+            bias = f(bn + ".bias") - f(bn + ".running_mean") * s
+            if b is not None:
+                bias = bias + b * s
+            return w * s.view(-1, 1, 1, 1), bias
+
+        # ---- STM encoders: torchvision ResNet-50 (conv1..layer3) with folded BN ------------------------
+        for enc in ("trimap.model.Encoder_Q", "trimap.model.Encoder_M"):
+            if enc.endswith("_M"):          # order must match frame_outputs' 22-channel memorize input
+                w = torch.cat([f(enc + ".conv1.weight"), f(enc + ".conv1_m.weight"), f(enc + ".conv1_o.weight"),
+                               f(enc + ".conv1_a.weight"), f(enc + ".conv1_h.weight")], dim=1)
+                put(enc + ".stem", *bn_fold(w, enc + ".bn1"), cin_pad=24)
+            else:
+                put(enc + ".stem", *bn_fold(f(enc + ".conv1.weight"), enc + ".bn1"), cin_pad=4)
+            for lname, blocks in (("res2", 3), ("res3", 4), ("res4", 6)):
+                for b in range(blocks):
+                    p = f"{enc}.{lname}.{b}"
+                    for c in ("1", "2", "3"):
+                        put(f"{p}.conv{c}", *bn_fold(f(f"{p}.conv{c}.weight"), f"{p}.bn{c}"))
+                    if b == 0:
+                        put(p + ".downsample", *bn_fold(f(p + ".downsample.0.weight"), p + ".downsample.1"))
+        for kv in ("trimap.model.KV_M_r4", "trimap.model.KV_Q_r4"):
+            put(kv + ".Key", f(kv + ".Key.weight"), f(kv + ".Key.bias"))
+            put(kv + ".Value", f(kv + ".Value.weight"), f(kv + ".Value.bias"))
+        d = "trimap.model.Decoder"
+        plain = [d + ".convFM", d + ".ResMM.conv1", d + ".ResMM.conv2", d + ".pred"]
+        for rf in ("RF3", "RF2"):
+            plain += [f"{d}.{rf}.convFS"] + [f"{d}.{rf}.{rb}.conv{c}" for rb in ("ResFS", "ResMM") for c in "12"]
+        plain += ["NET.decoder.conv_up4.2", "NET.decoder.conv_up4.4", "NET.refine.pred.0", "NET.refine.pred.2",
+                  "NET.refine.pred.4"]
+        for name in plain:
+            put(name, f(name + ".weight"), f(name + ".bias"))
+        put("NET.decoder.conv_up4.0", f("NET.decoder.conv_up4.0.weight"), f("NET.decoder.conv_up4.0.bias"), cin_pad=80)
+
+        # ---- FBA: weight-standardised convs + GroupNorm affine -----------------------------------------
+        def ws_put(name, cin_pad=None):
+            b = f(name + ".bias") if (name + ".bias") in sd else None
+            put(name, _ws(f(name + ".weight")), b, cin_pad=cin_pad)
+
+        def gn_put(name):
+            self.norm[name] = (f(name + ".weight").to(device), f(name + ".bias").to(device))
+
+        ws_put("NET.encoder.conv1", cin_pad=16); gn_put("NET.encoder.bn1")
+        for lname, blocks in (("layer1", 3), ("layer2", 4), ("layer3", 6), ("layer4", 3)):
+            for b in range(blocks):
+                p = f"NET.encoder.{lname}.{b}"
+                for c in ("1", "2", "3"):
+                    ws_put(f"{p}.conv{c}"); gn_put(f"{p}.bn{c}")
+                if b == 0:
+                    ws_put(p + ".downsample.0"); gn_put(p + ".downsample.1")
+        for i in range(4):
+            ws_put(f"NET.decoder.ppm.{i}.1"); gn_put(f"NET.decoder.ppm.{i}.2")
+        for c, n in (("conv_up1.0", "conv_up1.1"), ("conv_up1.3", "conv_up1.4"), ("conv_up2.0", "conv_up2.1"),
+                     ("conv_up3.0", "conv_up3.1")):
+            ws_put("NET.decoder." + c); gn_put("NET.decoder." + n)
+        ws_put("NET.refine.conv1.0", cin_pad=80); gn_put("NET.refine.conv1.1")
+        for l in ("layer1", "layer2"):
+            for c in ("1", "2"):
+                ws_put(f"NET.refine.{l}.conv{c}"); gn_put(f"NET.refine.{l}.bn{c}")
+
+        ms = lambda m, s: [float(v) for v in f(m).flatten()] + [float(v) for v in f(s).flatten()]
+        self.ms_alpha = ms("IMG_MEAN", "IMG_STD")
+        self.ms_q = ms("trimap.model.Encoder_Q.mean", "trimap.model.Encoder_Q.std")
+        self.ms_m = ms("trimap.model.Encoder_M.mean", "trimap.model.Encoder_M.std")
+
+
+class FramePlan:
+    """Device buffers for one padded frame size (allocated once, reused every frame)."""
+
+    def __init__(self, H, W, dtype, device):
+        self.H, self.W = H, W
+        self.Hp, self.Wp = H + (32 - H % 32) % 32, W + (32 - W % 32) % 32
+        self.pad_top, self.pad_left = (self.Hp - H) // 2, (self.Wp - W) // 2     # models/alpha/common.py:17-19
+        self.dtype, self.device = dtype, device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def buf(self, name, shape, dtype=None, zero=False):
+        t = self.bufs.get(name)
+        if t is None:
+            alloc = torch.zeros if zero else torch.empty
+            t = alloc(shape, dtype=dtype or self.dtype, device=self.device)
+            self.bufs[name] = t
+        assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
+        return t
+
+
+class MemoryBank:
+    """Pre-allocated key/value bank with in-place slot replacement.
+
+    Reference policy (models/alpha/model.py:472-493): slot 0 (first frame) is kept for ever; a ``memorize``
+    frame appends, any other frame overwrites the most recent slot; above ``max_memory_num`` the second-oldest
+    slot is dropped.  Softmax over the memory axis is order-invariant, so instead of re-concatenating tensors
+    every frame the new key/value are written straight into the slot that would be dropped.
+    Layout: keys [cap*HW, De] rows (location-major), values [Do, cap*HW] channel-major (K-major operand of the
+    P.V contraction).
+    """
+
+    def __init__(self, hw, cap, dtype, device):
+        self.hw, self.cap = hw, cap
+        self.keys = torch.zeros(cap * hw, DE, dtype=dtype, device=device)
+        self.vals = torch.zeros(DO, cap * hw, dtype=dtype, device=device)
+        self.order = []                 # logical (oldest..newest) -> physical slot
+
+    @property
+    def T(self):
+        return len(self.order)
+
+    def reset(self):
+        self.order = []
+
+    def next_slot(self, first_frame, memorize, max_memory_num):
+        """Returns (slot to write, new logical order) or (None, order) when the frame is not stored."""
+        o = list(self.order)
+        if max_memory_num == 0:
+            return (0, [0]) if first_frame else (None, o)
+        if max_memory_num == 1 or first_frame:
+            return 0, [0]
+        if memorize or len(o) == 1:
+            if len(o) + 1 > max_memory_num:            # append then drop logical slot 1 -> reuse its storage
+                s = o[1]
+                return s, [o[0]] + o[2:] + [s]
+            s = len(o)
+            assert s < self.cap, "memory bank capacity exceeded"
+            return s, o + [s]
+        return o[-1], o                                # overwrite the most recent slot
+
+    def key_slot(self, s):
+        return self.keys[s * self.hw:(s + 1) * self.hw]
+
+    def val_slot_ptr_offset(self, s):
+        return s * self.hw
+
+
+class Engine:
+    def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16):
+        self.dtype, self.device = dtype, torch.device(device)
+        self.w = PackedWeights(state_dict, dtype, self.device)
+        self.bank_capacity = bank_capacity
+        self.plans: Dict[tuple, FramePlan] = {}
+        self.banks: Dict[tuple, MemoryBank] = {}
+
+    # ------------------------------------------------------------------------------------------------
+    def plan(self, H, W) -> FramePlan:
+        k = (H, W)
+        if k not in self.plans:
+            self.plans[k] = FramePlan(H, W, self.dtype, self.device)
+        return self.plans[k]
+
+    def bank(self, pl: FramePlan) -> MemoryBank:
+        k = (pl.Hp, pl.Wp)
+        if k not in self.banks:
+            self.banks[k] = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), self.bank_capacity, self.dtype, self.device)
+        return self.banks[k]
+
+    # ---- building blocks ---------------------------------------------------------------------------
+    def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, **kw):
+        w, b = self.w.conv[name]
+        N, H, W, _ = x.shape
+        kh = w.shape[1]
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        if out is None:
+            out = pl.buf(out_name or name, (N, Ho, Wo, w.shape[0]))
+        return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, **kw)
+
+    def _tv_bottleneck(self, pl, p, x, stride, out=None):
+        """torchvision Bottleneck with BN folded; ReLUs and the residual add live in the conv epilogues."""
+        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU)
+        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU)
+        idn = self._conv(pl, p + ".downsample", x, stride=stride) if (p + ".downsample") in self.w.conv else x
+        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU)
+
+    def _tv_encoder(self, pl, enc, x):
+        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU)
+        N, H, W, C = c1.shape
+        x = ops.maxpool3x3s2(c1, pl.buf(enc + ".pool", (N, (H + 1) // 2, (W + 1) // 2, C)))
+        feats = []
+        for lname, blocks, stride in (("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2)):
+            for b in range(blocks):
+                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1)
+            feats.append(x)
+        return feats       # r2, r3, r4
+
+    def _gn(self, pl, name, x, *, act, res=None, out=None, stats=None):
+        g, b = self.w.norm[name]
+        if stats is None:
+            stats = pl.buf("gn_stats", (64,), torch.float64)
+            ops.gn_stats(x, stats)
+        return ops.gn_apply(x, stats, g, b, out if out is not None else x, act=act, res=res)
+
+    def _ws_gn(self, pl, conv, norm, x, *, act, res=None, out=None, stride=1, pad=0, dil=1, raw_name=None):
+        """WS-conv -> GroupNorm(32) -> activation (+residual).  GN statistics are accumulated by the conv
+        epilogue; the normalise/affine/activation pass runs in place unless ``out`` is given."""
+        stats = pl.buf("gn_stats." + conv, (64,), torch.float64)
+        raw = self._conv(pl, conv, x, raw_name, stride=stride, pad=pad, dil=dil, gn_stats=stats)
+        return self._gn(pl, norm, raw, act=act, res=res, out=out, stats=stats)
+
+    def _gn_bottleneck(self, pl, p, x, stride, dil, out=None):
+        t = self._ws_gn(pl, p + ".conv1", p + ".bn1", x, act=ACT_RELU)
+        t = self._ws_gn(pl, p + ".conv2", p + ".bn2", t, act=ACT_RELU, stride=stride, pad=dil, dil=dil)
+        if (p + ".downsample.0") in self.w.conv:
+            idn = self._ws_gn(pl, p + ".downsample.0", p + ".downsample.1", x, act=ACT_NONE, stride=stride)
+        else:
+            idn = x
+        return self._ws_gn(pl, p + ".conv3", p + ".bn3", t, act=ACT_RELU, res=idn, out=out)
+
+    def _resblock(self, pl, p, x, x_relu, *, out_name, final_relu=False, out_relu_name=None):
+        """STM ResBlock (STM.py:23-30): x + conv2(relu(conv1(relu(x)))).  ``x_relu`` is relu(x), written by
+        the producer of ``x``; returns (y, relu(y) or None)."""
+        r = self._conv(pl, p + ".conv1", x_relu, pad=1, act=ACT_RELU)
+        N, H, W, C = x.shape
+        y = pl.buf(out_name, (N, H, W, C))
+        yr = pl.buf(out_relu_name, (N, H, W, C)) if out_relu_name else None
+        self._conv(pl, p + ".conv2", r, out=y, pad=1, res=x, act=ACT_RELU if final_relu else ACT_NONE, out_relu=yr)
+        return y, yr
+
+    # ---- STM ---------------------------------------------------------------------------------------
+    def segment(self, pl: FramePlan, bank: MemoryBank):
+        """Propagated trimap logits [Hp*Wp][4] fp32 for the current frame (imgn must be ready)."""
+        imgn = pl.bufs["imgn"]
+        r2, r3, r4 = self._tv_encoder(pl, "trimap.model.Encoder_Q", imgn)
+        N, h, w, _ = r4.shape
+        m4in = pl.buf("m4in", (1, h, w, 2 * DO))
+        qk = self._conv(pl, "trimap.model.KV_Q_r4.Key", r4, "q_key", pad=1)
+        self._conv(pl, "trimap.model.KV_Q_r4.Value", r4, out=m4in[..., DO:], pad=1)
+        M = bank.T * bank.hw
+        ws_bytes = ops.memory_read_workspace(self.bank_capacity * bank.hw, h * w, DE, DO, self.dtype)
+        ws = pl.buf("read_ws", (ws_bytes // 4,), torch.float32)
+        ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws)
+        return self._stm_decoder(pl, m4in, r3, r2)
+
+    def _stm_decoder(self, pl, m4in, r3, r2):
+        d = "trimap.model.Decoder"
+        N, h, w, _ = m4in.shape
+        x0 = pl.buf("dec.x0", (1, h, w, 256)); x0r = pl.buf("dec.x0r", (1, h, w, 256))
+        self._conv(pl, d + ".convFM", m4in, out=x0, pad=1, out_relu=x0r)
+        m, _ = self._resblock(pl, d + ".ResMM", x0, x0r, out_name="dec.m4")
+        for rf, f in (("RF3", r3), ("RF2", r2)):
+            N, H, W, _ = f.shape
+            s0 = pl.buf(f"dec.{rf}.s0", (1, H, W, 256)); s0r = pl.buf(f"dec.{rf}.s0r", (1, H, W, 256))
+            self._conv(pl, f"{d}.{rf}.convFS", f, out=s0, pad=1, out_relu=s0r)
+            s, _ = self._resblock(pl, f"{d}.{rf}.ResFS", s0, s0r, out_name=f"dec.{rf}.s")
+            mmr = pl.buf(f"dec.{rf}.mmr", (1, H, W, 256))
+            mm = ops.upsample(m, pl.buf(f"dec.{rf}.mm", (1, H, W, 256)), add=s, out_relu=mmr)     # STM.py:115
+            # the last block's output is only read through F.relu (STM.py:134) -> fold it into the epilogue
+            m, _ = self._resblock(pl, f"{d}.{rf}.ResMM", mm, mmr, out_name=f"dec.{rf}.m", final_relu=rf == "RF2")
+        N, H, W, _ = m.shape
+        p2 = pl.buf("dec.p2", (1, H, W, 4), torch.float32, zero=True)
+        self._conv(pl, d + ".pred", m, out=p2[..., :3], pad=1)                        # relu(m2) applied above
+        logits = pl.buf("seg_logits", (1, pl.Hp, pl.Wp, 4), torch.float32, zero=True)
+        ops.upsample(p2[..., :3], logits[..., :3])                                    # STM.py:136
+        return logits
+
+    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int):
+        """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``."""
+        mem_in = pl.bufs["mem_in"]
+        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in)
+        N, h, w, _ = r4.shape
+        kdst = bank.key_slot(slot).view(1, h, w, DE)
+        self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1)
+        vdst = bank.vals[:, slot * bank.hw:]
+        self._conv(pl, "trimap.model.KV_M_r4.Value", r4, out=vdst, pad=1, out_strides=(1, bank.vals.shape[1]))
+
+    # ---- FBA ---------------------------------------------------------------------------------------
+    def matting(self, pl: FramePlan):
+        """x11 / cat4[64:72] / extras must be ready.  Produces raw heads, fused outputs and ``hid``."""
+        Hp, Wp = pl.Hp, pl.Wp
+        e = "NET.encoder"
+        x11 = pl.bufs["x11"]
+        cat3 = pl.buf("cat3", (1, Hp // 2, Wp // 2, 320))       # up(conv_up2) | conv_out[-5]
+        cat2 = pl.buf("cat2", (1, Hp // 4, Wp // 4, 512))       # up(conv_up1) | conv_out[-4]
+        cat1 = pl.buf("cat1", (1, Hp // 8, Wp // 8, 3072))      # conv5 | ppm x4
+        c1 = self._ws_gn(pl, e + ".conv1", e + ".bn1", x11, act=ACT_RELU, stride=2, pad=3, out=cat3[..., 256:],
+                         raw_name="enc.stem.raw")
+        x = ops.maxpool3x3s2(c1, pl.buf("enc.pool", (1, Hp // 4, Wp // 4, 64)))
+        cfg = (("layer1", 3, 1, 1, 1, cat2[..., 256:]), ("layer2", 4, 2, 1, 1, None),
+               ("layer3", 6, 1, 1, 2, None), ("layer4", 3, 1, 2, 4, cat1[..., :2048]))
+        for lname, blocks, stride, d0, dd, last_out in cfg:
+            for b in range(blocks):
+                x = self._gn_bottleneck(pl, f"{e}.{lname}.{b}", x, stride if b == 0 else 1, d0 if b == 0 else dd,
+                                        out=last_out if b == blocks - 1 else None)
+        # pyramid pooling (FBA/models.py:357-362)
+        conv5 = x
+        h8, w8 = conv5.shape[1:3]
+        pooled = pl.buf("ppm.pooled", (50, 2048))
+        ops.ppm_pool(conv5, pooled, pl.buf("ppm.rows", (h8 * 12 * 2048,), torch.float32))
+        off = 0
+        for i, s in enumerate((1, 2, 3, 6)):
+            cells = pooled[off:off + s * s].view(1, s, s, 2048); off += s * s
+            y = self._ws_gn(pl, f"NET.decoder.ppm.{i}.1", f"NET.decoder.ppm.{i}.2", cells, act=ACT_LEAKY)
+            ops.upsample(y, cat1[..., 2048 + 256 * i: 2304 + 256 * i])
+        dn = "NET.decoder"
+        x = self._ws_gn(pl, dn + ".conv_up1.0", dn + ".conv_up1.1", cat1, act=ACT_LEAKY, pad=1)
+        x = self._ws_gn(pl, dn + ".conv_up1.3", dn + ".conv_up1.4", x, act=ACT_LEAKY, pad=1)
+        ops.upsample(x, cat2[..., :256])
+        x = self._ws_gn(pl, dn + ".conv_up2.0", dn + ".conv_up2.1", cat2, act=ACT_LEAKY, pad=1)
+        ops.upsample(x, cat3[..., :256])
+        x = self._ws_gn(pl, dn + ".conv_up3.0", dn + ".conv_up3.1", cat3, act=ACT_LEAKY, pad=1)
+        cat4 = pl.bufs["cat4"]                                  # up(conv_up3) | imgn | img | two_chan | alpha | 0
+        ops.upsample(x, cat4[..., :64])
+        x = self._conv(pl, dn + ".conv_up4.0", cat4, pad=1, act=ACT_LEAKY)
+        hid_d = self._conv(pl, dn + ".conv_up4.2", x, pad=1, act=ACT_LEAKY)
+        raw7 = pl.buf("raw7", (1, Hp, Wp, 8), torch.float32, zero=True)
+        self._conv(pl, dn + ".conv_up4.4", hid_d, out=raw7[..., :7])
+        P = Hp * Wp
+        extras = pl.bufs["extras"]
+        out7 = pl.buf("out7", (P, 8), torch.float32)
+        ops.fba_head(raw7, 8, self.dtype, extras, P, out7, cat4[..., 72:73], cat4.stride(2))
+        # refinement (FBA/models.py:417-435)
+        r = "NET.refine"
+        x = self._ws_gn(pl, r + ".conv1.0", r + ".conv1.1", cat4, act=ACT_LEAKY, pad=1)
+        for l in ("layer1", "layer2"):
+            t = self._ws_gn(pl, f"{r}.{l}.conv1", f"{r}.{l}.bn1", x, act=ACT_RELU, pad=1)
+            x = self._ws_gn(pl, f"{r}.{l}.conv2", f"{r}.{l}.bn2", t, act=ACT_RELU, pad=1, res=x)
+        x = self._conv(pl, r + ".pred.0", x, pad=1, act=ACT_LEAKY)
+        hid = self._conv(pl, r + ".pred.2", x, "hid", pad=1, act=ACT_LEAKY)
+        raw10 = pl.buf("raw10", (1, Hp, Wp, 12), torch.float32, zero=True)
+        self._conv(pl, r + ".pred.4", hid, out=raw10[..., :10])
+        fused = pl.buf("fused", (P, 8), torch.float32)
+        ops.fba_head(raw10, 12, self.dtype, extras, P, fused)
+        return dict(raw7=raw7, out7=out7, raw10=raw10, fused=fused, hid=hid, conv5=conv5)
+
+    # ---- one frame (EvalModel.forward with tri=None, tri_gt=None) ------------------------------------
+    def frame(self, a, fg, bg, *, first_frame, last_frame, memorize, max_memory_num, radius, user_tri=None):
+        """a [H*W...] fp32, fg/bg [3,H,W] fp32 BGR 0..255 (device, contiguous).  Returns views of the plan's
+        output buffers: scaled_img [3,H,W], trimap [3,H,W], tri_gt [3,H,W] one-hot, alpha [H,W]."""
+        H, W = a.shape[-2:]
+        pl = self.plan(H, W)
+        bank = self.bank(pl)
+        Hp, Wp, P = pl.Hp, pl.Wp, pl.Hp * pl.Wp
+        f32 = torch.float32
+        img = pl.buf("img", (P, 4), f32)
+        scaled = pl.buf("scaled_img", (3, H, W), f32)
+        tri3 = pl.buf("tri3", (P, 4), f32)
+        imgn = pl.buf("imgn", (1, Hp, Wp, 4))
+        ops.preprocess(a, fg, bg, H, W, Hp, Wp, pl.pad_top, pl.pad_left, radius, self.w.ms_q, img, scaled, tri3, imgn,
+                       pl.buf("pre_scratch", (2 * H * W,), torch.uint8))
+        x11 = pl.buf("x11", (1, Hp, Wp, 16))
+        cat4 = pl.buf("cat4", (1, Hp, Wp, 80), zero=True)
+        extras = pl.buf("extras", (P, 8), f32)
+        d2 = pl.buf("d2", (2, P), torch.int32)
+        enc_args = (img, Hp, Wp, self.w.ms_alpha, x11, cat4[..., 64:72], extras, d2,
+                    pl.buf("edt_scratch", (2, P), torch.int32), pl.buf("seeds", (2, P), torch.uint8))
+        if first_frame:
+            bank.reset()
+            tri_first = tri3
+            if user_tri is not None:         # user / GT trimap for frame 0 (:395-401); padding = bg (:409-410)
+                tri_first = pl.buf("tri_user", (Hp, Wp, 4), f32)
+                tri_first.zero_(); tri_first[..., 0] = 1.0
+                tri_first[pl.pad_top:pl.pad_top + H, pl.pad_left:pl.pad_left + W, :3] = user_tri.permute(1, 2, 0)
+            ops.trimap_encode(tri_first, 4, False, *enc_args)                   # preds_trimap = tri_ (:429)
+        else:
+            logits = self.segment(pl, bank)
+            ops.trimap_encode(logits, 4, True, *enc_args)                       # softmax + make_trimap (:440-442)
+        net = self.matting(pl)
+        alpha = pl.buf("alpha_out", (H, W), f32)
+        trimap = pl.buf("trimap_out", (3, H, W), f32)
+        slot = None
+        if not last_frame:
+            slot, order = bank.next_slot(first_frame, memorize, max_memory_num)
+        mem_in = pl.buf("mem_in", (1, Hp, Wp, 24)) if slot is not None else None
+        ops.frame_outputs(net["raw10"], 12, net["fused"], net["hid"], extras, Hp, Wp, H, W, pl.pad_top, pl.pad_left,
+                          self.w.ms_m, mem_in, alpha, trimap)
+        if slot is not None:
+            self.memorize(pl, bank, slot)
+            bank.order = order
+        return scaled, trimap, tri3, alpha

@@ -1,0 +1,187 @@
+"""Thin tensor-level wrappers over the C ABI (``include/otvm_b200.h``).
+
+Activations are NHWC torch tensors ``[N, H, W, C]`` that may be channel slices of a wider buffer
+(``stride(2)`` is the per-pixel leading dimension).  Every wrapper launches on torch's current CUDA
+stream and raises :class:`otvm_b200._lib.OtvmError` on failure.  No wrapper computes anything in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, F32, ConvParams, ReadParams, check  # noqa: F401
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ld(t: torch.Tensor) -> int:
+    """per-pixel leading dimension of an NHWC tensor (possibly a channel slice)"""
+    assert t.dim() == 4 and t.stride(3) == 1, (t.shape, t.stride())
+    ld = t.stride(2)
+    assert t.shape[1] == 1 or t.stride(1) == t.shape[2] * ld
+    assert t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.shape[2] * ld
+    return ld
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=False, res=None, out_relu=None,
+           gn_stats=None, out_strides=None, cin=None):
+    """x [N,H,W,Cin(view)], w [Cout,KH,KW,Cin] packed, out NHWC view (or any buffer with ``out_strides`` =
+    (pixel_stride, channel_stride) in elements, used for the channel-major value bank)."""
+    lib = _lib.load()
+    N, H, W, Cx = x.shape
+    Cout, KH, KW, Cin = w.shape
+    assert (cin or Cx) == Cin, (x.shape, w.shape)
+    p = ConvParams()
+    p.inp, p.in_ld = x.data_ptr(), _ld(x)
+    p.N, p.H, p.W, p.Cin = N, H, W, Cin
+    p.weight, p.bias = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
+    p.Cout, p.KH, p.KW, p.stride, p.pad, p.dil = Cout, KH, KW, stride, pad, dil
+    p.out = out.data_ptr()
+    if out_strides is None:
+        p.out_ps, p.out_cs = _ld(out), 1
+    else:
+        p.out_ps, p.out_cs = out_strides
+    p.res, p.res_ld = (res.data_ptr(), _ld(res)) if res is not None else (None, 0)
+    p.out_relu, p.out_relu_ld = (out_relu.data_ptr(), _ld(out_relu)) if out_relu is not None else (None, 0)
+    p.act, p.relu_in, p.dtype = act, int(relu_in), _DT[x.dtype]
+    p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
+    p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    assert w.dtype == x.dtype and (bias is None or bias.dtype == torch.float32)
+    check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d")
+    return out
+
+
+def gn_stats(x, stats):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    check(lib.otvm_gn_stats(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _stream()), "otvm_gn_stats")
+
+
+def gn_apply(x, stats, gamma, beta, out, *, act=ACT_NONE, res=None, eps=1e-5):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    check(lib.otvm_gn_apply(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _p(gamma), _p(beta), eps,
+                            _p(res), _ld(res) if res is not None else 0, act, _p(out), _ld(out), _stream()),
+          "otvm_gn_apply")
+    return out
+
+
+def upsample(x, out, *, add=None, out_relu=None, out_nchw_f32=False):
+    """bilinear, align_corners=False.  ``out`` is NHWC [N,Ho,Wo,C] with the dtype of ``x``; when C is not a
+    multiple of 4 (the 3 STM logits) ``x`` and ``out`` are fp32 and ``out`` may instead be NCHW planes
+    [C,Ho,Wo] (``out_nchw_f32``)."""
+    lib = _lib.load()
+    N, Hi, Wi, Cc = x.shape
+    if out_nchw_f32:
+        Ho, Wo = out.shape[-2:]
+        old = 0
+    else:
+        Ho, Wo = out.shape[1:3]
+        old = _ld(out)
+    if Cc % 4 or out_nchw_f32:
+        assert out.dtype == torch.float32 and add is None
+    check(lib.otvm_upsample_bilinear(_p(x), _ld(x), N, Hi, Wi, Cc, Ho, Wo, _p(add),
+                                     _ld(add) if add is not None else 0, _p(out), old, _p(out_relu),
+                                     _ld(out_relu) if out_relu is not None else 0, _DT[x.dtype],
+                                     int(out_nchw_f32), _stream()), "otvm_upsample_bilinear")
+    return out
+
+
+def maxpool3x3s2(x, out):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    check(lib.otvm_maxpool3x3s2(_p(x), _ld(x), N, H, W, Cc, _p(out), _ld(out), _DT[x.dtype], _stream()),
+          "otvm_maxpool3x3s2")
+    return out
+
+
+def ppm_pool(x, out, scratch):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    check(lib.otvm_ppm_pool(_p(x), _ld(x), N, H, W, Cc, _p(out), _p(scratch), _DT[x.dtype], _stream()),
+          "otvm_ppm_pool")
+    return out
+
+
+def memory_read_workspace(M, HW, De, Do, dtype):
+    return int(_lib.load().otvm_memory_read_workspace(M, HW, De, Do, _DT[dtype]))
+
+
+def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
+    """keys [>=M, De] rows; vals [Do, ldv] channel-major; query NHWC view with De channels; out NHWC view with
+    Do channels (a slice of the 2*Do decoder input)."""
+    lib = _lib.load()
+    p = ReadParams()
+    De, Do = keys.shape[-1], vals.shape[0]
+    HW = query.shape[1] * query.shape[2]
+    p.keys, p.vals, p.ldv = keys.data_ptr(), vals.data_ptr(), ldv
+    p.query, p.q_ld = query.data_ptr(), _ld(query)
+    p.out, p.out_ld = out.data_ptr(), _ld(out)
+    p.M, p.HW, p.De, p.Do = M, HW, De, Do
+    p.dtype = _DT[keys.dtype]
+    p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    p.force_simt = int(force_simt)
+    check(lib.otvm_memory_read(C.byref(p), _stream()), "otvm_memory_read")
+    return out
+
+
+def preprocess(a, fg, bg, H, W, Hp, Wp, pad_top, pad_left, radius, mean_std, img, scaled_img, tri3, imgn, scratch):
+    lib = _lib.load()
+    ms = (C.c_float * 6)(*mean_std)
+    check(lib.otvm_preprocess(_p(a), _p(fg), _p(bg), H, W, Hp, Wp, pad_top, pad_left, radius, ms, _p(img),
+                              _p(scaled_img), _p(tri3), _p(imgn), _ld(imgn), _DT[imgn.dtype], _p(scratch),
+                              _stream()), "otvm_preprocess")
+
+
+def trimap_encode(tri, tri_ld, is_logit, img, Hp, Wp, mean_std, x11, cat_dst, extras, d2, scratch, seeds):
+    lib = _lib.load()
+    ms = (C.c_float * 6)(*mean_std)
+    check(lib.otvm_trimap_encode(_p(tri), tri_ld, int(is_logit), _p(img), Hp, Wp, ms, _p(x11), _ld(x11),
+                                 _p(cat_dst), _ld(cat_dst) if cat_dst is not None else 0, _DT[x11.dtype],
+                                 _p(extras), _p(d2), _p(scratch), _p(seeds), _stream()), "otvm_trimap_encode")
+
+
+def edt_sq(seed, d2, scratch):
+    lib = _lib.load()
+    H, W = seed.shape
+    check(lib.otvm_edt_sq(_p(seed), H, W, _p(d2), _p(scratch), _stream()), "otvm_edt_sq")
+    return d2
+
+
+def fba_head(raw, raw_ld, dtype, extras, P, out7, alpha_dst=None, alpha_ld=0):
+    lib = _lib.load()
+    check(lib.otvm_fba_head(_p(raw), raw_ld, _DT[dtype], int(raw.dtype == torch.float32), _p(extras), P, _p(out7),
+                            _p(alpha_dst), alpha_ld, _stream()), "otvm_fba_head")
+
+
+def frame_outputs(raw10, raw_ld, fused, hid, extras, Hp, Wp, H, W, pad_top, pad_left, mean_std, mem_in,
+                  alpha_out, trimap_out):
+    lib = _lib.load()
+    ms = (C.c_float * 6)(*mean_std)
+    check(lib.otvm_frame_outputs(_p(raw10), raw_ld, _p(fused), _p(hid), _ld(hid), _p(extras), Hp, Wp, H, W,
+                                 pad_top, pad_left, ms, _p(mem_in), _ld(mem_in) if mem_in is not None else 0,
+                                 _DT[hid.dtype], _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs")
+
+
+def nchw_to_nhwc(x, out):
+    lib = _lib.load()
+    N, Cc, H, W = x.shape
+    check(lib.otvm_nchw_to_nhwc(_p(x), N, Cc, H * W, _p(out), _ld(out), _DT[out.dtype], _stream()), "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x, out):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    check(lib.otvm_nhwc_to_nchw(_p(x), _ld(x), N, Cc, H * W, _p(out), _DT[x.dtype], _stream()), "nhwc_to_nchw")
+    return out

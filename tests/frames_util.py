@@ -1,0 +1,91 @@
+"""Run the oracle (CPU) and the B200 engine side by side on the synthetic clip and collect per-stage errors."""
+import os
+import sys
+import types
+
+import torch
+
+from util import ROOT, rel_err
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def build_model(kind, precision, radius=12, capacity=16):
+    import otvm_b200
+    from otvm_b200.fixtures import make_state_dict
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4))
+    os.environ["OTVM_BANK_CAPACITY"] = str(capacity)
+    mt = otvm_b200.get_model_trimap(cfg, "Test", radius)
+    ma = otvm_b200.get_model_alpha(cfg, mt, "Test", radius)
+    sd = make_state_dict(kind)
+    ma.load_state_dict(sd)
+    return ma.cuda().eval().set_precision(precision), sd
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).cpu()
+
+
+def force_bank(model, oracle, H, W):
+    """teacher forcing: overwrite the engine's bank with the oracle's (logical order == physical order)"""
+    eng = model.engine
+    pl = eng.plan(H, W)
+    bank = eng.bank(pl)
+    key, val = oracle.memories["key"][0, 0], oracle.memories["val"][0, 0]       # [C,T,h,w]
+    T = key.shape[1]
+    bank.keys[:T * bank.hw] = key.permute(1, 2, 3, 0).reshape(T * bank.hw, -1).to(bank.keys)
+    bank.vals[:, :T * bank.hw] = val.reshape(val.shape[0], T * bank.hw).to(bank.vals)
+    bank.order = list(range(T))
+
+
+def compare_frame(model, oracle, out, ref, H, W, first):
+    """dict stage -> scale-relative max error for the frame just run by both"""
+    eng = model.engine
+    pl = eng.plan(H, W)
+    b, tr = pl.bufs, oracle.trace
+    Hp, Wp = pl.Hp, pl.Wp
+    e = {}
+    if not first:
+        e["seg_logit"] = rel_err(nchw(b["seg_logits"][..., :3]), tr_pad(tr["seg_logit"], Hp, Wp))
+        e["read_mem"] = rel_err(nchw(b["m4in"]), tr["m4"])
+        e["q_key"] = rel_err(nchw(b["q_key"]), tr["k4"])
+    e["tri8"] = rel_err(nchw(b["x11"][..., 3:11]), tr["tri8"])
+    e["conv5"] = rel_err(nchw(b["cat1"][..., :2048]), tr["conv5"])
+    e["raw_decoder"] = rel_err(nchw(b["raw7"][..., :7]), tr["raw_decoder"])
+    e["dec_fused"] = rel_err(b["out7"].view(1, Hp, Wp, 8)[..., :7].permute(0, 3, 1, 2).cpu(), tr["output"])
+    e["raw_refine"] = rel_err(nchw(b["raw10"][..., :10]), tr["raw_refine"])
+    e["hid"] = rel_err(nchw(b["hid"]), tr["hid"])
+    e["refine_fused"] = rel_err(b["fused"].view(1, Hp, Wp, 8)[..., :7].permute(0, 3, 1, 2).cpu(), tr["refine_output"])
+    bank = eng.bank(pl)
+    s = bank.order[-1]
+    h, w = Hp // 16, Wp // 16
+    e["mem_key"] = rel_err(bank.key_slot(s).float().cpu().view(h, w, -1).permute(2, 0, 1), tr["mem_k"][0, :, 0])
+    e["mem_val"] = rel_err(bank.vals[:, s * bank.hw:(s + 1) * bank.hw].float().cpu().view(-1, h, w), tr["mem_v"][0, :, 0])
+    e["alpha"] = rel_err(out[3].cpu(), ref[3])
+    e["trimap"] = rel_err(out[1].cpu(), ref[1])
+    e["scaled_img"] = rel_err(out[0].cpu(), ref[0])
+    e["tri_gt"] = rel_err(out[2].cpu(), ref[2])
+    return e
+
+
+def tr_pad(x, Hp, Wp):
+    assert x.shape[-2:] == (Hp, Wp), "seg_logit trace is compared on sizes that need no pad-16 crop"
+    return x
+
+
+def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=True):
+    import otvm_oracle as O
+    from otvm_b200.fixtures import make_frame
+    model, sd = build_model(kind, precision)
+    oracle = O.OracleEvalModel(sd, dilate_kernel=12)
+    rows = []
+    for i in range(n_frames):
+        a, fg, bg = make_frame(0, i, H, W)
+        kw = dict(first_frame=(i == 0), last_frame=False, memorize=memorize, max_memory_num=max_mem)
+        ref = oracle(a, fg, bg, **kw)
+        out = model(a.cuda(), fg.cuda(), bg.cuda(), **kw)
+        torch.cuda.synchronize()
+        rows.append(compare_frame(model, oracle, out, ref, H, W, i == 0))
+        if teacher:
+            force_bank(model, oracle, H, W)
+    return rows

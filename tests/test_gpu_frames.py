@@ -1,0 +1,36 @@
+"""Frame-level parity of the B200 engine (through EvalModel.forward -> C ABI) against the oracle."""
+import pytest
+import torch
+
+from frames_util import run_clip
+from util import golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# north star: 1e-3 (fp32) on trimap logits and alpha matte; every compared tensor is held to it.
+FP32_TOL = 1e-3
+
+
+@pytest.mark.parametrize("kind,H,W", [("tempered", 128, 128), ("default", 128, 128), ("tempered", 120, 152)])
+def test_fp32_frames_teacher_forced(kind, H, W):
+    rows = run_clip(kind, "fp32", H, W, 3, max_mem=2 if H == 120 else 8)
+    for i, e in enumerate(rows):
+        for k, v in e.items():
+            assert v < FP32_TOL, (i, k, v, e)
+
+
+def test_fp32_free_running_matches_reference_golden():
+    """no teacher forcing: 3 frames at 256x256 against the REFERENCE's outputs (tests/golden)"""
+    import types, os
+    from frames_util import build_model
+    from otvm_b200.fixtures import make_frame
+    g = golden("clip_tempered_256")
+    model, _ = build_model("tempered", "fp32")
+    for i in range(3):
+        a, fg, bg = make_frame(0, i, 256, 256)
+        out = model(a.cuda(), fg.cuda(), bg.cuda(), first_frame=(i == 0), last_frame=False, memorize=True, max_memory_num=8)
+        assert rel_err(out[3][0, 0, 0].cpu(), g[f"f{i}_alpha"]) < 5e-3 * (i + 1)     # recurrent drift, see DESIGN.md
+        assert rel_err(out[1][0, 0].cpu(), g[f"f{i}_trimap"]) < 5e-3 * (i + 1)
+        b = model.engine.plan(256, 256).bufs
+        if i > 0:
+            assert rel_err(b["seg_logits"][0, ::2, ::2, :3].permute(2, 0, 1).cpu(), g[f"f{i}_seg_logit"]) < FP32_TOL * (i + 1)

@@ -1,0 +1,259 @@
+"""Kernel-level parity (through the C ABI) against plain PyTorch fp32 ops / the oracle, on the GPU.
+
+Tolerances are scale-relative max errors (tests/util.py:rel_err): 1e-4 for the strict fp32 kernels (pure
+re-association noise), 1e-2 for bf16 storage with fp32 accumulation, compared against the SAME op evaluated in
+fp32 on the bf16-rounded inputs; integer outputs (EDT, trimap classes) are bit-exact.
+"""
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import ROOT, rel_err
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+DTYPES = [torch.float32, torch.bfloat16]
+
+
+def _ops():
+    from otvm_b200 import ops
+    return ops
+
+
+def nhwc(x, dtype, ld=None):
+    """NCHW fp32 cpu -> NHWC device tensor (optionally a channel slice of a wider buffer)."""
+    N, C, H, W = x.shape
+    ld = ld or C
+    buf = torch.zeros(N, H, W, ld, dtype=dtype, device=DEV)
+    buf[..., :C] = x.permute(0, 2, 3, 1).to(DEV, dtype)
+    return buf[..., :C]
+
+
+def nchw(x):
+    return x.float().permute(0, 3, 1, 2).cpu()
+
+
+def rnd(dtype, x):
+    return x.to(dtype).float()
+
+
+CONV_CASES = [
+    # Cin, Cout, k, stride, pad, dil, H, W
+    (64, 64, 1, 1, 0, 1, 16, 16),
+    (64, 256, 3, 1, 1, 1, 16, 24),
+    (128, 128, 3, 2, 1, 1, 16, 16),
+    (256, 512, 1, 2, 0, 1, 16, 16),
+    (256, 256, 3, 1, 2, 2, 16, 16),
+    (512, 512, 3, 1, 4, 4, 8, 8),
+    (3, 64, 7, 2, 3, 1, 32, 32),
+    (22, 64, 7, 2, 3, 1, 32, 40),
+    (80, 32, 3, 1, 1, 1, 16, 16),
+    (16, 7, 1, 1, 0, 1, 8, 8),
+    (256, 3, 3, 1, 1, 1, 8, 8),
+    (2048, 256, 1, 1, 0, 1, 2, 2),
+    (1024, 128, 3, 1, 1, 1, 8, 8),
+    (320, 64, 3, 1, 1, 1, 20, 12),
+]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d(case, dtype):
+    ops = _ops()
+    Cin, Cout, k, s, p, d, H, W = case
+    g = torch.Generator().manual_seed(hash(case) & 0xFFFF)
+    x = torch.randn(1, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(rnd(dtype, x), rnd(dtype, w), b, s, p, d)
+    res = torch.randn_like(want)
+    want_res = F.leaky_relu(want + rnd(dtype, res), 0.01)
+    xd = nhwc(x, dtype, ld=Cin + 8 if Cin % 4 == 0 else None)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    bd = b.to(DEV)
+    Ho, Wo = want.shape[2:]
+    out = torch.zeros(1, Ho, Wo, Cout + 4, dtype=dtype, device=DEV)[..., :Cout] if Cout % 4 == 0 else \
+        torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    ops.conv2d(xd, wd, bd, out, stride=s, pad=p, dil=d)
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    # fused epilogue: residual + LeakyReLU + ReLU'd second output
+    out2 = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    outr = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    ops.conv2d(xd, wd, bd, out2, stride=s, pad=p, dil=d, res=nhwc(res, dtype), act=ops.ACT_LEAKY, out_relu=outr)
+    assert rel_err(nchw(out2), want_res) < TOL[dtype]
+    assert rel_err(nchw(outr), F.relu(want_res)) < TOL[dtype]
+    # relu on the input (STM ResBlock)
+    out3 = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    ops.conv2d(xd, wd, bd, out3, stride=s, pad=p, dil=d, relu_in=True, act=ops.ACT_RELU)
+    assert rel_err(nchw(out3), F.relu(F.conv2d(F.relu(rnd(dtype, x)), rnd(dtype, w), b, s, p, d))) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_conv2d_channel_major_out_and_f32_head(dtype):
+    """value-bank store (out[c*ldv + p]) and the fp32 head output used for the 7/10-channel predictions"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, 64, 8, 8, generator=g); w = torch.randn(32, 64, 3, 3, generator=g) / 24; b = torch.randn(32, generator=g)
+    want = F.conv2d(rnd(dtype, x), rnd(dtype, w), b, 1, 1)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    bank = torch.zeros(32, 3 * 64, dtype=dtype, device=DEV)
+    ops.conv2d(nhwc(x, dtype), wd, b.to(DEV), bank[:, 64:], pad=1, out_strides=(1, bank.shape[1]))
+    assert rel_err(bank[:, 64:128].float().cpu().view(32, 8, 8), want[0]) < TOL[dtype]
+    assert float(bank[:, :64].abs().max()) == 0 and float(bank[:, 128:].abs().max()) == 0
+    o32 = torch.zeros(1, 8, 8, 36, dtype=torch.float32, device=DEV)
+    ops.conv2d(nhwc(x, dtype), wd, b.to(DEV), o32[..., :32], pad=1)
+    assert rel_err(nchw(o32[..., :32]), want) < (1e-4 if dtype == torch.float32 else 2e-3)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,H,W", [(64, 32, 32), (256, 16, 8), (2048, 8, 8), (256, 1, 1), (256, 3, 3), (128, 5, 7)])
+def test_groupnorm(C, H, W, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(1, C, H, W, generator=g) * 3 + 1.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    res = torch.randn(1, C, H, W, generator=g)
+    want = F.relu(F.group_norm(rnd(dtype, x), 32, gamma, beta, 1e-5) + rnd(dtype, res))
+    xd = nhwc(x, dtype)
+    stats = torch.zeros(64, dtype=torch.float64, device=DEV)
+    ops.gn_stats(xd, stats)
+    xr = rnd(dtype, x).double().view(32, -1)
+    assert rel_err(stats.cpu().view(32, 2)[:, 0], xr.sum(1)) < 1e-5
+    assert rel_err(stats.cpu().view(32, 2)[:, 1], (xr * xr).sum(1)) < 1e-5
+    out = torch.zeros_like(xd)
+    ops.gn_apply(xd, stats, gamma.to(DEV), beta.to(DEV), out, act=ops.ACT_RELU, res=nhwc(res, dtype))
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    # statistics fused into the conv epilogue must agree with the stand-alone pass
+    w = torch.randn(C, 64, 1, 1, generator=g) / 8
+    xin = torch.randn(1, 64, H, W, generator=g)
+    raw = torch.zeros(1, H, W, C, dtype=dtype, device=DEV)
+    st2 = torch.zeros(64, dtype=torch.float64, device=DEV)
+    ops.conv2d(nhwc(xin, dtype), w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype), None, raw, gn_stats=st2)
+    ops.gn_stats(raw, stats)
+    assert rel_err(st2.cpu(), stats.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("C,Hi,Wi,Ho,Wo", [(256, 8, 8, 16, 16), (64, 16, 12, 32, 24), (256, 1, 1, 8, 8),
+                                           (256, 2, 2, 8, 12), (256, 3, 3, 8, 8), (256, 6, 6, 16, 16)])
+def test_upsample_bilinear(C, Hi, Wi, Ho, Wo, dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(Hi * Wo)
+    x = torch.randn(1, C, Hi, Wi, generator=g); add = torch.randn(1, C, Ho, Wo, generator=g)
+    want = rnd(dtype, add) + F.interpolate(rnd(dtype, x), size=(Ho, Wo), mode="bilinear", align_corners=False)
+    out = torch.zeros(1, Ho, Wo, C + 64, dtype=dtype, device=DEV)[..., 64:]
+    outr = torch.zeros(1, Ho, Wo, C, dtype=dtype, device=DEV)
+    ops.upsample(nhwc(x, dtype), out, add=nhwc(add, dtype), out_relu=outr)
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    assert rel_err(nchw(outr), F.relu(want)) < TOL[dtype]
+
+
+def test_upsample_logits_x4_fp32():
+    ops = _ops()
+    x = torch.randn(1, 3, 16, 20)
+    want = F.interpolate(x, scale_factor=4, mode="bilinear", align_corners=False)
+    xd = torch.zeros(1, 16, 20, 4, device=DEV); xd[..., :3] = x.permute(0, 2, 3, 1).to(DEV)
+    out = torch.zeros(1, 64, 80, 4, device=DEV)
+    ops.upsample(xd[..., :3], out[..., :3])
+    assert rel_err(nchw(out[..., :3]), want) < 1e-6
+    planes = torch.zeros(3, 64, 80, device=DEV)
+    ops.upsample(xd[..., :3], planes, out_nchw_f32=True)
+    assert rel_err(planes.cpu(), want[0]) < 1e-6
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_maxpool_and_ppm(dtype):
+    ops = _ops()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 64, 18, 22, generator=g)
+    out = torch.zeros(1, 9, 11, 64, dtype=dtype, device=DEV)
+    ops.maxpool3x3s2(nhwc(x, dtype, ld=80), out)
+    assert rel_err(nchw(out), F.max_pool2d(rnd(dtype, x), 3, 2, 1)) == 0
+    for H, W in ((8, 8), (16, 12), (64, 64), (5, 9)):
+        f = torch.randn(1, 128, H, W, generator=g)
+        pooled = torch.zeros(50, 128, dtype=dtype, device=DEV)
+        ops.ppm_pool(nhwc(f, dtype), pooled, torch.zeros(H * 12 * 128, device=DEV))
+        off = 0
+        for s in (1, 2, 3, 6):
+            want = F.adaptive_avg_pool2d(rnd(dtype, f), s)[0].reshape(128, s * s).t()
+            assert rel_err(pooled[off:off + s * s].float().cpu(), want) < TOL[dtype], (H, W, s)
+            off += s * s
+
+
+def test_edt_bit_exact():
+    import otvm_oracle as O
+    ops = _ops()
+    r = np.random.RandomState(0)
+    for (H, W), p in (((37, 53), 0.02), ((64, 64), 0.3), ((5, 90), 0.5), ((128, 96), 0.0005), ((33, 31), 0.0)):
+        seed = (r.uniform(size=(H, W)) < p)
+        if p > 0:
+            seed[r.randint(H), r.randint(W)] = True
+        d2 = torch.zeros(H, W, dtype=torch.int32, device=DEV)
+        ops.edt_sq(torch.from_numpy(seed.astype(np.uint8)).to(DEV), d2, torch.zeros(H, W, dtype=torch.int32, device=DEV))
+        got = d2.cpu().numpy()
+        if seed.any():
+            assert np.array_equal(got.astype(np.int64), O.edt_sq(~seed))
+        else:
+            assert (got == 0x3fffffff).all()
+
+
+MEM_CASES = [(1, 4, 4, 1.0), (3, 6, 5, 1.0), (2, 8, 8, 6.0), (5, 7, 9, 0.3), (8, 16, 16, 2.0), (3, 12, 20, 3.0)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("simt", [True, False])
+@pytest.mark.parametrize("case", MEM_CASES)
+def test_memory_read(case, simt, dtype):
+    """Memory.forward (STM.py:144-163) on random banks, incl. sharp (scale 6) and flat softmaxes, ragged sizes"""
+    import otvm_oracle as O
+    ops = _ops()
+    T, h, w, sc = case
+    r = np.random.RandomState(T * 100 + h)
+    t = lambda *s: torch.from_numpy(r.standard_normal(s).astype(np.float32))
+    m_in, m_out = t(1, 128, T, h, w) * sc, t(1, 512, T, h, w)
+    q_in, q_out = t(1, 128, h, w) * sc, t(1, 512, h, w)
+    want = O.memory_read(rnd(dtype, m_in), rnd(dtype, m_out), rnd(dtype, q_in), rnd(dtype, q_out))
+    hw, cap = h * w, T + 2
+    keys = torch.zeros(cap * hw, 128, dtype=dtype, device=DEV)
+    vals = torch.zeros(512, cap * hw, dtype=dtype, device=DEV)
+    keys[:T * hw] = m_in[0].permute(1, 2, 3, 0).reshape(T * hw, 128).to(DEV, dtype)
+    vals[:, :T * hw] = m_out[0].reshape(512, T * hw).to(DEV, dtype)
+    q = nhwc(q_in, dtype)
+    out = torch.zeros(1, h, w, 1024, dtype=dtype, device=DEV)
+    out[..., 512:] = q_out.permute(0, 2, 3, 1).to(DEV, dtype)
+    ws = torch.zeros(ops.memory_read_workspace(cap * hw, hw, 128, 512, dtype) // 4 + 1, device=DEV)
+    ops.memory_read(keys, vals, vals.shape[1], q, out[..., :512], T * hw, ws, force_simt=simt)
+    tol = 1e-4 if dtype == torch.float32 else 2e-2        # bf16: P is rounded to bf16 before P.V on tensor cores
+    assert rel_err(nchw(out), want) < tol
+
+
+def test_memory_read_golden_vectors():
+    """the reference's own Memory.forward outputs (tests/golden/memory_read.npz)"""
+    from util import golden
+    ops = _ops()
+    g = golden("memory_read")
+    ci = 0
+    while f"c{ci}_out" in g:
+        T, h, w = (int(v) for v in g[f"c{ci}_shape"])
+        sc = float(g[f"c{ci}_scale"])
+        r = np.random.RandomState(1000 + ci)
+        t = lambda *s: torch.from_numpy(r.standard_normal(s).astype(np.float32))
+        m_in, m_out = t(1, 128, T, h, w) * sc, t(1, 512, T, h, w)
+        q_in, q_out = t(1, 128, h, w) * sc, t(1, 512, h, w)
+        hw = h * w
+        keys = m_in[0].permute(1, 2, 3, 0).reshape(T * hw, 128).contiguous().to(DEV)
+        vals = m_out[0].reshape(512, T * hw).contiguous().to(DEV)
+        out = torch.zeros(1, h, w, 512, device=DEV)
+        ws = torch.zeros(ops.memory_read_workspace(T * hw, hw, 128, 512, torch.float32) // 4 + 1, device=DEV)
+        ops.memory_read(keys, vals, T * hw, nhwc(q_in, torch.float32), out, T * hw, ws)
+        assert rel_err(nchw(out)[0], g[f"c{ci}_out"][:512]) < 1e-4, ci
+        ci += 1
+    assert ci == 5
