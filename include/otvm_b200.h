@@ -41,6 +41,8 @@ OTVM_API int otvm_version(void);
 OTVM_API const char* otvm_strerror(int code);
 /* last CUDA error string seen by this library on the calling thread (for OTVM_ERR_CUDA) */
 OTVM_API const char* otvm_last_cuda_error(void);
+/* number of CUDA kernels this library has launched since it was loaded (all threads) */
+OTVM_API int64_t otvm_launch_count(void);
 /* 1 when the device is compute capability 10.x (tcgen05 / TMA paths usable) */
 OTVM_API int otvm_device_is_sm100(int device);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "otvm_version": (C.c_int, []),
     "otvm_strerror": (C.c_char_p, [C.c_int]),
     "otvm_last_cuda_error": (C.c_char_p, []),
+    "otvm_launch_count": (c_i64, []),
     "otvm_device_is_sm100": (C.c_int, [C.c_int]),
     "otvm_conv2d": (C.c_int, [C.POINTER(ConvParams), c_vp]),
     "otvm_conv2d_uses_tensor_cores": (C.c_int, [C.POINTER(ConvParams)]),

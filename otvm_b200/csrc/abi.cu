@@ -1,5 +1,6 @@
 // C-ABI entry points that dispatch between the FFMA (strict fp32 / fallback) and tcgen05 kernels.
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace otvm {
@@ -11,6 +12,9 @@ void set_cuda_error(cudaError_t e) {
   g_last_error[sizeof(g_last_error) - 1] = 0;
   cudaGetLastError();                          // clear the sticky-less error state
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
   static int n = 0;
@@ -29,7 +33,7 @@ int memory_read_simt(const otvm_read_params* p, cudaStream_t s);
 int memory_read_tc(const otvm_read_params* p, cudaStream_t s);
 bool memory_read_tc_supported(const otvm_read_params* p);
 int64_t memory_read_tc_workspace(int M, int HW, int De, int Do);
-int read_pick_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
+int read_max_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
 
 }  // namespace otvm
 
@@ -49,6 +53,8 @@ extern "C" const char* otvm_strerror(int code) {
 }
 
 extern "C" const char* otvm_last_cuda_error(void) { return g_last_error; }
+
+extern "C" int64_t otvm_launch_count(void) { return (int64_t)g_launches.load(); }
 
 extern "C" int otvm_device_is_sm100(int device) {
   int major = 0;
@@ -80,7 +86,7 @@ extern "C" int otvm_conv2d(const otvm_conv_params* p, void* stream) {
 extern "C" int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype) {
   (void)dtype; (void)De;
   // partial O (fp32) + (m, l) per split; both kernels use at most 64 splits and never more than M/64 blocks
-  int ns_simt = read_pick_splits(M, HW, Do, 64, 128, 64);
+  int ns_simt = read_max_splits(M, HW, Do, 64, 128, 64);
   int64_t ns = ns_simt;
   int64_t tc = memory_read_tc_workspace(M, HW, De, Do);
   int64_t simt = ns * HW * ((int64_t)Do + 2) * (int64_t)sizeof(float);

@@ -17,7 +17,8 @@ void set_cuda_error(cudaError_t e);          // abi.cu: remembers the string for
     if (_e != cudaSuccess) { ::otvm::set_cuda_error(_e); return OTVM_ERR_CUDA; } \
   } while (0)
 
-#define OTVM_LAUNCH_CHECK() OTVM_CUDA_CHECK(cudaGetLastError())
+void count_launch();                         // abi.cu: kernels launched by this library (otvm_launch_count)
+#define OTVM_LAUNCH_CHECK() do { ::otvm::count_launch(); OTVM_CUDA_CHECK(cudaGetLastError()); } while (0)
 
 template <typename T> struct DT;
 template <> struct DT<float> { static constexpr int code = OTVM_F32; };

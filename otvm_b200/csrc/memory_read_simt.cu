@@ -194,6 +194,17 @@ __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* _
   }
 }
 
+// upper bound of read_pick_splits that is monotonic in M (workspace sizing)
+int read_max_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block) {
+  int tiles = ceil_div(HW, rows_per_cta) * ceil_div(Do, cols_per_cta);
+  int nkb = ceil_div(M, keys_per_block);
+  int ns = ceil_div(2 * sm_count(), tiles);
+  if (ns < 1) ns = 1;
+  if (ns > nkb) ns = nkb;
+  if (ns > 64) ns = 64;
+  return ns;
+}
+
 int read_pick_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block) {
   int tiles = ceil_div(HW, rows_per_cta) * ceil_div(Do, cols_per_cta);
   int nkb = ceil_div(M, keys_per_block);

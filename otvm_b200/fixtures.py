@@ -8,9 +8,12 @@ reference does not exist) without shipping 296 MB of weights.
 
 Two kinds (SURVEY.md §7 hard part 1):
 
-* ``"default"``  – He-style fan-in scaling.  Like the reference's own random init this is badly
-  conditioned: the attention logits span several hundred, so the space-time softmax is almost one-hot and
-  the propagated trimap logits are saturated.  fp32-grade arithmetic is needed to track the reference here.
+Both kinds damp the last norm of every residual branch (a random WS+GN ResNet is otherwise chaotic, see the
+comment in ``make_state_dict``).
+
+* ``"default"``  – He-style fan-in scaling.  Like the reference's own random init the attention is badly
+  conditioned: the logits span several hundred, so the space-time softmax is almost one-hot and the
+  propagated trimap logits are saturated.  fp32-grade arithmetic is needed to track the reference here.
 * ``"tempered"`` – identical draws, but the Key projections are scaled so the attention logits are
   O(1..10), the STM prediction head is damped so the propagated trimap is soft, and the alpha heads get a
   0.5 bias so the clamps at ``FBA/models.py:383,426`` do not flatten the matte.  This is the fixture the
@@ -71,7 +74,7 @@ def make_state_dict(kind: str = "tempered", seed: int = 111) -> "OrderedDict[str
                 or (name.startswith("NET.refine.layer") and name.endswith(".bn2.weight"))
             if last and name.startswith("trimap."):
                 v *= np.float32(0.5)                   # keep the un-normalised BN residual stacks bounded
-            if temper and last and name.startswith("NET.") and not name.endswith(".downsample.1.weight"):
+            if last and name.startswith("NET.") and not name.endswith(".downsample.1.weight"):
                 # A random WS+GN ResNet is chaotic: zero-mean standardised weights cancel the mean of the
                 # post-ReLU activations, so relative noise grows ~1.2x per layer (bf16 rounding reaches 40 %
                 # rms at layer4).  Damping the residual branches keeps the amplification near 10x.

@@ -16,6 +16,47 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, F32, ConvParams, ReadPara
 _DT = {torch.float32: F32, torch.bfloat16: BF16}
 
 
+class Profiler:
+    """Optional per-op CUDA-event timing (bench.py): op family -> [events], flops, bytes."""
+
+    def __init__(self):
+        self.spans = {}
+
+    def span(self, key, flops=0.0, nbytes=0.0):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.spans.setdefault(key, []).append((e0, e1, flops, nbytes))
+        return e0, e1
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for k, v in self.spans.items():
+            out[k] = dict(calls=len(v), ms=sum(a.elapsed_time(b) for a, b, _, _ in v),
+                          flops=sum(f for _, _, f, _ in v), bytes=sum(n for _, _, _, n in v))
+        return out
+
+
+PROFILER: "Profiler | None" = None
+
+
+def launch_count() -> int:
+    return int(_lib.load().otvm_launch_count())
+
+
+def _timed(key, fn, flops=0.0, nbytes=0.0):
+    if PROFILER is None:
+        return fn()
+    e0, e1 = PROFILER.span(key, flops, nbytes)
+    e0.record()
+    r = fn()
+    e1.record()
+    return r
+
+
+def _nbytes(*ts):
+    return float(sum(t.shape.numel() * t.element_size() for t in ts if t is not None))
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -57,22 +98,33 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
     assert w.dtype == x.dtype and (bias is None or bias.dtype == torch.float32)
-    check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d")
+    if PROFILER is None:
+        check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d")
+        return out
+    Ho = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
+    Wo = (W + 2 * pad - dil * (KW - 1) - 1) // stride + 1
+    key = "conv_tcgen05" if lib.otvm_conv2d_uses_tensor_cores(C.byref(p)) else "conv_ffma"
+    es = x.element_size()
+    nb = (N * H * W * Cin + Cout * KH * KW * Cin) * es + N * Ho * Wo * Cout * out.element_size()
+    _timed(key, lambda: check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d"),
+           2.0 * N * Ho * Wo * Cout * KH * KW * Cin, float(nb))
     return out
 
 
 def gn_stats(x, stats):
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    check(lib.otvm_gn_stats(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _stream()), "otvm_gn_stats")
+    _timed("gn_stats", lambda: check(lib.otvm_gn_stats(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats),
+                                                       _stream()), "otvm_gn_stats"), nbytes=_nbytes(x))
 
 
 def gn_apply(x, stats, gamma, beta, out, *, act=ACT_NONE, res=None, eps=1e-5):
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    check(lib.otvm_gn_apply(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _p(gamma), _p(beta), eps,
-                            _p(res), _ld(res) if res is not None else 0, act, _p(out), _ld(out), _stream()),
-          "otvm_gn_apply")
+    _timed("gn_apply", lambda: check(
+        lib.otvm_gn_apply(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _p(gamma), _p(beta), eps,
+                          _p(res), _ld(res) if res is not None else 0, act, _p(out), _ld(out), _stream()),
+        "otvm_gn_apply"), nbytes=_nbytes(x, out, res))
     return out
 
 
@@ -90,26 +142,29 @@ def upsample(x, out, *, add=None, out_relu=None, out_nchw_f32=False):
         old = _ld(out)
     if Cc % 4 or out_nchw_f32:
         assert out.dtype == torch.float32 and add is None
-    check(lib.otvm_upsample_bilinear(_p(x), _ld(x), N, Hi, Wi, Cc, Ho, Wo, _p(add),
-                                     _ld(add) if add is not None else 0, _p(out), old, _p(out_relu),
-                                     _ld(out_relu) if out_relu is not None else 0, _DT[x.dtype],
-                                     int(out_nchw_f32), _stream()), "otvm_upsample_bilinear")
+    _timed("upsample", lambda: check(
+        lib.otvm_upsample_bilinear(_p(x), _ld(x), N, Hi, Wi, Cc, Ho, Wo, _p(add),
+                                   _ld(add) if add is not None else 0, _p(out), old, _p(out_relu),
+                                   _ld(out_relu) if out_relu is not None else 0, _DT[x.dtype],
+                                   int(out_nchw_f32), _stream()), "otvm_upsample_bilinear"),
+        nbytes=_nbytes(x, out, add, out_relu))
     return out
 
 
 def maxpool3x3s2(x, out):
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    check(lib.otvm_maxpool3x3s2(_p(x), _ld(x), N, H, W, Cc, _p(out), _ld(out), _DT[x.dtype], _stream()),
-          "otvm_maxpool3x3s2")
+    _timed("maxpool", lambda: check(lib.otvm_maxpool3x3s2(_p(x), _ld(x), N, H, W, Cc, _p(out), _ld(out),
+                                                          _DT[x.dtype], _stream()), "otvm_maxpool3x3s2"),
+           nbytes=_nbytes(x, out))
     return out
 
 
 def ppm_pool(x, out, scratch):
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    check(lib.otvm_ppm_pool(_p(x), _ld(x), N, H, W, Cc, _p(out), _p(scratch), _DT[x.dtype], _stream()),
-          "otvm_ppm_pool")
+    _timed("ppm_pool", lambda: check(lib.otvm_ppm_pool(_p(x), _ld(x), N, H, W, Cc, _p(out), _p(scratch),
+                                                       _DT[x.dtype], _stream()), "otvm_ppm_pool"), nbytes=_nbytes(x))
     return out
 
 
@@ -131,24 +186,28 @@ def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
     p.dtype = _DT[keys.dtype]
     p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     p.force_simt = int(force_simt)
-    check(lib.otvm_memory_read(C.byref(p), _stream()), "otvm_memory_read")
+    es = keys.element_size()
+    _timed("memory_read", lambda: check(lib.otvm_memory_read(C.byref(p), _stream()), "otvm_memory_read"),
+           2.0 * M * HW * (De + Do), float((De + Do) * M * es + De * HW * es + Do * HW * es))
     return out
 
 
 def preprocess(a, fg, bg, H, W, Hp, Wp, pad_top, pad_left, radius, mean_std, img, scaled_img, tri3, imgn, scratch):
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
-    check(lib.otvm_preprocess(_p(a), _p(fg), _p(bg), H, W, Hp, Wp, pad_top, pad_left, radius, ms, _p(img),
-                              _p(scaled_img), _p(tri3), _p(imgn), _ld(imgn), _DT[imgn.dtype], _p(scratch),
-                              _stream()), "otvm_preprocess")
+    _timed("glue", lambda: check(
+        lib.otvm_preprocess(_p(a), _p(fg), _p(bg), H, W, Hp, Wp, pad_top, pad_left, radius, ms, _p(img),
+                            _p(scaled_img), _p(tri3), _p(imgn), _ld(imgn), _DT[imgn.dtype], _p(scratch),
+                            _stream()), "otvm_preprocess"))
 
 
 def trimap_encode(tri, tri_ld, is_logit, img, Hp, Wp, mean_std, x11, cat_dst, extras, d2, scratch, seeds):
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
-    check(lib.otvm_trimap_encode(_p(tri), tri_ld, int(is_logit), _p(img), Hp, Wp, ms, _p(x11), _ld(x11),
-                                 _p(cat_dst), _ld(cat_dst) if cat_dst is not None else 0, _DT[x11.dtype],
-                                 _p(extras), _p(d2), _p(scratch), _p(seeds), _stream()), "otvm_trimap_encode")
+    _timed("trimap_encode_edt", lambda: check(
+        lib.otvm_trimap_encode(_p(tri), tri_ld, int(is_logit), _p(img), Hp, Wp, ms, _p(x11), _ld(x11),
+                               _p(cat_dst), _ld(cat_dst) if cat_dst is not None else 0, _DT[x11.dtype],
+                               _p(extras), _p(d2), _p(scratch), _p(seeds), _stream()), "otvm_trimap_encode"))
 
 
 def edt_sq(seed, d2, scratch):
@@ -160,17 +219,19 @@ def edt_sq(seed, d2, scratch):
 
 def fba_head(raw, raw_ld, dtype, extras, P, out7, alpha_dst=None, alpha_ld=0):
     lib = _lib.load()
-    check(lib.otvm_fba_head(_p(raw), raw_ld, _DT[dtype], int(raw.dtype == torch.float32), _p(extras), P, _p(out7),
-                            _p(alpha_dst), alpha_ld, _stream()), "otvm_fba_head")
+    _timed("glue", lambda: check(
+        lib.otvm_fba_head(_p(raw), raw_ld, _DT[dtype], int(raw.dtype == torch.float32), _p(extras), P, _p(out7),
+                          _p(alpha_dst), alpha_ld, _stream()), "otvm_fba_head"))
 
 
 def frame_outputs(raw10, raw_ld, fused, hid, extras, Hp, Wp, H, W, pad_top, pad_left, mean_std, mem_in,
                   alpha_out, trimap_out):
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
-    check(lib.otvm_frame_outputs(_p(raw10), raw_ld, _p(fused), _p(hid), _ld(hid), _p(extras), Hp, Wp, H, W,
-                                 pad_top, pad_left, ms, _p(mem_in), _ld(mem_in) if mem_in is not None else 0,
-                                 _DT[hid.dtype], _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs")
+    _timed("glue", lambda: check(
+        lib.otvm_frame_outputs(_p(raw10), raw_ld, _p(fused), _p(hid), _ld(hid), _p(extras), Hp, Wp, H, W,
+                               pad_top, pad_left, ms, _p(mem_in), _ld(mem_in) if mem_in is not None else 0,
+                               _DT[hid.dtype], _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs"))
 
 
 def nchw_to_nhwc(x, out):

@@ -8,6 +8,8 @@ import torch
 from util import ROOT, rel_err
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def build_model(kind, precision, radius=12, capacity=16):

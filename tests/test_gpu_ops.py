@@ -257,3 +257,60 @@ def test_memory_read_golden_vectors():
         assert rel_err(nchw(out)[0], g[f"c{ci}_out"][:512]) < 1e-4, ci
         ci += 1
     assert ci == 5
+
+
+TC_CASES = [
+    # Cin, Cout, k, pad, dil, H, W   (stride 1: the tcgen05 implicit-GEMM path)
+    (3072, 256, 3, 1, 1, 32, 32),
+    (64, 64, 3, 1, 1, 96, 128),
+    (96, 64, 3, 1, 1, 64, 64),
+    (96, 32, 3, 1, 1, 40, 72),
+    (32, 16, 3, 1, 1, 64, 64),
+    (16, 10, 1, 0, 1, 64, 64),
+    (2048, 512, 1, 0, 1, 16, 16),
+    (512, 2048, 1, 0, 1, 16, 16),
+    (512, 512, 3, 4, 4, 32, 32),
+    (1024, 512, 3, 1, 1, 32, 32),
+    (256, 256, 3, 1, 1, 20, 36),
+    (128, 128, 3, 1, 1, 9, 13),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv2d_tcgen05(case):
+    """bf16 stride-1 convs must run on the tcgen05 kernel and match fp32 math on the bf16-rounded operands"""
+    ops = _ops()
+    dtype = torch.bfloat16
+    Cin, Cout, k, p, d, H, W = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(1, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(rnd(dtype, x), rnd(dtype, w), b, 1, p, d)
+    res = torch.randn_like(want)
+    want2 = F.relu(want + rnd(dtype, res))
+    xd = nhwc(x, dtype, ld=Cin + 8)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    Ho, Wo = want.shape[2:]
+    head = Cout % 8 != 0
+    out = torch.zeros(1, Ho, Wo, Cout + (0 if head else 8), dtype=torch.float32 if head else dtype, device=DEV)[..., :Cout]
+    outr = None if head else torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    stats = torch.zeros(64, dtype=torch.float64, device=DEV) if Cout % 32 == 0 else None
+    prof = ops.Profiler()
+    ops.PROFILER = prof
+    try:
+        ops.conv2d(xd, wd, b.to(DEV), out, pad=p, dil=d, gn_stats=stats)
+        if not head:
+            out2 = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+            ops.conv2d(xd, wd, b.to(DEV), out2, pad=p, dil=d, res=nhwc(res, dtype), act=ops.ACT_RELU, out_relu=outr)
+    finally:
+        ops.PROFILER = None
+    assert set(prof.summary()) == {"conv_tcgen05"}
+    assert rel_err(nchw(out), want) < (2e-3 if head else 1e-2)
+    if not head:
+        assert rel_err(nchw(out2), want2) < 1e-2
+        assert rel_err(nchw(outr), want2) < 1e-2
+    if stats is not None:
+        q = rnd(dtype, want).double()[0].reshape(32, -1)
+        assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 2e-3
+        assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 2e-3
