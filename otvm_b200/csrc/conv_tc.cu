@@ -9,7 +9,8 @@
 // from it.  Weights [Cout][KH*KW*Cin] are the K-major B operand through a 2-D tensor map.
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / GroupNorm statistics / residual / activation -> global).
+// warps 2..5 = epilogue (TMEM -> registers -> bias / GroupNorm statistics / residual / activation -> swizzled
+// shared-memory tile that reuses the drained pipeline stages -> TMA tensor store, which also clips ragged tiles).
 // Ring of NSTAGE {A,B} stages with full/empty mbarriers; tcgen05.commit releases stages and publishes the
 // accumulator.  Up to two CTAs per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps
 // another's main loop.
@@ -23,6 +24,7 @@ struct ConvTcArgs {
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil;
   int TW, TH, tiles_x, tiles_y;
   int KC, nchunk, nstage;
+  uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
   uint32_t a_bytes, b_bytes, sbo, layout_type;
   const float* bias;
   void* out; int64_t out_ps, out_cs;
@@ -30,26 +32,47 @@ struct ConvTcArgs {
   bf16* out_relu; int64_t out_relu_ld;
   int act, out_f32;
   double* gn_stats;
+  long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
 };
 
 constexpr int kConvThreads = 192;
 
-template <int BN>
+// per-chunk GroupNorm partial sums: CGC consecutive channels form one slot
+template <int CH, int CGC>
+__device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int lane, float* sstat, int slot0) {
+#pragma unroll
+  for (int g = 0; g < CH / CGC; ++g) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CGC; ++j) { const float x = qv[g * CGC + j]; s1 += x; s2 += x * x; }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if (lane == 0) { atomicAdd(&sstat[(slot0 + g) * 2 + 0], s1); atomicAdd(&sstat[(slot0 + g) * 2 + 1], s2); }
+  }
+}
+
+enum { EPI_RES = 1, EPI_RELU2 = 2, EPI_DIRECT = 4 };
+
+template <int BN, bool GN, int EPI>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
+                                                               const __grid_constant__ CUtensorMap tmO,
+                                                               const __grid_constant__ CUtensorMap tmR,
                                                                const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   // carve: [stages x (A|B)] at 1024-byte alignment, then barriers
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t stage_bytes = a.a_bytes + a.b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)a.nstage * stage_bytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.aux_off);
   uint64_t* empty_bar = full_bar + a.nstage;
   uint64_t* accum_bar = empty_bar + a.nstage;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [BN][2] GroupNorm partials (per channel group)
+  float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
+  float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
   // tile coordinates
@@ -68,10 +91,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < 2 * 128; i += kConvThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < BN; i += kConvThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -86,6 +111,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         mbar_arrive_expect_tx(&full_bar[s], a.a_bytes + (uint32_t)(BN * a.KC * 2));
         tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, x0 - a.pad + kx * a.dil, y0 - a.pad + ky * a.dil, n_img);
         tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+        if (dbg && it == 0) dbg[2] = clock64();
       }
     }
   } else if (warp == 1) {
@@ -98,6 +124,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const uint32_t ph = (it / a.nstage) & 1;
         mbar_wait(&full_bar[s], ph);
         tcgen05_after_sync();
+        if (dbg && it == 0) dbg[3] = clock64();
         const uint32_t sa = base + (uint32_t)s * stage_bytes;
         const uint64_t adesc = make_smem_desc(sa, a.sbo, a.layout_type);
         const uint64_t bdesc = make_smem_desc(sa + a.a_bytes, a.sbo, a.layout_type);
@@ -106,105 +133,134 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
       }
       umma_commit(accum_bar);                                // accumulator complete
+      if (dbg) dbg[4] = clock64();
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    // Compile-time variants (EPI) keep the per-element instruction count low: the three store paths and the
+    // residual paths would otherwise all be issued as predicated-off instructions (measured: 1800 SASS
+    // instructions per 32-column chunk, which made the epilogue issue-bound at ~2000 cycles per chunk).
+    constexpr bool kRes = (EPI & EPI_RES) != 0, kRelu2 = (EPI & EPI_RELU2) != 0, kDirect = (EPI & EPI_DIRECT) != 0;
     const int q = warp & 3;
     const int r = q * 32 + lane;                             // tile row = pixel
     const int ty = r / a.TW, tx = r - ty * a.TW;
     const int oy = y0 + ty, ox = x0 + tx;
     const bool valid = oy < a.Ho && ox < a.Wo;
     const int64_t pix = ((int64_t)n_img * a.Ho + oy) * a.Wo + ox;
+    constexpr int CH = BN >= 32 ? 32 : 16;                   // columns per TMEM load
+    const int cg = GN ? a.Cout / 32 : 0;                     // channels per GroupNorm group
+    const int cgc = cg < CH ? cg : CH;
+    // act(v) = max(v,0) + slope*min(v,0): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
+    const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
     mbar_wait(accum_bar, 0);
     tcgen05_after_sync();
-    const int cg = a.gn_stats ? a.Cout / 32 : 0;             // channels per GroupNorm group
+    if (dbg && threadIdx.x == 64) dbg[5] = clock64();
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t raw[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-      tmem_wait_ld();
+    for (int c = 0; c < BN; c += CH) {
       const int cbase = n0 + c;
       if (cbase >= a.Cout) break;                            // warp-uniform
-      float v[16];
+      uint32_t raw[CH];
+      if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      // residual for this chunk is fetched while the TMEM load is in flight (host guarantees 16-byte alignment
+      // and Cout % CH == 0 whenever EPI_RES is selected)
+      uint4 rr[CH / 8];
+      if constexpr (kRes) {
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + cbase);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v[j] = __uint_as_float(raw[j]);
-        if (a.bias && cbase + j < a.Cout) v[j] += __ldg(a.bias + cbase + j);
+        for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
-      if (cg) {
+      tmem_wait_ld();
+      if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
+      float v[CH];
+#pragma unroll
+      for (int j = 0; j < CH; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + j);
+        v[j] = __uint_as_float(raw[j]) + b4.x; v[j + 1] = __uint_as_float(raw[j + 1]) + b4.y;
+        v[j + 2] = __uint_as_float(raw[j + 2]) + b4.z; v[j + 3] = __uint_as_float(raw[j + 3]) + b4.w;
+      }
+      if constexpr (GN) {
         // statistics of the values GroupNorm will read back (rounded to bf16); rows outside the image count 0
-        const int cgc = cg < 16 ? cg : 16, ngc = 16 / cgc;
-        for (int gsub = 0; gsub < ngc; ++gsub) {
-          float s1 = 0.f, s2 = 0.f;
-          if (valid) {
-            for (int j = gsub * cgc; j < (gsub + 1) * cgc; ++j) {
-              float qv = __bfloat162float(__float2bfloat16_rn(v[j]));
-              s1 += qv; s2 += qv * qv;
-            }
-          }
-          s1 = warp_sum(s1); s2 = warp_sum(s2);
-          if (lane == 0) {
-            const int gl = (c + gsub * cgc) / cgc;            // local slot: one per cgc channels of this tile
-            atomicAdd(&sstat[gl * 2 + 0], s1); atomicAdd(&sstat[gl * 2 + 1], s2);
-          }
+        float qv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) qv[j] = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+        const int slot0 = c / cgc;
+        switch (cgc) {
+          case 1: gn_chunk<CH, 1>(qv, lane, sstat, slot0); break;
+          case 2: gn_chunk<CH, 2>(qv, lane, sstat, slot0); break;
+          case 4: gn_chunk<CH, 4>(qv, lane, sstat, slot0); break;
+          case 8: gn_chunk<CH, 8>(qv, lane, sstat, slot0); break;
+          case 16: gn_chunk<CH, 16>(qv, lane, sstat, slot0); break;
+          default: gn_chunk<CH, CH>(qv, lane, sstat, slot0); break;
         }
       }
-      if (valid) {
-        if (a.res) {
-          const bf16* rp = a.res + pix * a.res_ld + cbase;
-          if (cbase + 15 < a.Cout && (reinterpret_cast<uintptr_t>(rp) & 15) == 0) {
-            uint4 r0 = *reinterpret_cast<const uint4*>(rp), r1 = *reinterpret_cast<const uint4*>(rp + 8);
-            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
-            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+      if constexpr (kRes) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              v[2 * j] += __low2float(h0[j]); v[2 * j + 1] += __high2float(h0[j]);
-              v[8 + 2 * j] += __low2float(h1[j]); v[9 + 2 * j] += __high2float(h1[j]);
+        for (int j = 0; j < CH / 8; ++j) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += __low2float(h[e]); v[8 * j + 2 * e + 1] += __high2float(h[e]); }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+      if constexpr (!kDirect) {
+        // swizzled staging tile(s): [BN/64][128 rows][min(BN,64) ch]; 16-byte chunk j of row r lands at the address the
+        // TMA swizzle expects, so 8 consecutive rows cover all 32 banks (conflict-free 16 B stores).  Rows outside
+        // the image are staged too and clipped by the tensor store.
+        constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2, MASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) {
+          const int cc = c + 8 * j;
+          uint32_t off = (uint32_t)(cc >> 6) * (128u * ROWB) + (uint32_t)r * ROWB + (uint32_t)(cc & 63) * 2u;
+          off ^= ((off >> 7) & MASK) << 4;
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(smem + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if constexpr (kRelu2) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(v[8 * j + 2 * e], 0.f), fmaxf(v[8 * j + 2 * e + 1], 0.f));
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
             }
-          } else {
-            for (int j = 0; j < 16; ++j) if (cbase + j < a.Cout) v[j] += __bfloat162float(rp[j]);
+            *reinterpret_cast<uint4*>(smem + 128u * BN * 2u + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = apply_act(v[j], a.act);
+      } else if (valid) {
+        // direct stores: fp32 heads ([P][8] / [P][12]) and the channel-major value bank (lanes = consecutive pixels)
         if (a.out_f32) {
           float* op = static_cast<float*>(a.out) + pix * a.out_ps + (int64_t)cbase * a.out_cs;
-          for (int j = 0; j < 16; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
         } else {
           bf16* op = static_cast<bf16*>(a.out) + pix * a.out_ps + (int64_t)cbase * a.out_cs;
-          if (a.out_cs == 1 && cbase + 15 < a.Cout && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
-            uint32_t pk[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            for (int j = 0; j < 16; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = __float2bfloat16_rn(v[j]);
-          }
-        }
-        if (a.out_relu) {
-          bf16* op = a.out_relu + pix * a.out_relu_ld + cbase;
-          if (cbase + 15 < a.Cout && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
-            uint32_t pk[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(v[2 * j], 0.f), fmaxf(v[2 * j + 1], 0.f));
-              pk[j] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(op) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *reinterpret_cast<uint4*>(op + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-          } else {
-            for (int j = 0; j < 16; ++j) if (cbase + j < a.Cout) op[j] = __float2bfloat16_rn(fmaxf(v[j], 0.f));
-          }
+          for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = __float2bfloat16_rn(v[j]);
         }
       }
     }
-    if (cg) {
+    if (dbg && threadIdx.x == 64) dbg[9] = clock64();
+    if constexpr (!kDirect) {
+      fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        constexpr int NSUB = BN > 64 ? BN / 64 : 1;
+        constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2;
+#pragma unroll
+        for (int sub = 0; sub < NSUB; ++sub) {
+          if (n0 + sub * 64 >= a.Cout) break;
+          tma_store_4d(&tmO, smem + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img);
+          if constexpr (kRelu2) tma_store_4d(&tmR, smem + 128u * BN * 2u + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img);
+        }
+        tma_store_commit_and_wait();
+      }
+    }
+    if constexpr (GN) {
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-      const int cgc = cg < 16 ? cg : 16;
       const int e = threadIdx.x - 64;                         // 0..127
       if (e < BN / cgc && n0 + e * cgc < a.Cout) {
         const int g = (n0 + e * cgc) / cg;
@@ -212,17 +268,46 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         atomicAdd(&a.gn_stats[g * 2 + 1], (double)sstat[e * 2 + 1]);
       }
     }
+    if (dbg && threadIdx.x == 64) dbg[6] = clock64();
     tcgen05_before_sync();
   }
   __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
   if (warp == 1) {
     tcgen05_after_sync();
     tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
+long long* g_conv_dbg = nullptr;   // dev hook (otvm_debug_set_conv_timestamps)
+
 // ---------------------------------------------------------------------------------------------------------
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16; }
+
+static bool aligned_view(const void* ptr, int64_t ld) {
+  return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0;
+}
+
+// epilogue variant for this problem, or -1 when no compiled variant covers it
+static int conv_tc_epi(const otvm_conv_params* p, int bn) {
+  const int ch = bn >= 32 ? 32 : 16;
+  int epi = 0;
+  if (p->res) {
+    if (!aligned_view(p->res, p->res_ld) || p->Cout % ch != 0) return -1;
+    epi |= EPI_RES;
+  }
+  const bool tma_ok = !p->out_f32 && p->out_cs == 1 && aligned_view(p->out, p->out_ps) && p->Cout % 8 == 0;
+  if (!tma_ok) {
+    if (p->out_relu || p->gn_stats || p->res) return -1;
+    return EPI_DIRECT;
+  }
+  if (p->out_relu) {
+    if (!aligned_view(p->out_relu, p->out_relu_ld) || p->gn_stats) return -1;
+    epi |= EPI_RELU2;
+  }
+  if (p->gn_stats && (epi & EPI_RELU2)) return -1;
+  return epi;
+}
 
 bool conv2d_tc_supported(const otvm_conv_params* p) {
   if (p->dtype != OTVM_BF16 || p->stride != 1 || p->relu_in) return false;
@@ -233,27 +318,40 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
   if (p->gn_stats && (p->N != 1 || p->Cout % 32 != 0)) return false;
   const int bn = pick_bn(p->Cout);
+  if (conv_tc_epi(p, bn) < 0) return false;
   if (p->gn_stats) {            // a GroupNorm group must not straddle tiles / 16-column chunks irregularly
     const int cg = p->Cout / 32;
-    if (cg > 16 && (cg % 16 != 0 || bn % cg != 0)) return false;
-    if (cg <= 16 && 16 % cg != 0) return false;
+    if (bn < 32) return false;
+    if (cg > 32 && (cg % 32 != 0 || bn % cg != 0)) return false;
+    if (cg <= 32 && 32 % cg != 0) return false;
   }
   static int sm100 = -1;
   if (sm100 < 0) { int dev = 0; cudaGetDevice(&dev); sm100 = otvm_device_is_sm100(dev); }
   return sm100 == 1;
 }
 
-template <int BN>
-static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvTcArgs& a, dim3 grid, size_t smem,
-                          cudaStream_t s) {
+template <int BN, bool GN, int EPI>
+static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                          const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
-  conv_tc_kernel<BN><<<grid, kConvThreads, smem, s>>>(tmA, tmB, a);
+  conv_tc_kernel<BN, GN, EPI><<<grid, kConvThreads, smem, s>>>(tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
+}
+
+template <int BN>
+static int dispatch_conv_tc(bool gn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                            const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+#define OTVM_CASE(G, E) if (gn == G && epi == (E)) return launch_conv_tc<BN, G, (E)>(tmA, tmB, tmO, tmR, a, grid, smem, s);
+  OTVM_CASE(false, 0) OTVM_CASE(false, EPI_RES) OTVM_CASE(false, EPI_RELU2) OTVM_CASE(false, EPI_RES | EPI_RELU2)
+  OTVM_CASE(false, EPI_DIRECT)
+  if constexpr (BN >= 32) { OTVM_CASE(true, 0) OTVM_CASE(true, EPI_RES) }
+#undef OTVM_CASE
+  return OTVM_ERR_UNSUPPORTED;
 }
 
 int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
@@ -281,6 +379,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.res = static_cast<const bf16*>(p->res); a.res_ld = p->res_ld;
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
+  a.dbg = g_conv_dbg;
   if (p->gn_stats) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
 
   const CUtensorMapSwizzle swz = a.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -301,13 +400,38 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     int rc = make_tmap_bf16(&tmB, p->weight, 2, dims, str, box, swz);
     if (rc) return rc;
   }
+  // epilogue through shared memory + TMA tensor store when the destination is a 16-byte aligned bf16 NHWC view
+  CUtensorMap tmO = tmA, tmR = tmA;
+  const int boxc = bn < 64 ? bn : 64;
+  const bool tma_store = !(conv_tc_epi(p, bn) & EPI_DIRECT);
+  if (tma_store) {
+    const CUtensorMapSwizzle oswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : boxc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)p->N};
+    uint32_t box[4] = {(uint32_t)boxc, (uint32_t)a.TW, (uint32_t)a.TH, 1};
+    uint64_t str[3] = {(uint64_t)p->out_ps * 2, (uint64_t)a.Wo * p->out_ps * 2, (uint64_t)a.Ho * a.Wo * p->out_ps * 2};
+    int rc = make_tmap_bf16(&tmO, p->out, 4, dims, str, box, oswz);
+    if (rc) return rc;
+    if (p->out_relu) {
+      uint64_t str2[3] = {(uint64_t)p->out_relu_ld * 2, (uint64_t)a.Wo * p->out_relu_ld * 2,
+                          (uint64_t)a.Ho * a.Wo * p->out_relu_ld * 2};
+      rc = make_tmap_bf16(&tmR, p->out_relu, 4, dims, str2, box, oswz);
+      if (rc) return rc;
+    }
+  }
   dim3 grid(a.tiles_x * a.tiles_y * p->N, ceil_div(p->Cout, bn));
-  const size_t smem = (size_t)nstage * stage + 1024 + (2 * nstage + 1) * 8 + 16 + 2 * 128 * sizeof(float);
+  size_t pipe = (size_t)nstage * stage;
+  const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
+  if (tma_store && staging > pipe) pipe = staging;           // the epilogue tile reuses the drained stages
+  const size_t smem = pipe + 1024 + (2 * nstage + 1) * 8 + 16 + (2 * 128 + 128) * sizeof(float);
+  a.aux_off = (uint32_t)pipe;
+  const bool gn = p->gn_stats != nullptr;
+  const int epi = conv_tc_epi(p, bn);
   switch (bn) {
-    case 128: return launch_conv_tc<128>(tmA, tmB, a, grid, smem, s);
-    case 64: return launch_conv_tc<64>(tmA, tmB, a, grid, smem, s);
-    case 32: return launch_conv_tc<32>(tmA, tmB, a, grid, smem, s);
-    default: return launch_conv_tc<16>(tmA, tmB, a, grid, smem, s);
+    case 128: return dispatch_conv_tc<128>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
+    case 64: return dispatch_conv_tc<64>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
+    case 32: return dispatch_conv_tc<32>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
+    default: return dispatch_conv_tc<16>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
   }
 }
 
@@ -336,3 +460,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 }
 
 }  // namespace otvm
+
+// dev hook (not part of the documented ABI): per-CTA clock64 timestamps of the next tcgen05 conv launches
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_timestamps(long long* buf) {
+  otvm::g_conv_dbg = buf;
+}

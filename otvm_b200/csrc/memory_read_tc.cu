@@ -1,0 +1,292 @@
+// Fused STM space-time memory read on tcgen05 tensor cores (reference models/trimap/STM.py:144-163).
+//
+//   O[q, :] = sum_m softmax_m( K[m,:].Q[q,:] / sqrt(128) ) * V[:, m]          (bf16 operands, fp32 accumulation)
+//
+// One CTA = 128 queries x 256 of the 512 value channels x one split of the memory axis, streaming 64-key blocks:
+//   TMA      : Q tile once; per block a K tile [64 keys x 128] and a V tile [256 ch x 64 keys] (channel-major
+//              bank => both are K-major UMMA operands), 3-stage mbarrier ring
+//   MMA warp : S_j = Q K_j^T (M128 N64 K128) into one of two TMEM S buffers, then O += P_{j-1} V_{j-1}
+//              (M128 N256 K64) -- S_j is issued BEFORE PV_{j-1} so the softmax of block j overlaps the PV MMA
+//   softmax  : 4 warps, thread = query row: tcgen05.ld S, online softmax in the exp2 domain with LAZY rescaling
+//              (the O accumulator in TMEM is only rescaled when the running max grows by more than 2^8),
+//              P written as bf16 into a swizzled K-major smem tile that the PV MMA reads directly
+// TMEM: O = 256 columns, S = 2 x 64 columns.  The [THW x HW] affinity never leaves the SM.  Per-split partial
+// (unnormalised O, m, l) go to the fp32 workspace and are merged by memory_read_combine_kernel.
+#include <math_constants.h>
+#include "tc_common.cuh"
+
+namespace otvm {
+
+using namespace tc;
+
+int read_pick_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
+int read_max_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
+int read_combine(const otvm_read_params* p, int nsplit, cudaStream_t s);
+
+constexpr int TQ = 128, TKB = 64, TDV = 256, TDE = 128, TNS = 3;
+constexpr uint32_t kQBytes = TQ * TDE * 2;            // 32 KB (two 64-wide swizzle atoms)
+constexpr uint32_t kKBytes = TKB * TDE * 2;           // 16 KB
+constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB
+constexpr uint32_t kPBytes = TQ * TKB * 2;            // 16 KB
+constexpr uint32_t kStage = kKBytes + kVBytes;
+constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256;
+constexpr int kReadThreads = 192;
+constexpr float kLazyLog2 = 8.f;
+
+struct ReadTcArgs {
+  int M, HW, Do, nsplit, blocks_per_split;
+  float scale_log2;
+  float* o_part; float* ml_part;
+};
+
+__global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                                                                         const __grid_constant__ CUtensorMap tmK,
+                                                                         const __grid_constant__ CUtensorMap tmV,
+                                                                         const ReadTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + kQBytes;
+  uint8_t* sP = sKV + TNS * kStage;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* kv_full = bars + 1;            // TNS
+  uint64_t* kv_empty = kv_full + TNS;      // TNS
+  uint64_t* s_full = kv_empty + TNS;       // 2
+  uint64_t* s_empty = s_full + 2;          // 2
+  uint64_t* p_full = s_empty + 2;          // 2
+  uint64_t* p_empty = p_full + 2;          // 2
+  uint64_t* o_done = p_empty + 2;          // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * TQ, c0 = blockIdx.y * TDV, split = blockIdx.z;
+  const int nb_total = (a.M + TKB - 1) / TKB;
+  const int kb0 = split * a.blocks_per_split;
+  const int nb = min(a.blocks_per_split, nb_total - kb0);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < TNS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4);
+      mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
+    }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + TDV;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, kQBytes);
+      tma_load_2d(sQ, &tmQ, q_full, 0, q0);
+      tma_load_2d(sQ + kQBytes / 2, &tmQ, q_full, 64, q0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j % TNS;
+        mbar_wait(&kv_empty[s], ((j / TNS) & 1) ^ 1);
+        uint8_t* st = sKV + (size_t)s * kStage;
+        const int key0 = (kb0 + j) * TKB;
+        mbar_arrive_expect_tx(&kv_full[s], kStage);
+        tma_load_2d(st, &tmK, &kv_full[s], 0, key0);
+        tma_load_2d(st + kKBytes / 2, &tmK, &kv_full[s], 64, key0);
+        tma_load_2d(st + kKBytes, &tmV, &kv_full[s], key0, c0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, TKB);
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, TDV);
+      const uint32_t q_addr = base;
+      auto issue_pv = [&](int j) {                         // O += P_j V_j
+        const int s = j % TNS, b = j & 1;
+        mbar_wait(&p_full[b], (j >> 1) & 1);
+        tcgen05_after_sync();
+        const uint64_t pdesc = make_smem_desc(base + kQBytes + TNS * kStage + (uint32_t)b * kPBytes, 1024, 2);
+        const uint64_t vdesc = make_smem_desc(base + kQBytes + (uint32_t)s * kStage + kKBytes, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < TKB / 16; ++k)
+          umma_bf16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (j | k) != 0);
+        umma_commit(&kv_empty[s]);                         // K_j / V_j stage free
+        umma_commit(&p_empty[b]);                          // P buffer free, O holds blocks 0..j
+      };
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j % TNS, b = j & 1;
+        mbar_wait(&kv_full[s], (j / TNS) & 1);
+        if (j >= 2) mbar_wait(&s_empty[b], ((j >> 1) - 1) & 1);      // softmax finished reading S[b] of block j-2
+        tcgen05_after_sync();
+        const uint32_t k_addr = base + kQBytes + (uint32_t)s * kStage;
+#pragma unroll
+        for (int k = 0; k < TDE / 16; ++k) {               // two 64-wide atoms, 4 K-steps each
+          const uint32_t atom = (k >> 2), kk = (k & 3);
+          const uint64_t qd = make_smem_desc(q_addr + atom * (kQBytes / 2), 1024, 2) + (uint64_t)(2 * kk);
+          const uint64_t kd = make_smem_desc(k_addr + atom * (kKBytes / 2), 1024, 2) + (uint64_t)(2 * kk);
+          umma_bf16(tmem_s + (uint32_t)b * TKB, qd, kd, idesc_s, k != 0);
+        }
+        umma_commit(&s_full[b]);
+        if (j > 0) issue_pv(j - 1);
+      }
+      issue_pv(nb - 1);
+      umma_commit(o_done);
+    }
+  } else {
+    // ===== softmax / correction / epilogue: thread = query row =====
+    const int qd = warp & 3;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    float m_used = -CUDART_INF_F, l_sum = 0.f;
+    for (int j = 0; j < nb; ++j) {
+      const int b = j & 1;
+      mbar_wait(&s_full[b], (j >> 1) & 1);
+      tcgen05_after_sync();
+      uint32_t raw[2][32];
+      tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB, raw[0]);
+      tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB + 32, raw[1]);
+      tmem_wait_ld();
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[b]);             // S[b] may be overwritten by block j+2
+      const int key0 = (kb0 + j) * TKB;
+      float sc[64];
+      float mx = -CUDART_INF_F;
+#pragma unroll
+      for (int i = 0; i < 64; ++i) {
+        float v = __uint_as_float(raw[i >> 5][i & 31]) * a.scale_log2;
+        v = (key0 + i < a.M) ? v : -CUDART_INF_F;
+        sc[i] = v; mx = fmaxf(mx, v);
+      }
+      // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
+      const bool grow = mx > m_used + kLazyLog2;
+      if (j == 0) {
+        m_used = mx;                                       // O not written yet: nothing to rescale
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = grow ? mx : m_used;
+        const float alpha = exp2f(m_used - m_new);
+        mbar_wait(&p_empty[b ^ 1], ((j - 1) >> 1) & 1);    // PV of block j-1 (and all earlier) complete
+        tcgen05_after_sync();
+#pragma unroll 1
+        for (int c = 0; c < TDV; c += 32) {
+          uint32_t o[32];
+          tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st32(tmem_o + lane_base + (uint32_t)c, o);
+        }
+        tmem_wait_st();
+        tcgen05_before_sync();
+        l_sum *= alpha;
+        m_used = m_new;
+      }
+      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);        // PV of block j-2 finished reading P[b]
+      uint8_t* prow = sP + (size_t)b * kPBytes;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {                     // 8 chunks of 8 keys (16 bytes)
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = exp2f(sc[ch * 8 + 2 * e] - m_used), p1 = exp2f(sc[ch * 8 + 2 * e + 1] - m_used);
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          l_sum += __low2float(h) + __high2float(h);       // the sum uses the rounded weights the MMA will see
+          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        uint32_t off = (uint32_t)r * 128u + (uint32_t)ch * 16u;
+        off ^= ((off >> 7) & 7u) << 4;
+        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+    }
+    // ---- partial results of this split
+    mbar_wait(o_done, 0);
+    tcgen05_after_sync();
+    const int q = q0 + r;
+    float* op = a.o_part + ((int64_t)split * a.HW + q) * a.Do + c0;
+#pragma unroll 1
+    for (int c = 0; c < TDV; c += 32) {
+      uint32_t o[32];
+      tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
+      tmem_wait_ld();
+      if (q < a.HW) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(op + c + i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+      }
+    }
+    if (q < a.HW && blockIdx.y == 0) {
+      a.ml_part[((int64_t)split * a.HW + q) * 2 + 0] = m_used;
+      a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum;
+    }
+    tcgen05_before_sync();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+bool memory_read_tc_supported(const otvm_read_params* p) {
+  if (p->dtype != OTVM_BF16 || p->De != TDE || p->Do % TDV != 0) return false;
+  if (p->q_ld % 8 != 0 || p->ldv % 8 != 0 || p->out_ld % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p->keys) & 15) || (reinterpret_cast<uintptr_t>(p->vals) & 15) ||
+      (reinterpret_cast<uintptr_t>(p->query) & 15))
+    return false;
+  static int sm100 = -1;
+  if (sm100 < 0) { int dev = 0; cudaGetDevice(&dev); sm100 = otvm_device_is_sm100(dev); }
+  return sm100 == 1;
+}
+
+int64_t memory_read_tc_workspace(int M, int HW, int De, int Do) {
+  (void)De;
+  int64_t ns = read_max_splits(M, HW, Do, TQ, TDV, TKB);
+  return ns * HW * ((int64_t)Do + 2) * (int64_t)sizeof(float);
+}
+
+int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
+  ReadTcArgs a;
+  a.M = p->M; a.HW = p->HW; a.Do = p->Do;
+  a.nsplit = read_pick_splits(p->M, p->HW, p->Do, TQ, TDV, TKB);
+  a.blocks_per_split = ceil_div(ceil_div(p->M, TKB), a.nsplit);
+  a.scale_log2 = (float)(1.4426950408889634 / sqrt((double)p->De));
+  a.o_part = static_cast<float*>(p->workspace);
+  a.ml_part = a.o_part + (int64_t)a.nsplit * p->HW * p->Do;
+  CUtensorMap tmQ, tmK, tmV;
+  {
+    uint64_t dims[2] = {(uint64_t)TDE, (uint64_t)p->HW}; uint64_t str[1] = {(uint64_t)p->q_ld * 2};
+    uint32_t box[2] = {64, TQ};
+    int rc = make_tmap_bf16(&tmQ, p->query, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)TDE, (uint64_t)p->M}; uint64_t str[1] = {(uint64_t)TDE * 2};
+    uint32_t box[2] = {64, TKB};
+    int rc = make_tmap_bf16(&tmK, p->keys, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p->M, (uint64_t)p->Do}; uint64_t str[1] = {(uint64_t)p->ldv * 2};
+    uint32_t box[2] = {TKB, TDV};
+    int rc = make_tmap_bf16(&tmV, p->vals, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kReadSmem));
+    attr = true;
+  }
+  dim3 grid(ceil_div(p->HW, TQ), p->Do / TDV, a.nsplit);
+  memory_read_tc_kernel<<<grid, kReadThreads, kReadSmem, s>>>(tmQ, tmK, tmV, a);
+  OTVM_LAUNCH_CHECK();
+  return read_combine(p, a.nsplit, s);
+}
+
+}  // namespace otvm

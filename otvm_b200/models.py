@@ -123,9 +123,10 @@ class EvalModel(nn.Module):
         eng = self.engine
         H, W = a.shape[-2:]
         dev = self.IMG_MEAN.device
-        a_ = a.to(dev, torch.float32).reshape(H, W).contiguous()
-        fg_ = fg.to(dev, torch.float32).reshape(3, H, W).contiguous()
-        bg_ = bg.to(dev, torch.float32).reshape(3, H, W).contiguous()
+        # the engine copies these into its static input buffers (H2D straight from pinned host memory is fine)
+        a_ = a.float().reshape(H, W)
+        fg_ = fg.float().reshape(3, H, W)
+        bg_ = bg.float().reshape(3, H, W)
         user_tri = None
         if first_frame and (tri is not None or tri_gt is not None):
             # models/alpha/model.py:395-401: a user trimap (BGR, 0..255) or a GT one-hot trimap seeds frame 0

@@ -37,6 +37,7 @@ class Profiler:
 
 
 PROFILER: "Profiler | None" = None
+PROFILE_SHAPES = False          # dev: one profiler key per conv shape
 
 
 def launch_count() -> int:
@@ -104,6 +105,8 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     Ho = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (KW - 1) - 1) // stride + 1
     key = "conv_tcgen05" if lib.otvm_conv2d_uses_tensor_cores(C.byref(p)) else "conv_ffma"
+    if PROFILE_SHAPES:
+        key += f" Cin={Cin} Cout={Cout} k={KH} s={stride} d={dil} {H}x{W}"
     es = x.element_size()
     nb = (N * H * W * Cin + Cout * KH * KW * Cin) * es + N * Ho * Wo * Cout * out.element_size()
     _timed(key, lambda: check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d"),
