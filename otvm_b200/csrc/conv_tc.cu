@@ -21,7 +21,7 @@ namespace otvm {
 using namespace tc;
 
 struct ConvTcArgs {
-  int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil;
+  int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil, stride;
   int TW, TH, tiles_x, tiles_y;
   int KC, nchunk, nstage;
   uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const int ky = tap / a.KW, kx = tap - ky * a.KW;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], a.a_bytes + (uint32_t)(BN * a.KC * 2));
-        tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, x0 - a.pad + kx * a.dil, y0 - a.pad + ky * a.dil, n_img);
+        tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, x0 * a.stride - a.pad + kx * a.dil,
+                    y0 * a.stride - a.pad + ky * a.dil, n_img);
         tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
         if (dbg && it == 0) dbg[2] = clock64();
       }
@@ -310,10 +311,11 @@ static int conv_tc_epi(const otvm_conv_params* p, int bn) {
 }
 
 bool conv2d_tc_supported(const otvm_conv_params* p) {
-  if (p->dtype != OTVM_BF16 || p->stride != 1 || p->relu_in) return false;
+  if (p->dtype != OTVM_BF16 || p->stride > 2 || p->relu_in) return false;
   if (p->Cin % 16 != 0 || p->in_ld % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p->in) & 15) || (reinterpret_cast<uintptr_t>(p->weight) & 15)) return false;
-  const int Ho = p->H + 2 * p->pad - p->dil * (p->KH - 1), Wo = p->W + 2 * p->pad - p->dil * (p->KW - 1);
+  const int Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
+  const int Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
   if (Wo < 8 || Ho < 1 || (int64_t)Ho * Wo < 64) return false;
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
   if (p->gn_stats && (p->N != 1 || p->Cout % 32 != 0)) return false;
@@ -335,7 +337,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
   conv_tc_kernel<BN, GN, EPI><<<grid, kConvThreads, smem, s>>>(tmA, tmB, tmO, tmR, a);
@@ -357,8 +359,9 @@ static int dispatch_conv_tc(bool gn, int epi, const CUtensorMap& tmA, const CUte
 int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   ConvTcArgs a;
   a.N = p->N; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
-  a.pad = p->pad; a.dil = p->dil;
-  a.Ho = p->H + 2 * p->pad - p->dil * (p->KH - 1); a.Wo = p->W + 2 * p->pad - p->dil * (p->KW - 1);
+  a.pad = p->pad; a.dil = p->dil; a.stride = p->stride;
+  a.Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
+  a.Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
   int tw = 8; while (tw * 2 <= a.Wo && tw < 128) tw *= 2;
   a.TW = tw; a.TH = 128 / tw;
   a.tiles_x = ceil_div(a.Wo, a.TW); a.tiles_y = ceil_div(a.Ho, a.TH);
@@ -370,7 +373,11 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.sbo = 8u * a.KC * 2;
   a.layout_type = a.KC == 64 ? 2u : a.KC == 32 ? 4u : 6u;
   const uint32_t stage = a.a_bytes + a.b_bytes;
-  int nstage = (int)((96u * 1024u) / stage);
+  // two CTAs per SM (<= 96 KB of stages each) when the grid is larger than one wave; a grid that fits in one
+  // wave is latency-bound instead, so it gets a deeper ring (up to ~190 KB, one CTA per SM)
+  const int64_t ctas = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
+  const uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
+  int nstage = (int)(budget / stage);
   if (nstage > 8) nstage = 8;
   const int num_k = a.KH * a.KW * a.nchunk;
   if (nstage > num_k) nstage = num_k < 2 ? 2 : num_k;
@@ -388,8 +395,10 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   {
     uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
     uint64_t str[3] = {(uint64_t)p->in_ld * 2, (uint64_t)p->W * p->in_ld * 2, (uint64_t)p->H * p->W * p->in_ld * 2};
-    uint32_t box[4] = {(uint32_t)a.KC, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    int rc = make_tmap_bf16(&tmA, p->in, 4, dims, str, box, swz);
+    // stride-2 convolutions: TMA traversal stride 2 along W and H (a box of 2*TW x 2*TH input pixels yields TW x TH)
+    uint32_t box[4] = {(uint32_t)a.KC, (uint32_t)(a.TW * p->stride), (uint32_t)(a.TH * p->stride), 1};
+    uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
+    int rc = make_tmap_bf16(&tmA, p->in, 4, dims, str, box, swz, es);
     if (rc) return rc;
   }
   {
@@ -449,10 +458,11 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, CUtensorMapSwizzle swz) {
+                   const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return OTVM_ERR_UNSUPPORTED;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -91,17 +91,38 @@ __global__ void edt_cols_kernel(const uint8_t* __restrict__ seed, int H, int W, 
   int m = idx / W, x = idx - m * W;
   const uint8_t* s = seed + (int64_t)m * H * W;
   int* g = g2 + (int64_t)m * H * W;
+  // two sweeps; the seed bytes are fetched 8 rows at a time so the loads of a chunk are in flight together
   int d = EDT_INF;                                    // distance (not squared) to the last seed above
-  for (int y = 0; y < H; ++y) {
-    d = s[(int64_t)y * W + x] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
-    g[(int64_t)y * W + x] = d;
+  for (int y0 = 0; y0 < H; y0 += 8) {
+    uint8_t sv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sv[i] = (y0 + i < H) ? __ldg(s + (int64_t)(y0 + i) * W + x) : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (y0 + i < H) {
+        d = sv[i] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
+        g[(int64_t)(y0 + i) * W + x] = d;
+      }
+    }
   }
   d = EDT_INF;
-  for (int y = H - 1; y >= 0; --y) {
-    d = s[(int64_t)y * W + x] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
-    int up = g[(int64_t)y * W + x];
-    int best = min(up, d);
-    g[(int64_t)y * W + x] = best >= 32768 ? EDT_INF : best * best;
+  for (int y1 = H - 1; y1 >= 0; y1 -= 8) {
+    uint8_t sv[8]; int up[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int y = y1 - i;
+      sv[i] = y >= 0 ? __ldg(s + (int64_t)y * W + x) : 0;
+      up[i] = y >= 0 ? g[(int64_t)y * W + x] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int y = y1 - i;
+      if (y >= 0) {
+        d = sv[i] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
+        const int best = min(up[i], d);
+        g[(int64_t)y * W + x] = best >= 32768 ? EDT_INF : best * best;
+      }
+    }
   }
 }
 

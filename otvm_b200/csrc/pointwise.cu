@@ -54,17 +54,22 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        const T* __restrict__ res, int64_t res_ld, int act,
                                                        T* __restrict__ out, int64_t out_ld) {
   extern __shared__ float sc_sh[];               // [C] scale, [C] shift
+  __shared__ float g_mean[32], g_rstd[32];
   float* sc = sc_sh; float* sh = sc_sh + C;
   const int n = blockIdx.y;
   const int cg = C >> 5;
-  const double cnt = (double)HW * cg;
+  if (threadIdx.x < 32) {                        // fp64 only for the 32 group moments (E[x^2] - E[x]^2 cancels)
+    const double cnt = (double)HW * cg;
+    const double mean = stats[(n * 32 + threadIdx.x) * 2] / cnt;
+    const double var = stats[(n * 32 + threadIdx.x) * 2 + 1] / cnt - mean * mean;
+    g_mean[threadIdx.x] = (float)mean;
+    g_rstd[threadIdx.x] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int g = c / cg;
-    double mean = stats[(n * 32 + g) * 2] / cnt;
-    double var = stats[(n * 32 + g) * 2 + 1] / cnt - mean * mean;
-    float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
-    float s = rstd * gamma[c];
-    sc[c] = s; sh[c] = beta[c] - (float)mean * s;
+    const int g = c / cg;
+    const float s = g_rstd[g] * gamma[c];
+    sc[c] = s; sh[c] = beta[c] - g_mean[g] * s;
   }
   __syncthreads();
   const int c4n = C >> 2;

@@ -176,6 +176,6 @@ EncodeTiledFn get_encode_tiled();
 
 // bf16 tensor map; dims/strides innermost first, strides in BYTES for dims 1..rank-1
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, CUtensorMapSwizzle swz);
+                   const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides = nullptr);
 
 }  // namespace otvm

@@ -44,6 +44,9 @@ class PackedWeights:
         self.dtype, self.device = dtype, device
         self.conv: Dict[str, tuple] = {}
         self.norm: Dict[str, tuple] = {}
+        # stem channel padding: the tcgen05 path needs Cin % 16 == 0 (one 32-byte swizzle span per pixel)
+        bf = dtype == torch.bfloat16
+        self.cin_img, self.cin_mem = (16, 32) if bf else (4, 24)
         f = lambda k: sd[k].detach().to("cpu", torch.float32)
 
         def put(name, w, b, cin_pad=None):
@@ -66,9 +69,9 @@ class PackedWeights:
             if enc.endswith("_M"):          # order must match frame_outputs' 22-channel memorize input
                 w = torch.cat([f(enc + ".conv1.weight"), f(enc + ".conv1_m.weight"), f(enc + ".conv1_o.weight"),
                                f(enc + ".conv1_a.weight"), f(enc + ".conv1_h.weight")], dim=1)
-                put(enc + ".stem", *bn_fold(w, enc + ".bn1"), cin_pad=24)
+                put(enc + ".stem", *bn_fold(w, enc + ".bn1"), cin_pad=self.cin_mem)
             else:
-                put(enc + ".stem", *bn_fold(f(enc + ".conv1.weight"), enc + ".bn1"), cin_pad=4)
+                put(enc + ".stem", *bn_fold(f(enc + ".conv1.weight"), enc + ".bn1"), cin_pad=self.cin_img)
             for lname, blocks in (("res2", 3), ("res3", 4), ("res4", 6)):
                 for b in range(blocks):
                     p = f"{enc}.{lname}.{b}"
@@ -279,7 +282,7 @@ class Engine:
     # ---- STM ---------------------------------------------------------------------------------------
     def segment(self, pl: FramePlan, bank: MemoryBank):
         """Propagated trimap logits [Hp*Wp][4] fp32 for the current frame (imgn must be ready)."""
-        imgn = pl.bufs["imgn"]
+        imgn = pl.bufs["imgn"]                      # [1,Hp,Wp,cin_img]: 3 normalised channels + zeros
         r2, r3, r4 = self._tv_encoder(pl, "trimap.model.Encoder_Q", imgn)
         N, h, w, _ = r4.shape
         m4in = pl.buf("m4in", (1, h, w, 2 * DO))
@@ -315,7 +318,7 @@ class Engine:
 
     def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int):
         """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``."""
-        mem_in = pl.bufs["mem_in"]
+        mem_in = pl.bufs["mem_in"]                  # [1,Hp,Wp,cin_mem]: 22 channels + zeros
         _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in)
         N, h, w, _ = r4.shape
         kdst = bank.key_slot(slot).view(1, h, w, DE)
@@ -391,7 +394,7 @@ class Engine:
         img = pl.buf("img", (P, 4), f32)
         scaled = pl.buf("scaled_img", (3, H, W), f32)
         tri3 = pl.buf("tri3", (P, 4), f32)
-        imgn = pl.buf("imgn", (1, Hp, Wp, 4))
+        imgn = pl.buf("imgn", (1, Hp, Wp, self.w.cin_img), zero=True)[..., :4]
         ops.preprocess(a, fg, bg, H, W, Hp, Wp, pl.pad_top, pl.pad_left, radius, self.w.ms_q, img, scaled, tri3, imgn,
                        pl.buf("pre_scratch", (2 * H * W,), torch.uint8))
         x11 = pl.buf("x11", (1, Hp, Wp, 16))
@@ -413,7 +416,7 @@ class Engine:
         net = self.matting(pl)
         alpha = pl.buf("alpha_out", (H, W), f32)
         trimap = pl.buf("trimap_out", (3, H, W), f32)
-        mem_in = pl.buf("mem_in", (1, Hp, Wp, 24)) if slot is not None else None
+        mem_in = pl.buf("mem_in", (1, Hp, Wp, self.w.cin_mem), zero=True)[..., :24] if slot is not None else None
         ops.frame_outputs(net["raw10"], 12, net["fused"], net["hid"], extras, Hp, Wp, H, W, pl.pad_top, pl.pad_left,
                           self.w.ms_m, mem_in, alpha, trimap)
         if slot is not None:

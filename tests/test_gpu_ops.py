@@ -314,3 +314,20 @@ def test_conv2d_tcgen05(case):
         q = rnd(dtype, want).double()[0].reshape(32, -1)
         assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 2e-3
         assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("s", [1, 2, 3, 6])
+def test_conv1x1_on_ppm_cells(s, dtype):
+    """the pyramid-pooling 1x1 convs run on s*s pixels (small-M kernel) with fused GroupNorm statistics"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(s)
+    x = torch.randn(1, 2048, s, s, generator=g); w = torch.randn(256, 2048, 1, 1, generator=g) / 45; b = torch.randn(256, generator=g)
+    want = F.conv2d(rnd(dtype, x), rnd(dtype, w), b)
+    out = torch.zeros(1, s, s, 256, dtype=dtype, device=DEV)
+    stats = torch.zeros(64, dtype=torch.float64, device=DEV)
+    ops.conv2d(nhwc(x, dtype), w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype), b.to(DEV), out, gn_stats=stats)
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    q = rnd(dtype, nchw(out))[0].double().reshape(32, -1)
+    assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 1e-5
+    assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 1e-5
