@@ -69,6 +69,7 @@ typedef struct {
   int32_t dtype;                                  /* OTVM_F32 / OTVM_BF16 for in, weight, out, res          */
   int32_t out_f32;                                /* 1: `out` is fp32 even when dtype is bf16 (heads)       */
   double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
+  void* workspace;     int64_t workspace_bytes;   /* optional fp32 scratch: enables split-K for small grids */
 } otvm_conv_params;
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d would run this problem on the tcgen05 implicit-GEMM kernel (else the FFMA kernel) */

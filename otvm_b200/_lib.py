@@ -27,6 +27,7 @@ class ConvParams(C.Structure):
         ("out_relu", c_vp), ("out_relu_ld", c_i64),
         ("act", c_i32), ("relu_in", c_i32), ("dtype", c_i32), ("out_f32", c_i32),
         ("gn_stats", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
 
 

@@ -24,6 +24,8 @@ struct ConvTcArgs {
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil, stride;
   int TW, TH, tiles_x, tiles_y;
   int KC, nchunk, nstage;
+  int k_per_split;             // K iterations per blockIdx.z slice (split-K); == num_k without split
+  int64_t split_stride;        // elements between the fp32 partial outputs of consecutive K slices
   uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
   uint32_t a_bytes, b_bytes, sbo, layout_type;
   const float* bias;
@@ -71,7 +73,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = a.dbg ? a.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 : nullptr;
+  long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   const int ty_i = bx % a.tiles_y; const int n_img = bx / a.tiles_y;
   const int x0 = tx_i * a.TW, y0 = ty_i * a.TH;
   const int n0 = blockIdx.y * BN;
-  const int num_k = a.KH * a.KW * a.nchunk;
+  const int num_k_all = a.KH * a.KW * a.nchunk;
+  const int it0 = blockIdx.z * a.k_per_split;
+  const int num_k = min(a.k_per_split, num_k_all - it0);      // this CTA's K range is [it0, it0 + num_k)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const int s = it % a.nstage;
         const uint32_t ph = (it / a.nstage) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = it / a.nchunk, chunk = it - tap * a.nchunk;
+        const int tap = (it0 + it) / a.nchunk, chunk = (it0 + it) - tap * a.nchunk;
         const int ky = tap / a.KW, kx = tap - ky * a.KW;
         uint8_t* sa = smem + (size_t)s * stage_bytes;
         mbar_arrive_expect_tx(&full_bar[s], a.a_bytes + (uint32_t)(BN * a.KC * 2));
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       } else if (valid) {
         // direct stores: fp32 heads ([P][8] / [P][12]) and the channel-major value bank (lanes = consecutive pixels)
         if (a.out_f32) {
-          float* op = static_cast<float*>(a.out) + pix * a.out_ps + (int64_t)cbase * a.out_cs;
+          float* op = static_cast<float*>(a.out) + (int64_t)blockIdx.z * a.split_stride + pix * a.out_ps + (int64_t)cbase * a.out_cs;
 #pragma unroll
           for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
         } else {
@@ -277,6 +281,75 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (warp == 1) {
     tcgen05_after_sync();
     tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// split-K second pass: sum the fp32 partial tiles and run the fused epilogue (bias, GroupNorm statistics of the
+// stored values, residual, activation, optional ReLU'd second output) on the 4 channels each thread owns
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, int S, int64_t M, int Cout,
+                                                            const float* __restrict__ bias, const bf16* __restrict__ res,
+                                                            int64_t res_ld, int act, void* __restrict__ out, int64_t out_ps,
+                                                            int64_t out_cs, int out_f32, bf16* __restrict__ out_relu,
+                                                            int64_t out_relu_ld, double* __restrict__ gn_stats) {
+  __shared__ float sstat[32][2];
+  const int c4n = Cout >> 2;
+  const int64_t total = M * c4n;
+  const int cg = gn_stats ? Cout / 32 : 1;
+  if (gn_stats) {
+    if (threadIdx.x < 32) { sstat[threadIdx.x][0] = 0.f; sstat[threadIdx.x][1] = 0.f; }
+    __syncthreads();
+  }
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / c4n; const int c = (int)(idx - p * c4n) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int z = 0; z < S; ++z) {
+      const float4 t = *reinterpret_cast<const float4*>(ws + ((int64_t)z * M + p) * Cout + c);
+      v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
+    }
+    if (bias) { v[0] += bias[c]; v[1] += bias[c + 1]; v[2] += bias[c + 2]; v[3] += bias[c + 3]; }
+    if (gn_stats) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float q0 = __bfloat162float(__float2bfloat16_rn(v[2 * h])), q1 = __bfloat162float(__float2bfloat16_rn(v[2 * h + 1]));
+        if (cg >= 2) {
+          atomicAdd(&sstat[(c + 2 * h) / cg][0], q0 + q1); atomicAdd(&sstat[(c + 2 * h) / cg][1], q0 * q0 + q1 * q1);
+        } else {
+          atomicAdd(&sstat[c + 2 * h][0], q0); atomicAdd(&sstat[c + 2 * h][1], q0 * q0);
+          atomicAdd(&sstat[c + 2 * h + 1][0], q1); atomicAdd(&sstat[c + 2 * h + 1][1], q1 * q1);
+        }
+      }
+    }
+    if (res) {
+      float r[4];
+      load4(res + p * res_ld + c, r);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], act);
+    if (out_f32) {
+      float* o = static_cast<float*>(out) + p * out_ps + (int64_t)c * out_cs;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[(int64_t)j * out_cs] = v[j];
+    } else {
+      bf16* o = static_cast<bf16*>(out) + p * out_ps + (int64_t)c * out_cs;
+      if (out_cs == 1 && aligned4(o)) store4(o, v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[(int64_t)j * out_cs] = __float2bfloat16_rn(v[j]);
+      }
+    }
+    if (out_relu) {
+      float rl[4] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f)};
+      store4(out_relu + p * out_relu_ld + c, rl);
+    }
+  }
+  if (gn_stats) {
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      atomicAdd(&gn_stats[threadIdx.x * 2 + 0], (double)sstat[threadIdx.x][0]);
+      atomicAdd(&gn_stats[threadIdx.x * 2 + 1], (double)sstat[threadIdx.x][1]);
+    }
   }
 }
 
@@ -382,6 +455,21 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   const int num_k = a.KH * a.KW * a.nchunk;
   if (nstage > num_k) nstage = num_k < 2 ? 2 : num_k;
   a.nstage = nstage;
+  // split-K: a grid that fills less than half of the SMs walks K serially at TMA/L2 latency; slice K across
+  // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
+  int nsplit = 1;
+  const int64_t Mtot = (int64_t)p->N * a.Ho * a.Wo;
+  if (p->workspace && ctas * 2 <= sm_count() && num_k >= 48 && p->Cout % 4 == 0 &&
+      (!p->res || p->res_ld % 4 == 0) && (!p->out_relu || p->out_relu_ld % 4 == 0)) {
+    nsplit = (int)(sm_count() / ctas);
+    if (nsplit > num_k / 12) nsplit = num_k / 12;          // >= 12 K iterations per slice: the extra pass must pay off
+    if (nsplit > 16) nsplit = 16;
+    while (nsplit > 1 && (int64_t)nsplit * Mtot * p->Cout * 4 > p->workspace_bytes) --nsplit;
+  }
+  a.k_per_split = ceil_div(num_k, nsplit);
+  nsplit = ceil_div(num_k, a.k_per_split);
+  a.split_stride = Mtot * p->Cout;
+  if (a.nstage > a.k_per_split) a.nstage = a.k_per_split < 2 ? 2 : a.k_per_split;
   a.bias = p->bias; a.out = p->out; a.out_ps = p->out_ps; a.out_cs = p->out_cs;
   a.res = static_cast<const bf16*>(p->res); a.res_ld = p->res_ld;
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
@@ -428,7 +516,30 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
       if (rc) return rc;
     }
   }
-  dim3 grid(a.tiles_x * a.tiles_y * p->N, ceil_div(p->Cout, bn));
+  dim3 grid(a.tiles_x * a.tiles_y * p->N, ceil_div(p->Cout, bn), nsplit);
+  if (nsplit > 1) {
+    ConvTcArgs b = a;                       // raw fp32 partial tiles into the workspace, epilogue deferred
+    b.bias = nullptr; b.out = p->workspace; b.out_ps = p->Cout; b.out_cs = 1; b.res = nullptr; b.out_relu = nullptr;
+    b.act = OTVM_ACT_NONE; b.out_f32 = 1; b.gn_stats = nullptr;
+    const size_t smem_s = (size_t)a.nstage * stage + 1024 + (2 * a.nstage + 1) * 8 + 16 + (2 * 128 + 128) * sizeof(float);
+    b.aux_off = (uint32_t)((size_t)a.nstage * stage);
+    int rc;
+    switch (bn) {
+      case 128: rc = dispatch_conv_tc<128>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      case 64: rc = dispatch_conv_tc<64>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      case 32: rc = dispatch_conv_tc<32>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      default: rc = dispatch_conv_tc<16>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+    }
+    if (rc) return rc;
+    const int64_t total = Mtot * (p->Cout / 4);
+    int g = (int)((total + 255) / 256); if (g > sm_count() * 8) g = sm_count() * 8;
+    splitk_finish_kernel<<<g, 256, 0, s>>>(static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout, p->bias,
+                                           static_cast<const bf16*>(p->res), p->res_ld, p->act, p->out, p->out_ps,
+                                           p->out_cs, p->out_f32, static_cast<bf16*>(p->out_relu), p->out_relu_ld,
+                                           p->gn_stats);
+    OTVM_LAUNCH_CHECK();
+    return OTVM_OK;
+  }
   size_t pipe = (size_t)nstage * stage;
   const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
   if (tma_store && staging > pipe) pipe = staging;           // the epilogue tile reuses the drained stages

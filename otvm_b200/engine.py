@@ -226,7 +226,8 @@ class Engine:
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         if out is None:
             out = pl.buf(out_name or name, (N, Ho, Wo, w.shape[0]))
-        return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, **kw)
+        ws = pl.buf("conv_splitk_ws", (16 << 20,), torch.float32)       # 64 MB fp32 scratch for split-K partial tiles
+        return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, workspace=ws, **kw)
 
     def _tv_bottleneck(self, pl, p, x, stride, out=None):
         """torchvision Bottleneck with BN folded; ReLUs and the residual add live in the conv epilogues."""

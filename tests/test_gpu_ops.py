@@ -314,6 +314,18 @@ def test_conv2d_tcgen05(case):
         q = rnd(dtype, want).double()[0].reshape(32, -1)
         assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 2e-3
         assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 2e-3
+    # with a workspace, small grids take the split-K route (fp32 partial tiles + fused finish kernel)
+    ws = torch.zeros(8 << 20, device=DEV)
+    out3 = torch.zeros_like(out.contiguous()) if head else torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV)
+    stats3 = torch.zeros(64, dtype=torch.float64, device=DEV) if stats is not None else None
+    ops.conv2d(xd, wd, b.to(DEV), out3, pad=p, dil=d, gn_stats=stats3, workspace=ws)
+    assert rel_err(nchw(out3), want) < (2e-3 if head else 1e-2)
+    if stats is not None:
+        assert rel_err(stats3.cpu(), stats.cpu()) < 2e-3
+    if not head:
+        out4 = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV); outr4 = torch.zeros_like(out4)
+        ops.conv2d(xd, wd, b.to(DEV), out4, pad=p, dil=d, res=nhwc(res, dtype), act=ops.ACT_RELU, out_relu=outr4, workspace=ws)
+        assert rel_err(nchw(out4), want2) < 1e-2 and rel_err(nchw(outr4), want2) < 1e-2
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
