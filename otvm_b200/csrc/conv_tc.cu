@@ -39,16 +39,20 @@ struct ConvTcArgs {
 
 constexpr int kConvThreads = 192;
 
-// per-chunk GroupNorm partial sums: CGC consecutive channels form one slot
+// per-chunk GroupNorm partial sums: CGC consecutive channels form one slot.  Every thread (= tile row) parks its
+// partial (sum, sum of squares) per slot in shared memory, sred[which][slot][129]; after the chunk loop one thread
+// per (slot, which) adds up the 128 rows.  (Warp-shuffle trees cost 10 shuffles per slot per thread, which made
+// the epilogue of the 64-channel full-resolution convolutions, 32 groups of 2, as long as their main loop.)
+constexpr int kSredPitch = 129;
 template <int CH, int CGC>
-__device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int lane, float* sstat, int slot0) {
+__device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int r, float* sred, int slot0) {
 #pragma unroll
   for (int g = 0; g < CH / CGC; ++g) {
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < CGC; ++j) { const float x = qv[g * CGC + j]; s1 += x; s2 += x * x; }
-    s1 = warp_sum(s1); s2 = warp_sum(s2);
-    if (lane == 0) { atomicAdd(&sstat[(slot0 + g) * 2 + 0], s1); atomicAdd(&sstat[(slot0 + g) * 2 + 1], s2); }
+    sred[(slot0 + g) * kSredPitch + r] = s1;
+    sred[(32 + slot0 + g) * kSredPitch + r] = s2;
   }
 }
 
@@ -155,6 +159,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     constexpr int CH = BN >= 32 ? 32 : 16;                   // columns per TMEM load
     const int cg = GN ? a.Cout / 32 : 0;                     // channels per GroupNorm group
     const int cgc = cg < CH ? cg : CH;
+    float* sred = reinterpret_cast<float*>(smem + 128u * BN * 2u);   // behind the staging tile, inside the drained stages
     // act(v) = max(v,0) + slope*min(v,0): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
     const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
     mbar_wait(accum_bar, 0);
@@ -191,12 +196,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         for (int j = 0; j < CH; ++j) qv[j] = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
         const int slot0 = c / cgc;
         switch (cgc) {
-          case 1: gn_chunk<CH, 1>(qv, lane, sstat, slot0); break;
-          case 2: gn_chunk<CH, 2>(qv, lane, sstat, slot0); break;
-          case 4: gn_chunk<CH, 4>(qv, lane, sstat, slot0); break;
-          case 8: gn_chunk<CH, 8>(qv, lane, sstat, slot0); break;
-          case 16: gn_chunk<CH, 16>(qv, lane, sstat, slot0); break;
-          default: gn_chunk<CH, CH>(qv, lane, sstat, slot0); break;
+          case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
+          case 2: gn_chunk<CH, 2>(qv, r, sred, slot0); break;
+          case 4: gn_chunk<CH, 4>(qv, r, sred, slot0); break;
+          case 8: gn_chunk<CH, 8>(qv, r, sred, slot0); break;
+          case 16: gn_chunk<CH, 16>(qv, r, sred, slot0); break;
+          default: gn_chunk<CH, CH>(qv, r, sred, slot0); break;
         }
       }
       if constexpr (kRes) {
@@ -266,11 +271,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     }
     if constexpr (GN) {
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-      const int e = threadIdx.x - 64;                         // 0..127
-      if (e < BN / cgc && n0 + e * cgc < a.Cout) {
-        const int g = (n0 + e * cgc) / cg;
-        atomicAdd(&a.gn_stats[g * 2 + 0], (double)sstat[e * 2 + 0]);
-        atomicAdd(&a.gn_stats[g * 2 + 1], (double)sstat[e * 2 + 1]);
+      const int e = threadIdx.x - 64;                         // 0..127: (which, slot) = (e / 32.., e % nslot)
+      const int nslot = BN / cgc;                             // <= 32 (host-checked)
+      if (e < 2 * nslot) {
+        const int which = e / nslot, slot = e - which * nslot;
+        if (n0 + slot * cgc < a.Cout) {
+          const float* row = sred + (which * 32 + slot) * kSredPitch;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 128; ++i) acc += row[i];
+          atomicAdd(&a.gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
+        }
       }
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
@@ -399,6 +410,7 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
     if (bn < 32) return false;
     if (cg > 32 && (cg % 32 != 0 || bn % cg != 0)) return false;
     if (cg <= 32 && 32 % cg != 0) return false;
+    if (bn / (cg < 32 ? cg : 32) > 32) return false;          // at most 32 (slot, row) partial columns in smem
   }
   static int sm100 = -1;
   if (sm100 < 0) { int dev = 0; cudaGetDevice(&dev); sm100 = otvm_device_is_sm100(dev); }
@@ -542,7 +554,9 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   }
   size_t pipe = (size_t)nstage * stage;
   const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
-  if (tma_store && staging > pipe) pipe = staging;           // the epilogue tile reuses the drained stages
+  size_t need = tma_store ? staging : 0;
+  if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
+  if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
   const size_t smem = pipe + 1024 + (2 * nstage + 1) * 8 + 16 + (2 * 128 + 128) * sizeof(float);
   a.aux_off = (uint32_t)pipe;
   const bool gn = p->gn_stats != nullptr;
