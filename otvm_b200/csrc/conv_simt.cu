@@ -184,49 +184,58 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 // 1x1 convolution on a handful of pixels (the pyramid-pooling branches: 1..36 pixels x 2048 -> 256 channels,
 // FBA/models.py:300-305).  A 64x64 GEMM tile would leave all but a few SMs idle and walk K serially; here one warp
 // owns one output channel, the 32 lanes split K, and the weights are read exactly once.
-template <typename T>
-__global__ void __launch_bounds__(256) conv1x1_smallm_kernel(const ConvArgs a) {
+template <typename T, int MP>
+__global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
+  // one CTA per output channel; its 4 warps split K, every lane keeps one accumulator per pixel (M <= MP), so the
+  // weights are read once and all activation loads of a K step are independent (latency-bound otherwise)
+  __shared__ float part[4][MP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int co = blockIdx.x * 8 + warp;
-  if (co >= a.Cout) return;
+  const int co = blockIdx.x;
   const T* __restrict__ in = static_cast<const T*>(a.in);
   const T* __restrict__ wr = static_cast<const T*>(a.w) + (int64_t)co * a.K;
-  const float bias = a.bias ? a.bias[co] : 0.f;
   const int M = (int)a.M;
-  float s1 = 0.f, s2 = 0.f;
-  for (int p0 = 0; p0 < M; p0 += 8) {
-    float acc[8];
+  float acc[MP];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int k = lane * 4; k < a.K; k += 128) {
-      float wv[4];
-      load4(wr + k, wv);
+  for (int i = 0; i < MP; ++i) acc[i] = 0.f;
+  const int kq = (a.K + 3) / 4;                       // K range of this warp (multiple of 4 by the FAST contract)
+  const int kend = min(a.K, (warp + 1) * kq);
+  for (int k = warp * kq + lane * 4; k < kend; k += 128) {
+    float wv[4];
+    load4(wr + k, wv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        if (p0 + i < M) {
-          float xv[4];
-          load4(in + (int64_t)(p0 + i) * a.in_ld + k, xv);
-          acc[i] = fmaf(wv[0], xv[0], acc[i]); acc[i] = fmaf(wv[1], xv[1], acc[i]);
-          acc[i] = fmaf(wv[2], xv[2], acc[i]); acc[i] = fmaf(wv[3], xv[3], acc[i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float v = warp_sum(acc[i]) + bias;
-      if (lane == 0 && p0 + i < M) {
-        float qv = to_f(from_f<T>(v));
-        s1 += qv; s2 += qv * qv;
-        v = apply_act(v, a.act);
-        if (a.out_f32) static_cast<float*>(a.out)[(int64_t)(p0 + i) * a.out_ps + (int64_t)co * a.out_cs] = v;
-        else static_cast<T*>(a.out)[(int64_t)(p0 + i) * a.out_ps + (int64_t)co * a.out_cs] = from_f<T>(v);
+    for (int i = 0; i < MP; ++i) {
+      if (i < M) {
+        float xv[4];
+        load4(in + (int64_t)i * a.in_ld + k, xv);
+        acc[i] = fmaf(wv[0], xv[0], acc[i]); acc[i] = fmaf(wv[1], xv[1], acc[i]);
+        acc[i] = fmaf(wv[2], xv[2], acc[i]); acc[i] = fmaf(wv[3], xv[3], acc[i]);
       }
     }
   }
-  if (a.gn_stats && lane == 0) {
-    const int g = co / (a.Cout / 32);
-    atomicAdd(&a.gn_stats[g * 2 + 0], (double)s1);
-    atomicAdd(&a.gn_stats[g * 2 + 1], (double)s2);
+#pragma unroll
+  for (int i = 0; i < MP; ++i) {
+    const float v = warp_sum(acc[i]);
+    if (lane == 0) part[warp][i] = v;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = lane; i < M; i += 32) {
+      float v = part[0][i] + part[1][i] + part[2][i] + part[3][i] + (a.bias ? a.bias[co] : 0.f);
+      const float qv = to_f(from_f<T>(v));
+      s1 += qv; s2 += qv * qv;
+      v = apply_act(v, a.act);
+      if (a.out_f32) static_cast<float*>(a.out)[(int64_t)i * a.out_ps + (int64_t)co * a.out_cs] = v;
+      else static_cast<T*>(a.out)[(int64_t)i * a.out_ps + (int64_t)co * a.out_cs] = from_f<T>(v);
+    }
+    if (a.gn_stats) {
+      s1 = warp_sum(s1); s2 = warp_sum(s2);
+      if (lane == 0) {
+        const int g = co / (a.Cout / 32);
+        atomicAdd(&a.gn_stats[g * 2 + 0], (double)s1);
+        atomicAdd(&a.gn_stats[g * 2 + 1], (double)s2);
+      }
+    }
   }
 }
 
@@ -236,8 +245,11 @@ static int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   const T* in = static_cast<const T*>(a.in);
   const T* w = static_cast<const T*>(a.w);
   bool fast = (a.Cin % BK == 0) && (a.in_ld % 4 == 0) && aligned4(in) && aligned4(w);
-  if (fast && a.KH == 1 && a.KW == 1 && a.stride == 1 && a.pad == 0 && a.M <= 64 && !a.res && !a.out_relu && !a.relu_in) {
-    conv1x1_smallm_kernel<T><<<ceil_div(a.Cout, 8), 256, 0, s>>>(a);
+  if (fast && a.KH == 1 && a.KW == 1 && a.stride == 1 && a.pad == 0 && a.M <= 40 && a.K % 16 == 0 && !a.res && !a.out_relu &&
+      !a.relu_in) {
+    if (a.M <= 4) conv1x1_smallm_kernel<T, 4><<<a.Cout, 128, 0, s>>>(a);
+    else if (a.M <= 12) conv1x1_smallm_kernel<T, 12><<<a.Cout, 128, 0, s>>>(a);
+    else conv1x1_smallm_kernel<T, 40><<<a.Cout, 128, 0, s>>>(a);
     OTVM_LAUNCH_CHECK();
     return OTVM_OK;
   }

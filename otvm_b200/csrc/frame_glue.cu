@@ -82,72 +82,83 @@ __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, cons
 
 // ---------------------------------------------------------------------------------------------------
 // exact squared Euclidean distance transform (two passes, integer arithmetic)
-//   pass 1 (columns): g2[y][x] = squared distance to the nearest seed in column x
-//   pass 2 (rows)   : d2[y][x] = min_x' (x-x')^2 + g2[y][x']       (lower envelope by exhaustive search in smem)
+//   pass 1 (rows)   : g2[y][x] = squared distance to the nearest seed in row y -- one warp per row, the nearest seed
+//                     to the left / right comes from a warp max / min scan carried across 32-pixel chunks
+//   pass 2 (columns): d2[y][x] = min_y' (y-y')^2 + g2[y'][x] -- a 32-column strip of g2 sits in shared memory and
+//                     every pixel searches outwards from its own row until dy^2 can no longer beat the best value
 // ---------------------------------------------------------------------------------------------------
-__global__ void edt_cols_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask, int* __restrict__ g2) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= W * nmask) return;
-  int m = idx / W, x = idx - m * W;
-  const uint8_t* s = seed + (int64_t)m * H * W;
-  int* g = g2 + (int64_t)m * H * W;
-  // two sweeps; the seed bytes are fetched 8 rows at a time so the loads of a chunk are in flight together
-  int d = EDT_INF;                                    // distance (not squared) to the last seed above
-  for (int y0 = 0; y0 < H; y0 += 8) {
-    uint8_t sv[8];
+__global__ void __launch_bounds__(256) edt_rowscan_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask,
+                                                          int* __restrict__ g2) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= H * nmask) return;
+  const uint8_t* s = seed + (int64_t)warp * W;        // rows of all masks are contiguous
+  int* g = g2 + (int64_t)warp * W;
+  // left-to-right: position of the nearest seed at or before x
+  int carry = -EDT_INF;
+  for (int x0 = 0; x0 < W; x0 += 32) {
+    const int x = x0 + lane;
+    int pos = (x < W && s[x]) ? x : -EDT_INF;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) sv[i] = (y0 + i < H) ? __ldg(s + (int64_t)(y0 + i) * W + x) : 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (y0 + i < H) {
-        d = sv[i] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
-        g[(int64_t)(y0 + i) * W + x] = d;
-      }
-    }
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, pos, o); if (lane >= o) pos = max(pos, t); }
+    pos = max(pos, carry);
+    if (x < W) g[x] = pos;                            // stash the left position; finished below
+    carry = __shfl_sync(0xffffffffu, pos, 31);
   }
-  d = EDT_INF;
-  for (int y1 = H - 1; y1 >= 0; y1 -= 8) {
-    uint8_t sv[8]; int up[8];
+  carry = EDT_INF;
+  for (int x0 = ((W - 1) / 32) * 32; x0 >= 0; x0 -= 32) {
+    const int x = x0 + lane;
+    int pos = (x < W && s[x]) ? x : EDT_INF;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int y = y1 - i;
-      sv[i] = y >= 0 ? __ldg(s + (int64_t)y * W + x) : 0;
-      up[i] = y >= 0 ? g[(int64_t)y * W + x] : 0;
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_down_sync(0xffffffffu, pos, o); if (lane + o < 32) pos = min(pos, t); }
+    pos = min(pos, carry);
+    if (x < W) {
+      const int left = g[x];
+      const int dl = left <= -EDT_INF ? EDT_INF : x - left, dr = pos >= EDT_INF ? EDT_INF : pos - x;
+      const int d = min(dl, dr);
+      g[x] = d >= 32768 ? EDT_INF : d * d;
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int y = y1 - i;
-      if (y >= 0) {
-        d = sv[i] ? 0 : (d >= EDT_INF ? EDT_INF : d + 1);
-        const int best = min(up[i], d);
-        g[(int64_t)y * W + x] = best >= 32768 ? EDT_INF : best * best;
-      }
-    }
+    carry = __shfl_sync(0xffffffffu, pos, 0);
   }
 }
 
-__global__ void edt_rows_kernel(const int* __restrict__ g2, int H, int W, int* __restrict__ d2) {
-  extern __shared__ int row[];
-  const int y = blockIdx.x, m = blockIdx.y;
-  const int* g = g2 + ((int64_t)m * H + y) * W;
-  for (int x = threadIdx.x; x < W; x += blockDim.x) row[x] = g[x];
+__global__ void __launch_bounds__(256) edt_cols_kernel(const int* __restrict__ g2, int H, int W, int* __restrict__ d2) {
+  extern __shared__ int strip[];                      // [H][32]
+  const int x0 = blockIdx.x * 32, m = blockIdx.y;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5, nwy = blockDim.x >> 5;
+  const int x = x0 + lane;
+  const int* g = g2 + (int64_t)m * H * W;
+  for (int y = wy; y < H; y += nwy) strip[y * 32 + lane] = x < W ? g[(int64_t)y * W + x] : EDT_INF;
   __syncthreads();
-  for (int x = threadIdx.x; x < W; x += blockDim.x) {
-    int best = EDT_INF;
-    for (int xp = 0; xp < W; ++xp) {
-      int dx = x - xp;
-      int v = row[xp] + dx * dx;                      // EDT_INF + dx^2 stays below 2^31
-      best = min(best, v);
+  if (x >= W) return;
+  // blockIdx.z splits the rows so that the grid covers the GPU (the whole strip is still needed for the search)
+  const int rows_per = (H + gridDim.z - 1) / gridDim.z;
+  const int y_lo = blockIdx.z * rows_per, y_hi = min(H, y_lo + rows_per);
+  for (int y = y_lo + wy; y < y_hi; y += nwy) {
+    int best = strip[y * 32 + lane];
+    for (int dy = 1; dy < H; ++dy) {
+      const int dd = dy * dy;
+      if (dd >= best) break;                          // rows further away cannot improve the minimum
+      if (y - dy >= 0) best = min(best, strip[(y - dy) * 32 + lane] + dd);
+      if (y + dy < H) best = min(best, strip[(y + dy) * 32 + lane] + dd);
     }
     d2[((int64_t)m * H + y) * W + x] = best >= EDT_INF ? EDT_INF : best;
   }
 }
 
 static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int* scratch, cudaStream_t s) {
-  edt_cols_kernel<<<ceil_div(W * nmask, 128), 128, 0, s>>>(seed, H, W, nmask, scratch);
+  edt_rowscan_kernel<<<ceil_div((int64_t)H * nmask * 32, 256), 256, 0, s>>>(seed, H, W, nmask, scratch);
   OTVM_LAUNCH_CHECK();
-  int threads = W >= 256 ? 256 : (W >= 128 ? 128 : 64);
-  edt_rows_kernel<<<dim3(H, nmask), threads, W * sizeof(int), s>>>(scratch, H, W, d2);
+  const size_t smem = (size_t)H * 32 * sizeof(int);
+  if (smem > 200 * 1024) return OTVM_ERR_UNSUPPORTED;
+  static bool attr = false;
+  if (!attr) {
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(edt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  int ysplit = ceil_div(2 * sm_count(), ceil_div(W, 32) * nmask);
+  if (ysplit > 32) ysplit = 32;
+  if (ysplit < 1) ysplit = 1;
+  edt_cols_kernel<<<dim3(ceil_div(W, 32), nmask, ysplit), 256, smem, s>>>(scratch, H, W, d2);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
