@@ -158,10 +158,15 @@ def run_b200(args):
     ms_e2e = timed(e2e_step)
 
     # instrumented pass: device time per kernel family (CUDA events around every C-ABI call)
+    # Each instrumented frame is queued behind a ~25 ms device-side sleep so that the GPU never waits for the
+    # host between launches: the event pairs then bracket pure device execution (an idle GPU would stamp the
+    # start event early and charge the host-side launch latency to the kernel).
     prof_frames = min(4, args.steps)
     ops.PROFILER = ops.Profiler()
     for i in range(prof_frames):
+        torch.cuda._sleep(50_000_000)
         step(i, dev)
+        torch.cuda.synchronize()
     fam = ops.PROFILER.summary()
     ops.PROFILER = None
     pk = peaks()

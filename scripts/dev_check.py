@@ -9,3 +9,7 @@ for kind, prec, H, W in [("tempered", "fp32", 128, 128), ("default", "fp32", 128
             print(kind, prec, H, W, "frame", i, " ".join(f"{k}={v:.1e}" for k, v in e.items()), flush=True)
     except Exception as ex:
         import traceback; traceback.print_exc()
+
+rows = run_clip("tempered", "bf16", 256, 256, 3, with_mean=True)
+for i, e in enumerate(rows):
+    print("bf16 256 frame", i, " ".join(f"{k}={v[0]:.1e}/{v[1]:.1e}" for k, v in e.items()), flush=True)

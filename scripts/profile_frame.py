@@ -13,7 +13,10 @@ m(*fr[0], first_frame=True, **kw)
 for i in range(1, 10): m(*fr[i % 4], first_frame=False, **kw)
 ops.PROFILE_SHAPES = True; ops.PROFILER = ops.Profiler()
 n = 3
-for i in range(n): m(*fr[i % 4], first_frame=False, **kw)
+for i in range(n):
+    torch.cuda._sleep(50_000_000)
+    m(*fr[i % 4], first_frame=False, **kw)
+    torch.cuda.synchronize()
 s = ops.PROFILER.summary(); ops.PROFILER = None
 tot = sum(v["ms"] for v in s.values())
 print(f"total {tot/n:.3f} ms/frame")

@@ -5,7 +5,7 @@ import types
 
 import torch
 
-from util import ROOT, rel_err
+from util import ROOT, mean_err, rel_err
 
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 if ROOT not in sys.path:
@@ -40,8 +40,8 @@ def force_bank(model, oracle, H, W):
     bank.order = list(range(T))
 
 
-def compare_frame(model, oracle, out, ref, H, W, first):
-    """dict stage -> scale-relative max error for the frame just run by both"""
+def compare_frame(model, oracle, out, ref, H, W, first, rel_err=rel_err):
+    """dict stage -> scale-relative error (max by default, mean with rel_err=mean_err) for the frame just run by both"""
     eng = model.engine
     pl = eng.plan(H, W)
     b, tr = pl.bufs, oracle.trace
@@ -75,7 +75,7 @@ def tr_pad(x, Hp, Wp):
     return x
 
 
-def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=True):
+def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=True, with_mean=False):
     import otvm_oracle as O
     from otvm_b200.fixtures import make_frame
     model, sd = build_model(kind, precision)
@@ -87,7 +87,10 @@ def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=
         ref = oracle(a, fg, bg, **kw)
         out = model(a.cuda(), fg.cuda(), bg.cuda(), **kw)
         torch.cuda.synchronize()
-        rows.append(compare_frame(model, oracle, out, ref, H, W, i == 0))
+        e = compare_frame(model, oracle, out, ref, H, W, i == 0)
+        if with_mean:
+            e = {k: (v, m) for (k, v), m in zip(e.items(), compare_frame(model, oracle, out, ref, H, W, i == 0, rel_err=mean_err).values())}
+        rows.append(e)
         if teacher:
             force_bank(model, oracle, H, W)
     return rows

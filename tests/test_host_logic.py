@@ -1,0 +1,151 @@
+"""CPU-only checks of the host side: state-dict contract, weight packing, memory-bank policy, C ABI exports,
+clip sharding across ranks (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from util import ROOT
+
+
+def test_state_dict_contract():
+    """785 keys with the reference's names/shapes; strict load like eval.py:79"""
+    import types
+    import otvm_b200
+    from otvm_b200.fixtures import make_state_dict
+    from otvm_b200.spec import state_spec
+    spec = state_spec()
+    assert len(spec) == 785
+    assert spec["NET.encoder.conv1.weight"].shape == (64, 11, 7, 7)
+    assert spec["NET.refine.conv1.0.weight"].shape == (64, 73, 3, 3)
+    assert spec["NET.refine.pred.4.weight"].shape == (10, 16, 1, 1)
+    assert spec["trimap.model.Encoder_M.conv1_h.weight"].shape == (64, 16, 7, 7)
+    assert spec["trimap.model.KV_M_r4.Value.weight"].shape == (512, 1024, 3, 3)
+    assert sum(int(torch.tensor(e.shape).prod()) if e.shape else 1 for e in spec.values()) == 73949006
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4))
+    mt = otvm_b200.get_model_trimap(cfg, "Test", 12)
+    ma = otvm_b200.get_model_alpha(cfg, mt, "Test", 12)
+    sd = make_state_dict("tempered")
+    assert set(ma.state_dict()) == set(spec) == set(sd)
+    ma.load_state_dict(sd)                      # strict
+    with pytest.raises(RuntimeError):           # no CPU fallback: forward needs a CUDA device
+        if not torch.cuda.is_available():
+            ma.engine
+        else:
+            raise RuntimeError("gpu present")
+
+
+def test_fixture_weights_are_stable():
+    """name-keyed RandomState draws: the same bits here, in the golden generator and on the GPU box"""
+    from otvm_b200.fixtures import make_frame, make_state_dict
+    sd = make_state_dict("tempered")
+    w = sd["trimap.model.KV_Q_r4.Key.weight"]
+    assert abs(float(w.double().sum()) - float(make_state_dict("tempered")["trimap.model.KV_Q_r4.Key.weight"].double().sum())) == 0
+    a, fg, bg = make_frame(0, 3, 64, 96)
+    assert a.shape == (1, 1, 1, 64, 96) and fg.shape == (1, 1, 3, 64, 96)
+    assert 0 <= float(a.min()) and float(a.max()) <= 1 and 0 <= float(fg.min()) and float(fg.max()) < 255
+    assert ((a > 0) & (a < 1)).any() and (a == 0).any() and (a == 1).any()
+
+
+def test_weight_packing_matches_torch_semantics():
+    """BN folding, weight standardisation and the fused 22-channel Encoder_M stem against plain torch ops"""
+    import torch.nn.functional as F
+    from otvm_b200.engine import PackedWeights, _ws
+    from otvm_b200.fixtures import make_state_dict
+    sd = make_state_dict("default")
+    pw = PackedWeights(sd, torch.float32, "cpu")
+    g = torch.Generator().manual_seed(0)
+    # folded BN == conv -> batch_norm(eval)
+    p = "trimap.model.Encoder_Q.res3.0"
+    x = torch.randn(1, 256, 8, 8, generator=g)
+    want = F.batch_norm(F.conv2d(x, sd[p + ".downsample.0.weight"], None, 2), sd[p + ".downsample.1.running_mean"],
+                        sd[p + ".downsample.1.running_var"], sd[p + ".downsample.1.weight"],
+                        sd[p + ".downsample.1.bias"], False, 0.0, 1e-5)
+    w, b = pw.conv[p + ".downsample"]
+    got = F.conv2d(x, w.permute(0, 3, 1, 2), b, 2)
+    assert float((got - want).abs().max()) < 1e-4
+    # weight standardisation folded once == layers_WS.Conv2d.forward
+    w, b = pw.conv["NET.encoder.layer1.0.conv2"]
+    assert float((w.permute(0, 3, 1, 2) - _ws(sd["NET.encoder.layer1.0.conv2.weight"])).abs().max()) == 0
+    # five Encoder_M stems summed (STM.py:63,67) == one conv over the concatenated 22 channels (+2 zero pads)
+    e = "trimap.model.Encoder_M"
+    f, m, o, a, h = (torch.randn(1, c, 16, 16, generator=g) for c in (3, 1, 1, 1, 16))
+    conv = lambda n, t: F.conv2d(t, sd[f"{e}.{n}.weight"], None, 2, 3)
+    pre = conv("conv1", f) + conv("conv1_m", m) + conv("conv1_o", o) + conv("conv1_a", a) + conv("conv1_h", h)
+    want = F.batch_norm(pre, sd[e + ".bn1.running_mean"], sd[e + ".bn1.running_var"], sd[e + ".bn1.weight"],
+                        sd[e + ".bn1.bias"], False, 0.0, 1e-5)
+    w, b = pw.conv[e + ".stem"]
+    xin = torch.cat([f, m, o, a, h, torch.zeros(1, w.shape[3] - 22, 16, 16)], 1)
+    got = F.conv2d(xin, w.permute(0, 3, 1, 2), b, 2, 3)
+    assert float((got - want).abs().max()) < 1e-4
+
+
+def _reference_policy(events, max_n):
+    """models/alpha/model.py:472-493 on a list of frame ids"""
+    mem = None
+    for i, (first, memorize) in enumerate(events):
+        new = [i]
+        if max_n == 0:
+            if first:
+                mem = new
+        elif max_n == 1:
+            mem = new
+        else:
+            if first:
+                mem = new
+            elif memorize:
+                mem = mem + new
+            else:
+                mem = (mem + new) if len(mem) == 1 else (mem[:-1] + new)
+            if len(mem) > max_n:
+                mem = mem[:1] + mem[2:]
+    return mem
+
+
+@pytest.mark.parametrize("max_n", [0, 1, 2, 3, 5, 8])
+def test_memory_bank_policy_matches_reference(max_n):
+    """in-place slot replacement holds exactly the frames the reference's torch.cat policy would hold"""
+    import random
+    from otvm_b200.engine import MemoryBank
+    rng = random.Random(max_n)
+    bank = MemoryBank(hw=4, cap=16, dtype=torch.float32, device="cpu")
+    content = {}
+    events = [(True, True)] + [(False, rng.random() < 0.4) for _ in range(60)]
+    for i, (first, memorize) in enumerate(events):
+        if first:
+            bank.reset()
+        slot, order = bank.next_slot(first, memorize, max_n)
+        if slot is not None:
+            content[slot] = i
+            bank.order = order
+        want = _reference_policy(events[:i + 1], max_n)
+        assert [content[s] for s in bank.order] == want, (i, bank.order, want)
+        assert len(set(bank.order)) == len(bank.order) and all(s < 16 for s in bank.order)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """the shared library loads without a GPU and exports exactly what include/otvm_b200.h declares"""
+    from otvm_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "otvm_b200.h")).read()
+    declared = set(re.findall(r"OTVM_API\s+[\w\s\*]+?\b(otvm_\w+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.otvm_version() == 1
+    assert lib.otvm_strerror(-3).decode().startswith("unsupported")
+    assert ctypes.sizeof(_lib.ConvParams) == 168 and ctypes.sizeof(_lib.ReadParams) == 104   # sizeof() of the C structs
+
+
+def test_clip_sharding_two_ranks_gloo():
+    """bench.py's multi-GPU layout: clip c -> rank c mod N, no data-path collective; only the timing max-reduce"""
+    env = dict(os.environ, OTVM_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_gloo_worker.py")],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert "OK 2" in r.stdout, r.stdout + r.stderr

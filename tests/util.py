@@ -26,3 +26,11 @@ def frac_off(got, want, tol):
     want = torch.as_tensor(want).double().cpu()
     scale = max(float(want.abs().max()), 1e-12)
     return float(((got - want).abs() > tol * scale).double().mean())
+
+
+def mean_err(got, want):
+    """mean|got-want| / max|want| — robust companion of rel_err for bf16 paths (a few pixels flip trimap class)."""
+    got = torch.as_tensor(np.asarray(got) if not torch.is_tensor(got) else got).double().cpu()
+    want = torch.as_tensor(np.asarray(want) if not torch.is_tensor(want) else want).double().cpu()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    return float((got - want).abs().mean() / max(float(want.abs().max()), 1e-12))
