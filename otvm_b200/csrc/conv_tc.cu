@@ -23,7 +23,7 @@ using namespace tc;
 struct ConvTcArgs {
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil, stride;
   int TW, TH, tiles_x, tiles_y;
-  int KC, nchunk, nstage;
+  int KC, nchunk, nstage, ksub; // nstage ring groups of ksub K-chunks each
   int k_per_split;             // K iterations per blockIdx.z slice (split-K); == num_k without split
   int64_t split_stride;        // elements between the fp32 partial outputs of consecutive K slices
   uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
+  int4* ktab = reinterpret_cast<int4*>(sbias + 128);                 // [num_k] TMA coordinates per K chunk (16 B aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 : nullptr;
+  long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
   if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
@@ -100,51 +101,84 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < 2 * 128; i += kConvThreads) sstat[i] = 0.f;
   for (int i = threadIdx.x; i < BN; i += kConvThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+  // The producer threads must not spend their (serial) instruction stream on div/mod: every thread fills part of
+  // a per-CTA table of TMA coordinates up front.
+  for (int i = threadIdx.x; i < num_k; i += kConvThreads) {
+    const int tap = (it0 + i) / a.nchunk, chunk = (it0 + i) - tap * a.nchunk;
+    const int ky = tap / a.KW, kx = tap - ky * a.KW;
+    ktab[i] = make_int4(chunk * a.KC, x0 * a.stride - a.pad + kx * a.dil, y0 * a.stride - a.pad + ky * a.dil,
+                        tap * a.Cin + chunk * a.KC);
+  }
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      for (int it = 0; it < num_k; ++it) {
-        const int s = it % a.nstage;
-        const uint32_t ph = (it / a.nstage) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        const int tap = (it0 + it) / a.nchunk, chunk = (it0 + it) - tap * a.nchunk;
-        const int ky = tap / a.KW, kx = tap - ky * a.KW;
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], a.a_bytes + (uint32_t)(BN * a.KC * 2));
-        tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, x0 * a.stride - a.pad + kx * a.dil,
-                    y0 * a.stride - a.pad + ky * a.dil, n_img);
-        tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
-        if (dbg && it == 0) dbg[2] = clock64();
+  // NOTE on the single-thread loops below: one thread issuing a dependent scalar chain is the pipeline's critical
+  // path (measured ~830 cycles per K iteration with runtime div/mod for the stage / tap / chunk indices, and ~430
+  // when all 32 lanes polled the mbarrier, vs 256 cycles of MMA work), so indices are carried incrementally and
+  // exactly one thread per role runs its loop.
+  if (warp == 0 || warp == 2) {
+    // ===== TMA producers: warp 0 loads the activation boxes, warp 2 the weight boxes (it joins the epilogue
+    // afterwards).  Each ring slot ("group") holds KSUB K-chunks behind ONE full/empty barrier pair, so the
+    // ~400-cycle wait/arrive/issue latency of a single thread is paid once per KSUB chunks.  The A-side thread posts
+    // the expected byte count of the whole group; a B box landing first only makes the transaction count
+    // transiently negative, the phase cannot complete before the A-side arrival. =====
+    const bool load_a = warp == 0;
+    int g = 0; uint32_t ph = 0;
+    const uint32_t sub_tx = a.a_bytes + (uint32_t)(BN * a.KC * 2);
+    for (int it = 0; it < num_k; it += a.ksub) {
+      const int nsub = min(a.ksub, num_k - it);
+      mbar_wait(&empty_bar[g], ph ^ 1);
+      if (elect_one()) {
+        uint8_t* sa = smem + (size_t)g * a.ksub * stage_bytes;
+        if (load_a) mbar_arrive_expect_tx(&full_bar[g], sub_tx * nsub);
+        for (int u = 0; u < nsub; ++u) {
+          const int4 co = ktab[it + u];                     // {channel0, x, y, weight k0} of this K chunk
+          if (load_a) tma_load_4d(sa, &tmA, &full_bar[g], co.x, co.y, co.z, n_img);
+          else tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[g], co.w, n0);
+          sa += stage_bytes;
+        }
+        if (dbg && load_a && it == 0) dbg[2] = clock64();
+        if (dbg && load_a && it < 16 * a.ksub) dbg[32 + it / a.ksub] = clock64();
       }
+      __syncwarp();
+      if (++g == a.nstage) { g = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one elected thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
-      const int ksteps = a.KC / 16;
-      for (int it = 0; it < num_k; ++it) {
-        const int s = it % a.nstage;
-        const uint32_t ph = (it / a.nstage) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tcgen05_after_sync();
+    // ===== MMA issuer (one elected thread); descriptors are advanced by adding byte offsets >> 4 to the low word =====
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+    const int ksteps = a.KC / 16;
+    const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
+    const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
+    const uint32_t stage16 = stage_bytes >> 4;
+    int g = 0; uint32_t ph = 0, goff = 0;
+    for (int it = 0; it < num_k; it += a.ksub) {
+      const int nsub = min(a.ksub, num_k - it);
+      mbar_wait(&full_bar[g], ph);
+      tcgen05_after_sync();
+      if (elect_one()) {
         if (dbg && it == 0) dbg[3] = clock64();
-        const uint32_t sa = base + (uint32_t)s * stage_bytes;
-        const uint64_t adesc = make_smem_desc(sa, a.sbo, a.layout_type);
-        const uint64_t bdesc = make_smem_desc(sa + a.a_bytes, a.sbo, a.layout_type);
-        for (int k = 0; k < ksteps; ++k)                     // +32 bytes (>>4 = 2) per UMMA_K=16 inside the swizzle span
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
-        umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
+        if (dbg && it < 16 * a.ksub) dbg[16 + it / a.ksub] = clock64();
+        uint64_t ad = adesc0 + goff, bd = bdesc0 + goff;
+        for (int u = 0; u < nsub; ++u) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | u | k) != 0);
+          ad += stage16; bd += stage16;
+        }
+        umma_commit(&empty_bar[g]);                          // frees the group when these MMAs have read it
+        if (it + a.ksub >= num_k) {
+          umma_commit(accum_bar);                            // accumulator complete
+          if (dbg) dbg[4] = clock64();
+        }
       }
-      umma_commit(accum_bar);                                // accumulator complete
-      if (dbg) dbg[4] = clock64();
+      __syncwarp();
+      goff += stage16 * a.ksub;
+      if (++g == a.nstage) { g = 0; ph ^= 1; goff = 0; }
     }
-  } else {
+  }
+  if (warp >= 2) {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
     // Compile-time variants (EPI) keep the per-element instruction count low: the three store paths and the
     // residual paths would otherwise all be issued as predicated-off instructions (measured: 1800 SASS
@@ -422,7 +456,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
   conv_tc_kernel<BN, GN, EPI><<<grid, kConvThreads, smem, s>>>(tmA, tmB, tmO, tmR, a);
@@ -458,14 +492,19 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.sbo = 8u * a.KC * 2;
   a.layout_type = a.KC == 64 ? 2u : a.KC == 32 ? 4u : 6u;
   const uint32_t stage = a.a_bytes + a.b_bytes;
-  // two CTAs per SM (<= 96 KB of stages each) when the grid is larger than one wave; a grid that fits in one
+  // two CTAs per SM (<= 96 KB of ring each) when the grid is larger than one wave; a grid that fits in one
   // wave is latency-bound instead, so it gets a deeper ring (up to ~190 KB, one CTA per SM)
   const int64_t ctas = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
   const uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
-  int nstage = (int)(budget / stage);
-  if (nstage > 8) nstage = 8;
   const int num_k = a.KH * a.KW * a.nchunk;
-  if (nstage > num_k) nstage = num_k < 2 ? 2 : num_k;
+  // K-chunks per barrier group: as many as keep >= 3 groups in the ring (<= 4, <= num_k)
+  int ksub = 1;
+  while (ksub < 4 && ksub * 2 <= num_k && (uint32_t)(ksub * 2 * 3) * stage <= budget) ksub *= 2;
+  a.ksub = ksub;
+  int nstage = (int)(budget / (stage * ksub));
+  if (nstage > 8) nstage = 8;
+  const int ngroups_total = ceil_div(num_k, ksub);
+  if (nstage > ngroups_total) nstage = ngroups_total < 2 ? 2 : ngroups_total;
   a.nstage = nstage;
   // split-K: a grid that fills less than half of the SMs walks K serially at TMA/L2 latency; slice K across
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
@@ -481,7 +520,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.k_per_split = ceil_div(num_k, nsplit);
   nsplit = ceil_div(num_k, a.k_per_split);
   a.split_stride = Mtot * p->Cout;
-  if (a.nstage > a.k_per_split) a.nstage = a.k_per_split < 2 ? 2 : a.k_per_split;
+  { const int gps = ceil_div(a.k_per_split, a.ksub); if (a.nstage > gps) a.nstage = gps < 2 ? 2 : gps; }
   a.bias = p->bias; a.out = p->out; a.out_ps = p->out_ps; a.out_cs = p->out_cs;
   a.res = static_cast<const bf16*>(p->res); a.res_ld = p->res_ld;
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
@@ -533,8 +572,8 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     ConvTcArgs b = a;                       // raw fp32 partial tiles into the workspace, epilogue deferred
     b.bias = nullptr; b.out = p->workspace; b.out_ps = p->Cout; b.out_cs = 1; b.res = nullptr; b.out_relu = nullptr;
     b.act = OTVM_ACT_NONE; b.out_f32 = 1; b.gn_stats = nullptr;
-    const size_t smem_s = (size_t)a.nstage * stage + 1024 + (2 * a.nstage + 1) * 8 + 16 + (2 * 128 + 128) * sizeof(float);
-    b.aux_off = (uint32_t)((size_t)a.nstage * stage);
+    const size_t smem_s = (size_t)a.nstage * a.ksub * stage + 1024 + 16 * 8 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)a.k_per_split * 16;
+    b.aux_off = (uint32_t)((size_t)a.nstage * a.ksub * stage);
     int rc;
     switch (bn) {
       case 128: rc = dispatch_conv_tc<128>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
@@ -552,12 +591,12 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     OTVM_LAUNCH_CHECK();
     return OTVM_OK;
   }
-  size_t pipe = (size_t)nstage * stage;
+  size_t pipe = (size_t)nstage * ksub * stage;
   const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
   size_t need = tma_store ? staging : 0;
   if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
-  const size_t smem = pipe + 1024 + (2 * nstage + 1) * 8 + 16 + (2 * 128 + 128) * sizeof(float);
+  const size_t smem = pipe + 1024 + 16 * 8 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
   a.aux_off = (uint32_t)pipe;
   const bool gn = p->gn_stats != nullptr;
   const int epi = conv_tc_epi(p, bn);

@@ -11,6 +11,28 @@ static inline int grid_for(int64_t work_items, int block) {
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
+// 8 consecutive elements <-> float[8] (one 16-byte bf16 access or two 16-byte fp32 accesses)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (n, group) sum and sum of squares in fp64 (fp32 partials per thread/block).
 // ------------------------------------------------------------------------------------------------------
@@ -46,50 +68,58 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-template <typename T>
+// GroupNorm apply: every thread owns 8 fixed channels (scale/shift live in registers) and walks the pixels with
+// 16-byte accesses, 4 pixels in flight per thread; a warp touches 512 contiguous bytes of one or more pixels.
+template <typename T, bool RES>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
                                                        const T* __restrict__ res, int64_t res_ld, int act,
                                                        T* __restrict__ out, int64_t out_ld) {
-  extern __shared__ float sc_sh[];               // [C] scale, [C] shift
-  __shared__ float g_mean[32], g_rstd[32];
-  float* sc = sc_sh; float* sh = sc_sh + C;
   const int n = blockIdx.y;
+  const int tpp = C >> 3;                         // threads per pixel (divides 256)
+  const int cv = (threadIdx.x % tpp) * 8;
+  const int ppb = 256 / tpp;                      // pixels per block pass
   const int cg = C >> 5;
-  if (threadIdx.x < 32) {                        // fp64 only for the 32 group moments (E[x^2] - E[x]^2 cancels)
+  float sc[8], sh[8];
+  {
     const double cnt = (double)HW * cg;
-    const double mean = stats[(n * 32 + threadIdx.x) * 2] / cnt;
-    const double var = stats[(n * 32 + threadIdx.x) * 2 + 1] / cnt - mean * mean;
-    g_mean[threadIdx.x] = (float)mean;
-    g_rstd[threadIdx.x] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cg;
-    const float s = g_rstd[g] * gamma[c];
-    sc[c] = s; sh[c] = beta[c] - g_mean[g] * s;
-  }
-  __syncthreads();
-  const int c4n = C >> 2;
-  const int64_t total = HW * c4n;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
-    int64_t pix = idx / c4n; int c = (int)(idx - pix * c4n) * 4;
-    float v[4];
-    load4(x + ((int64_t)n * HW + pix) * ld + c, v);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = fmaf(v[j], sc[c + j], sh[c + j]);
-    if (res) {
-      float r[4];
-      load4(res + ((int64_t)n * HW + pix) * res_ld + c, r);
+    for (int j = 0; j < 8; ++j) {
+      const int g = (cv + j) / cg;
+      const double mean = stats[(n * 32 + g) * 2] / cnt;
+      const double var = stats[(n * 32 + g) * 2 + 1] / cnt - mean * mean;      // fp64: E[x^2] - E[x]^2 cancels
+      const float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+      sc[j] = rstd * gamma[cv + j];
+      sh[j] = beta[cv + j] - (float)mean * sc[j];
+    }
+  }
+  const float slope = act == OTVM_ACT_NONE ? 1.f : act == OTVM_ACT_RELU ? 0.f : 0.01f;
+  const T* xb = x + (int64_t)n * HW * ld + cv;
+  const T* rb = RES ? res + (int64_t)n * HW * res_ld + cv : nullptr;
+  T* ob = out + (int64_t)n * HW * out_ld + cv;
+  const int64_t stride = (int64_t)gridDim.x * ppb;
+  for (int64_t p0 = (int64_t)blockIdx.x * ppb + threadIdx.x / tpp; p0 < HW; p0 += 4 * stride) {
+    float v[4][8], r[4][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] += r[j];
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < HW) { load8(xb + p * ld, v[u]); if (RES) load8(rb + p * res_ld, r[u]); }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], act);
-    store4(out + ((int64_t)n * HW + pix) * out_ld + c, v);
+    for (int u = 0; u < 4; ++u) {
+      const int64_t p = p0 + u * stride;
+      if (p < HW) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(v[u][j], sc[j], sh[j]);
+          if (RES) y += r[u][j];
+          v[u][j] = fmaxf(y, 0.f) + slope * fminf(y, 0.f);
+        }
+        store8(ob + p * out_ld, v[u]);
+      }
+    }
   }
 }
 
@@ -112,11 +142,18 @@ template <typename T>
 static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const double* stats, const float* gamma,
                       const float* beta, float eps, const void* res, int64_t res_ld, int act, void* out,
                       int64_t out_ld, cudaStream_t s) {
-  int64_t total = (int64_t)HW * (C / 4);
-  dim3 grid(grid_for(total, 256), N);
-  gn_apply_kernel<T><<<grid, 256, 2 * C * sizeof(float), s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma,
-                                                             beta, eps, static_cast<const T*>(res), res_ld, act,
-                                                             static_cast<T*>(out), out_ld);
+  const int tpp = C / 8, ppb = 256 / tpp;
+  int64_t blocks = ((int64_t)HW + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4);
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  dim3 grid((unsigned)blocks, N);
+  if (res)
+    gn_apply_kernel<T, true><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
+                                                  static_cast<const T*>(res), res_ld, act, static_cast<T*>(out), out_ld);
+  else
+    gn_apply_kernel<T, false><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
+                                                   nullptr, 0, act, static_cast<T*>(out), out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -170,6 +207,45 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
       store4(out_relu + pix * out_relu_ld + c, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample8_kernel(const T* __restrict__ in, int64_t in_ld, int Hi, int Wi,
+                                                        int C, int Ho, int Wo, float sy, float sx,
+                                                        const T* __restrict__ add, int64_t add_ld,
+                                                        T* __restrict__ out, int64_t out_ld,
+                                                        T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+  const int c8n = C >> 3;
+  const int64_t total = (int64_t)N * Ho * Wo * c8n;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    int64_t pix = idx / c8n; int c = (int)(idx - pix * c8n) * 8;
+    int n = (int)(pix / ((int64_t)Ho * Wo));
+    int r = (int)(pix - (int64_t)n * Ho * Wo);
+    int oy = r / Wo, ox = r - oy * Wo;
+    int y0, y1, x0, x1; float ly, lx;
+    src_index(sy, oy, Hi, y0, y1, ly);
+    src_index(sx, ox, Wi, x0, x1, lx);
+    const T* b = in + (int64_t)n * Hi * Wi * in_ld + c;
+    float v00[8], v01[8], v10[8], v11[8], o[8], a8[8];
+    load8(b + ((int64_t)y0 * Wi + x0) * in_ld, v00);
+    load8(b + ((int64_t)y0 * Wi + x1) * in_ld, v01);
+    load8(b + ((int64_t)y1 * Wi + x0) * in_ld, v10);
+    load8(b + ((int64_t)y1 * Wi + x1) * in_ld, v11);
+    if (add) load8(add + pix * add_ld + c, a8);
+    const float hy = 1.f - ly, hx = 1.f - lx;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
+      if (add) o[j] = a8[j] + o[j];
+    }
+    store8(out + pix * out_ld + c, o);
+    if (out_relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+      store8(out_relu + pix * out_relu_ld + c, o);
     }
   }
 }
@@ -337,8 +413,9 @@ extern "C" int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, i
                              const double* stats, const float* gamma, const float* beta, float eps,
                              const void* res, int64_t res_ld, int32_t act, void* out, int64_t out_ld,
                              void* stream) {
-  if (!x || !stats || !out || C % 32 != 0 || ld % 4 != 0 || out_ld % 4 != 0 || (res && res_ld % 4 != 0))
+  if (!x || !stats || !out || C % 64 != 0 || C > 2048 || ld % 8 != 0 || out_ld % 8 != 0 || (res && res_ld % 8 != 0))
     return OTVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res)) & 15) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DISPATCH_DTYPE(dtype,
                  gn_apply_t<float>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, s),
@@ -358,6 +435,19 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
         out_nchw_f32 == 1);
   } else {
     if (in_ld % 4 || out_ld % 4 || (add && add_ld % 4) || (out_relu && out_relu_ld % 4)) return OTVM_ERR_ARG;
+    const bool wide = C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 && (!add || add_ld % 8 == 0) &&
+                      (!out_relu || out_relu_ld % 8 == 0) &&
+                      !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add) |
+                         reinterpret_cast<uintptr_t>(out_relu)) & 15);
+    if (wide) {
+      int64_t total8 = (int64_t)N * Ho * Wo * (C / 8);
+      upsample8_kernel<T><<<grid_for(total8, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
+                                                                sy, sx, static_cast<const T*>(add), add_ld,
+                                                                static_cast<T*>(out), out_ld,
+                                                                static_cast<T*>(out_relu), out_relu_ld, N);
+      OTVM_LAUNCH_CHECK();
+      return OTVM_OK;
+    }
     int64_t total = (int64_t)N * Ho * Wo * (C / 4);
     upsample_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
                                                            sy, sx, static_cast<const T*>(add), add_ld,
