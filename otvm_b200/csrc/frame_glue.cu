@@ -85,7 +85,7 @@ __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, cons
 //   pass 1 (rows)   : g2[y][x] = squared distance to the nearest seed in row y -- one warp per row, the nearest seed
 //                     to the left / right comes from a warp max / min scan carried across 32-pixel chunks
 //   pass 2 (columns): d2[y][x] = min_y' (y-y')^2 + g2[y'][x] -- a 32-column strip of g2 sits in shared memory and
-//                     every pixel searches outwards from its own row until dy^2 can no longer beat the best value
+//                     every pixel takes the exhaustive minimum over its column (integer, branch-free)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) edt_rowscan_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask,
                                                           int* __restrict__ g2) {
@@ -134,13 +134,18 @@ __global__ void __launch_bounds__(256) edt_cols_kernel(const int* __restrict__ g
   const int rows_per = (H + gridDim.z - 1) / gridDim.z;
   const int y_lo = blockIdx.z * rows_per, y_hi = min(H, y_lo + rows_per);
   for (int y = y_lo + wy; y < y_hi; y += nwy) {
-    int best = strip[y * 32 + lane];
-    for (int dy = 1; dy < H; ++dy) {
-      const int dd = dy * dy;
-      if (dd >= best) break;                          // rows further away cannot improve the minimum
-      if (y - dy >= 0) best = min(best, strip[(y - dy) * 32 + lane] + dd);
-      if (y + dy < H) best = min(best, strip[(y + dy) * 32 + lane] + dd);
+    // branch-free exhaustive minimum over the column (masks with a handful of seeds make every early-exit search
+    // degenerate into a divergent full scan, which measured 6x slower than this)
+    int best = EDT_INF;
+    int yp = 0;
+    for (; yp + 8 <= H; yp += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int dy = y - (yp + u);
+        best = min(best, strip[(yp + u) * 32 + lane] + dy * dy);
+      }
     }
+    for (; yp < H; ++yp) { const int dy = y - yp; best = min(best, strip[yp * 32 + lane] + dy * dy); }
     d2[((int64_t)m * H + y) * W + x] = best >= EDT_INF ? EDT_INF : best;
   }
 }

@@ -82,18 +82,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   const int cv = (threadIdx.x % tpp) * 8;
   const int ppb = 256 / tpp;                      // pixels per block pass
   const int cg = C >> 5;
-  float sc[8], sh[8];
-  {
+  __shared__ float g_mean[32], g_rstd[32];
+  if (threadIdx.x < 32) {                         // fp64 only for the 32 group moments (E[x^2] - E[x]^2 cancels)
     const double cnt = (double)HW * cg;
+    const double mean = stats[(n * 32 + threadIdx.x) * 2] / cnt;
+    const double var = stats[(n * 32 + threadIdx.x) * 2 + 1] / cnt - mean * mean;
+    g_mean[threadIdx.x] = (float)mean;
+    g_rstd[threadIdx.x] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+  }
+  __syncthreads();
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (cv + j) / cg;
-      const double mean = stats[(n * 32 + g) * 2] / cnt;
-      const double var = stats[(n * 32 + g) * 2 + 1] / cnt - mean * mean;      // fp64: E[x^2] - E[x]^2 cancels
-      const float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
-      sc[j] = rstd * gamma[cv + j];
-      sh[j] = beta[cv + j] - (float)mean * sc[j];
-    }
+  for (int j = 0; j < 8; ++j) {
+    const int g = (cv + j) / cg;
+    sc[j] = g_rstd[g] * gamma[cv + j];
+    sh[j] = beta[cv + j] - g_mean[g] * sc[j];
   }
   const float slope = act == OTVM_ACT_NONE ? 1.f : act == OTVM_ACT_RELU ? 0.f : 0.01f;
   const T* xb = x + (int64_t)n * HW * ld + cv;
