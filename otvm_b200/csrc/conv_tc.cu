@@ -75,7 +75,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
-  int4* ktab = reinterpret_cast<int4*>(sbias + 128);                 // [num_k] TMA coordinates per K chunk (16 B aligned)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -101,14 +100,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
   for (int i = threadIdx.x; i < 2 * 128; i += kConvThreads) sstat[i] = 0.f;
   for (int i = threadIdx.x; i < BN; i += kConvThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
-  // The producer threads must not spend their (serial) instruction stream on div/mod: every thread fills part of
-  // a per-CTA table of TMA coordinates up front.
-  for (int i = threadIdx.x; i < num_k; i += kConvThreads) {
-    const int tap = (it0 + i) / a.nchunk, chunk = (it0 + i) - tap * a.nchunk;
-    const int ky = tap / a.KW, kx = tap - ky * a.KW;
-    ktab[i] = make_int4(chunk * a.KC, x0 * a.stride - a.pad + kx * a.dil, y0 * a.stride - a.pad + ky * a.dil,
-                        tap * a.Cin + chunk * a.KC);
-  }
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
@@ -126,25 +117,30 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     // the expected byte count of the whole group; a B box landing first only makes the transaction count
     // transiently negative, the phase cannot complete before the A-side arrival. =====
     const bool load_a = warp == 0;
-    int g = 0; uint32_t ph = 0;
-    const uint32_t sub_tx = a.a_bytes + (uint32_t)(BN * a.KC * 2);
-    for (int it = 0; it < num_k; it += a.ksub) {
-      const int nsub = min(a.ksub, num_k - it);
-      mbar_wait(&empty_bar[g], ph ^ 1);
+    int s = 0; uint32_t ph = 0;
+    int tap = it0 / a.nchunk, chunk = it0 - tap * a.nchunk;
+    int ky = tap / a.KW, kx = tap - ky * a.KW;
+    const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
+    const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
+    // The loop body is kept minimal and warp-uniform (elected lane issues): the serial instruction stream of this
+    // warp is the pipeline's critical path.  Measured per-iteration periods of variants of this loop: runtime
+    // div/mod indices 830 cycles, coordinate table in smem 700, nested K-chunk groups 870, this form 425.
+    for (int it = 0; it < num_k; ++it) {
+      mbar_wait(&empty_bar[s], ph ^ 1);
       if (elect_one()) {
-        uint8_t* sa = smem + (size_t)g * a.ksub * stage_bytes;
-        if (load_a) mbar_arrive_expect_tx(&full_bar[g], sub_tx * nsub);
-        for (int u = 0; u < nsub; ++u) {
-          const int4 co = ktab[it + u];                     // {channel0, x, y, weight k0} of this K chunk
-          if (load_a) tma_load_4d(sa, &tmA, &full_bar[g], co.x, co.y, co.z, n_img);
-          else tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[g], co.w, n0);
-          sa += stage_bytes;
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        if (load_a) {
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, cx + kx * a.dil, cy + ky * a.dil, n_img);
+          if (dbg && it == 0) dbg[2] = clock64();
+          if (dbg && it < 16) dbg[32 + it] = clock64();
+        } else {
+          tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
         }
-        if (dbg && load_a && it == 0) dbg[2] = clock64();
-        if (dbg && load_a && it < 16 * a.ksub) dbg[32 + it / a.ksub] = clock64();
       }
       __syncwarp();
-      if (++g == a.nstage) { g = 0; ph ^= 1; }
+      if (++s == a.nstage) { s = 0; ph ^= 1; }
+      if (++chunk == a.nchunk) { chunk = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one elected thread); descriptors are advanced by adding byte offsets >> 4 to the low word =====
@@ -153,29 +149,25 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
     const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
     const uint32_t stage16 = stage_bytes >> 4;
-    int g = 0; uint32_t ph = 0, goff = 0;
-    for (int it = 0; it < num_k; it += a.ksub) {
-      const int nsub = min(a.ksub, num_k - it);
-      mbar_wait(&full_bar[g], ph);
+    int s = 0; uint32_t ph = 0, soff = 0;
+    for (int it = 0; it < num_k; ++it) {
+      mbar_wait(&full_bar[s], ph);
       tcgen05_after_sync();
       if (elect_one()) {
         if (dbg && it == 0) dbg[3] = clock64();
-        if (dbg && it < 16 * a.ksub) dbg[16 + it / a.ksub] = clock64();
-        uint64_t ad = adesc0 + goff, bd = bdesc0 + goff;
-        for (int u = 0; u < nsub; ++u) {
-          for (int k = 0; k < ksteps; ++k)
-            umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (it | u | k) != 0);
-          ad += stage16; bd += stage16;
-        }
-        umma_commit(&empty_bar[g]);                          // frees the group when these MMAs have read it
-        if (it + a.ksub >= num_k) {
+        if (dbg && it < 16) dbg[16 + it] = clock64();
+        const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+        umma_bf16(tmem_base, ad, bd, idesc, it != 0);
+        for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+        umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
+        if (it == num_k - 1) {
           umma_commit(accum_bar);                            // accumulator complete
           if (dbg) dbg[4] = clock64();
         }
       }
       __syncwarp();
-      goff += stage16 * a.ksub;
-      if (++g == a.nstage) { g = 0; ph ^= 1; goff = 0; }
+      soff += stage16;
+      if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
     }
   }
   if (warp >= 2) {
@@ -497,9 +489,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   const int64_t ctas = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
   const uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
   const int num_k = a.KH * a.KW * a.nchunk;
-  // K-chunks per barrier group: as many as keep >= 3 groups in the ring (<= 4, <= num_k)
-  int ksub = 1;
-  while (ksub < 4 && ksub * 2 <= num_k && (uint32_t)(ksub * 2 * 3) * stage <= budget) ksub *= 2;
+  int ksub = 1;                            // (K-chunk groups per barrier were measured slower; kept at 1)
   a.ksub = ksub;
   int nstage = (int)(budget / (stage * ksub));
   if (nstage > 8) nstage = 8;
@@ -621,16 +611,21 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides) {
+int make_tmap(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return OTVM_ERR_UNSUPPORTED;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? OTVM_OK : OTVM_ERR_ARG;
+}
+
+int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box, CUtensorMapSwizzle swz, const uint32_t* elem_strides) {
+  return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swz, elem_strides);
 }
 
 }  // namespace otvm

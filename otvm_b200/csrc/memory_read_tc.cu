@@ -33,15 +33,24 @@ constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256
 constexpr int kReadThreads = 192;
 constexpr float kLazyLog2 = 8.f;
 
+// 2^x on the SFU (ex2.approx.ftz): relative error ~2^-22, far below the bf16 rounding of P
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct ReadTcArgs {
   int M, HW, Do, nsplit, blocks_per_split;
   float scale_log2;
   float* o_part; float* ml_part;
+  long long* dbg;             // dev: per-CTA clock64 timestamps (NULL in production)
 };
 
 __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                          const __grid_constant__ CUtensorMap tmK,
                                                                          const __grid_constant__ CUtensorMap tmV,
+                                                                         const __grid_constant__ CUtensorMap tmO,
                                                                          const ReadTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -61,6 +70,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
+  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
   const int q0 = blockIdx.x * TQ, c0 = blockIdx.y * TDV, split = blockIdx.z;
   const int nb_total = (a.M + TKB - 1) / TKB;
   const int kb0 = split * a.blocks_per_split;
@@ -83,6 +94,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + TDV;
+  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -149,6 +161,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tcgen05_after_sync();
+      if (dbg && threadIdx.x == 64 && j < 24) dbg[8 + j] = clock64();
       uint32_t raw[2][32];
       tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB, raw[0]);
       tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB + 32, raw[1]);
@@ -160,10 +173,18 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       float sc[64];
       float mx = -CUDART_INF_F;
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float v = __uint_as_float(raw[i >> 5][i & 31]) * a.scale_log2;
-        v = (key0 + i < a.M) ? v : -CUDART_INF_F;
-        sc[i] = v; mx = fmaxf(mx, v);
+      for (int i = 0; i < 64; ++i) { sc[i] = __uint_as_float(raw[i >> 5][i & 31]) * a.scale_log2; }
+      if (key0 + TKB > a.M) {                              // ragged last block only (block-uniform branch)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) sc[i] = (key0 + i < a.M) ? sc[i] : -CUDART_INF_F;
+      }
+      {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
+        float m8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m8[i] = sc[i];
+#pragma unroll
+        for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], sc[i]);
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       }
       // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
       const bool grow = mx > m_used + kLazyLog2;
@@ -188,46 +209,61 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         l_sum *= alpha;
         m_used = m_new;
       }
-      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);        // PV of block j-2 finished reading P[b]
+      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);   // PV of block j-2 finished reading P[b]
       uint8_t* prow = sP + (size_t)b * kPBytes;
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial sums (no 64-deep FADD chain)
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {                     // 8 chunks of 8 keys (16 bytes)
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = exp2f(sc[ch * 8 + 2 * e] - m_used), p1 = exp2f(sc[ch * 8 + 2 * e + 1] - m_used);
+          const float p0 = fast_exp2(sc[ch * 8 + 2 * e] - m_used), p1 = fast_exp2(sc[ch * 8 + 2 * e + 1] - m_used);
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          l_sum += __low2float(h) + __high2float(h);       // the sum uses the rounded weights the MMA will see
+          l4[e] += __low2float(h) + __high2float(h);       // the sum uses the rounded weights the MMA will see
           pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         uint32_t off = (uint32_t)r * 128u + (uint32_t)ch * 16u;
         off ^= ((off >> 7) & 7u) << 4;
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
+      l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (dbg && threadIdx.x == 64 && j < 24) dbg[32 + j] = clock64();
     }
     // ---- partial results of this split
     mbar_wait(o_done, 0);
     tcgen05_after_sync();
+    if (dbg && threadIdx.x == 64) dbg[2] = clock64();
     const int q = q0 + r;
-    float* op = a.o_part + ((int64_t)split * a.HW + q) * a.Do + c0;
+    // partial O: TMEM -> swizzled fp32 tiles [8 chunks][128 rows][32 floats] in the drained K/V stages -> TMA store
+    // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction)
 #pragma unroll 1
     for (int c = 0; c < TDV; c += 32) {
       uint32_t o[32];
       tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
       tmem_wait_ld();
-      if (q < a.HW) {
+      uint8_t* tile = sKV + (size_t)(c >> 5) * (TQ * 128);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4)
-          *reinterpret_cast<uint4*>(op + c + i) = make_uint4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+      for (int i = 0; i < 8; ++i) {
+        uint32_t off = (uint32_t)r * 128u + (uint32_t)i * 16u;
+        off ^= ((off >> 7) & 7u) << 4;
+        *reinterpret_cast<uint4*>(tile + off) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
+    }
+    fence_proxy_async_smem();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+#pragma unroll 1
+      for (int c = 0; c < TDV; c += 32) tma_store_3d(&tmO, sKV + (size_t)(c >> 5) * (TQ * 128), c0 + c, q0, split);
+      tma_store_commit_and_wait();
     }
     if (q < a.HW && blockIdx.y == 0) {
       a.ml_part[((int64_t)split * a.HW + q) * 2 + 0] = m_used;
       a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum;
     }
+    if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     tcgen05_before_sync();
   }
   __syncthreads();
@@ -236,6 +272,20 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     tmem_dealloc<512>(tmem_base);
   }
 }
+
+// one CTA per SM (208 KB of shared memory): split the memory axis so that the grid is one wave
+static int read_tc_splits(int M, int HW, int Do) {
+  const int tiles = ceil_div(HW, TQ) * (Do / TDV);
+  const int nkb = ceil_div(M, TKB);
+  int ns = sm_count() / tiles;
+  if (ns < 1) ns = 1;
+  if (ns > nkb) ns = nkb;
+  if (ns > 64) ns = 64;
+  const int bps = ceil_div(nkb, ns);
+  return ceil_div(nkb, bps);
+}
+
+long long* g_read_dbg = nullptr;   // dev hook (otvm_debug_set_read_timestamps)
 
 bool memory_read_tc_supported(const otvm_read_params* p) {
   if (p->dtype != OTVM_BF16 || p->De != TDE || p->Do % TDV != 0) return false;
@@ -250,18 +300,20 @@ bool memory_read_tc_supported(const otvm_read_params* p) {
 
 int64_t memory_read_tc_workspace(int M, int HW, int De, int Do) {
   (void)De;
-  int64_t ns = read_max_splits(M, HW, Do, TQ, TDV, TKB);
+  int64_t ns = read_tc_splits(M, HW, Do);
+  { int64_t nsm = read_max_splits(M, HW, Do, TQ, TDV, TKB); if (nsm > ns) ns = nsm; }
   return ns * HW * ((int64_t)Do + 2) * (int64_t)sizeof(float);
 }
 
 int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
   ReadTcArgs a;
   a.M = p->M; a.HW = p->HW; a.Do = p->Do;
-  a.nsplit = read_pick_splits(p->M, p->HW, p->Do, TQ, TDV, TKB);
+  a.nsplit = read_tc_splits(p->M, p->HW, p->Do);
   a.blocks_per_split = ceil_div(ceil_div(p->M, TKB), a.nsplit);
   a.scale_log2 = (float)(1.4426950408889634 / sqrt((double)p->De));
   a.o_part = static_cast<float*>(p->workspace);
   a.ml_part = a.o_part + (int64_t)a.nsplit * p->HW * p->Do;
+  a.dbg = g_read_dbg;
   CUtensorMap tmQ, tmK, tmV;
   {
     uint64_t dims[2] = {(uint64_t)TDE, (uint64_t)p->HW}; uint64_t str[1] = {(uint64_t)p->q_ld * 2};
@@ -284,9 +336,21 @@ int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
     attr = true;
   }
   dim3 grid(ceil_div(p->HW, TQ), p->Do / TDV, a.nsplit);
-  memory_read_tc_kernel<<<grid, kReadThreads, kReadSmem, s>>>(tmQ, tmK, tmV, a);
+  CUtensorMap tmO;
+  {   // fp32 partial outputs [nsplit][HW][Do]: 32-float (128-byte) rows, 128-row boxes, clipped at HW
+    uint64_t dims[3] = {(uint64_t)p->Do, (uint64_t)p->HW, (uint64_t)a.nsplit};
+    uint64_t str[2] = {(uint64_t)p->Do * 4, (uint64_t)p->HW * p->Do * 4};
+    uint32_t box[3] = {32, TQ, 1};
+    int rc = make_tmap(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.o_part, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  memory_read_tc_kernel<<<grid, kReadThreads, kReadSmem, s>>>(tmQ, tmK, tmV, tmO, a);
   OTVM_LAUNCH_CHECK();
   return read_combine(p, a.nsplit, s);
 }
 
 }  // namespace otvm
+
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_read_timestamps(long long* buf) {
+  otvm::g_read_dbg = buf;
+}
