@@ -161,6 +161,17 @@ def run_b200(args):
     # Each instrumented frame is queued behind a ~25 ms device-side sleep so that the GPU never waits for the
     # host between launches: the event pairs then bracket pure device execution (an idle GPU would stamp the
     # start event early and charge the host-side launch latency to the kernel).
+    if args.no_profile:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(world * args.steps / (ms_dev * 1e-3), 3), "unit": "frames/s",
+                              "n_gpus": world, "steps": args.steps, "ms_per_step": round(ms_dev / args.steps, 4),
+                              "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "frames/s"},
+                              "gpu_launches": int(launches), "clocks": clk,
+                              "config": {"overlap": os.environ.get("OTVM_OVERLAP", "1"), "pdl": os.environ.get("OTVM_PDL", "1")}}),
+                  flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     prof_frames = min(4, args.steps)
     ops.PROFILER = ops.Profiler()
     for i in range(prof_frames):
@@ -278,6 +289,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true", help="dev: skip the instrumented per-family pass")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OTVM_ABI_VERSION 1
+#define OTVM_ABI_VERSION 2
 #if defined(__GNUC__)
 #define OTVM_API __attribute__((visibility("default")))
 #else
@@ -45,6 +45,12 @@ OTVM_API const char* otvm_last_cuda_error(void);
 OTVM_API int64_t otvm_launch_count(void);
 /* 1 when the device is compute capability 10.x (tcgen05 / TMA paths usable) */
 OTVM_API int otvm_device_is_sm100(int device);
+/* Programmatic dependent launch between consecutive kernels of a stream (default on; env OTVM_PDL=0 disables):
+ * the next kernel's prologue overlaps the tail of the previous one; also recorded as programmatic edges when
+ * the stream is being captured into a CUDA graph. */
+OTVM_API void otvm_set_pdl(int enabled);
+/* cudaMemsetAsync(ptr, 0, bytes) on `stream` (e.g. the per-frame GroupNorm statistics arena) */
+OTVM_API int otvm_zero_async(void* ptr, int64_t bytes, void* stream);
 
 /* ---- convolution ------------------------------------------------------------------------------------
  * Replaces every nn.Conv2d / F.conv2d on the path: models/trimap/STM.py:17-19,37-43,107,122-127,169-170;
@@ -70,7 +76,9 @@ typedef struct {
   int32_t out_f32;                                /* 1: `out` is fp32 even when dtype is bf16 (heads)       */
   double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
   void* workspace;     int64_t workspace_bytes;   /* optional fp32 scratch: enables split-K for small grids */
-} otvm_conv_params;
+  int32_t gn_stats_zeroed;                        /* 1: caller already zeroed gn_stats on this stream (one   */
+  int32_t reserved;                               /*    otvm_zero_async over an arena instead of a memset    */
+} otvm_conv_params;                               /*    node in front of every convolution)                  */
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d would run this problem on the tcgen05 implicit-GEMM kernel (else the FFMA kernel) */
 OTVM_API int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);

@@ -28,6 +28,7 @@ class ConvParams(C.Structure):
         ("act", c_i32), ("relu_in", c_i32), ("dtype", c_i32), ("out_f32", c_i32),
         ("gn_stats", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
+        ("gn_stats_zeroed", c_i32), ("reserved", c_i32),
     ]
 
 
@@ -50,6 +51,8 @@ SIGNATURES = {
     "otvm_last_cuda_error": (C.c_char_p, []),
     "otvm_launch_count": (c_i64, []),
     "otvm_device_is_sm100": (C.c_int, [C.c_int]),
+    "otvm_set_pdl": (None, [C.c_int]),
+    "otvm_zero_async": (C.c_int, [c_vp, c_i64, c_vp]),
     "otvm_conv2d": (C.c_int, [C.POINTER(ConvParams), c_vp]),
     "otvm_conv2d_uses_tensor_cores": (C.c_int, [C.POINTER(ConvParams)]),
     "otvm_gn_stats": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
@@ -92,7 +95,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
-    if lib.otvm_version() != 1:
+    if lib.otvm_version() != 2:
         raise OtvmError("ABI version mismatch")
     _lib = lib
     return lib

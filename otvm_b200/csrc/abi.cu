@@ -1,4 +1,5 @@
 // C-ABI entry points that dispatch between the FFMA (strict fp32 / fallback) and tcgen05 kernels.
+#include <stdlib.h>
 #include <string.h>
 #include <atomic>
 #include "common.cuh"
@@ -15,6 +16,12 @@ void set_cuda_error(cudaError_t e) {
 
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) { const char* e = getenv("OTVM_PDL"); g_pdl = (e && e[0] == '0') ? 0 : 1; }
+  return g_pdl == 1;
+}
 
 int sm_count() {
   static int n = 0;
@@ -55,6 +62,14 @@ extern "C" const char* otvm_strerror(int code) {
 extern "C" const char* otvm_last_cuda_error(void) { return g_last_error; }
 
 extern "C" int64_t otvm_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" void otvm_set_pdl(int enabled) { otvm::g_pdl = enabled ? 1 : 0; }
+
+extern "C" int otvm_zero_async(void* ptr, int64_t bytes, void* stream) {
+  if (!ptr || bytes < 0) return OTVM_ERR_ARG;
+  OTVM_CUDA_CHECK(cudaMemsetAsync(ptr, 0, (size_t)bytes, static_cast<cudaStream_t>(stream)));
+  return OTVM_OK;
+}
 
 extern "C" int otvm_device_is_sm100(int device) {
   int major = 0;

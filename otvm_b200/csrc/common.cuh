@@ -66,6 +66,32 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// Every kernel of the frame is launched with programmatic stream serialisation: the NEXT kernel's CTAs may become
+// resident (and run their prologue: barrier init, TMEM allocation, tensor-map prefetch, constant loads) while this
+// kernel drains.  Contract for every kernel in this library:
+//   * pdl_wait() before the first access to global memory that another kernel may have written / may still read;
+//   * pdl_trigger() only once the CTA holds every resource it will ever need (tcgen05 kernels: after TMEM
+//     allocation, otherwise a dependent CTA could grab the columns a not-yet-allocated primary CTA is waiting for);
+//   * no kernel exits without having executed pdl_wait() (completion order stays transitive along the stream).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_trigger(); pdl_wait(); }
+
+bool pdl_enabled();                          // abi.cu: OTVM_PDL env (default on), otvm_set_pdl()
+
+template <typename... Params, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 // number of SMs of the current device (cached)
 int sm_count();
 

@@ -26,6 +26,7 @@ constexpr int BM = 64, BN = 64, BK = 16, LDS_PAD = 4;
 
 template <typename T, bool FAST>
 __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ __align__(16) float As[2][BK][BM + LDS_PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + LDS_PAD];
   __shared__ float gsum[BN][2];
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 // owns one output channel, the 32 lanes split K, and the weights are read exactly once.
 template <typename T, int MP>
 __global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   // one CTA per output channel; its 4 warps split K, every lane keeps one accumulator per pixel (M <= MP), so the
   // weights are read once and all activation loads of a K step are independent (latency-bound otherwise)
   __shared__ float part[4][MP];
@@ -247,14 +249,14 @@ static int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   bool fast = (a.Cin % BK == 0) && (a.in_ld % 4 == 0) && aligned4(in) && aligned4(w);
   if (fast && a.KH == 1 && a.KW == 1 && a.stride == 1 && a.pad == 0 && a.M <= 40 && a.K % 16 == 0 && !a.res && !a.out_relu &&
       !a.relu_in) {
-    if (a.M <= 4) conv1x1_smallm_kernel<T, 4><<<a.Cout, 128, 0, s>>>(a);
-    else if (a.M <= 12) conv1x1_smallm_kernel<T, 12><<<a.Cout, 128, 0, s>>>(a);
-    else conv1x1_smallm_kernel<T, 40><<<a.Cout, 128, 0, s>>>(a);
+    if (a.M <= 4) launch_k(conv1x1_smallm_kernel<T, 4>, a.Cout, 128, 0, s, a);
+    else if (a.M <= 12) launch_k(conv1x1_smallm_kernel<T, 12>, a.Cout, 128, 0, s, a);
+    else launch_k(conv1x1_smallm_kernel<T, 40>, a.Cout, 128, 0, s, a);
     OTVM_LAUNCH_CHECK();
     return OTVM_OK;
   }
-  if (fast) conv_simt_kernel<T, true><<<grid, 256, 0, s>>>(a);
-  else conv_simt_kernel<T, false><<<grid, 256, 0, s>>>(a);
+  if (fast) launch_k(conv_simt_kernel<T, true>, grid, 256, 0, s, a);
+  else launch_k(conv_simt_kernel<T, false>, grid, 256, 0, s, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -274,7 +276,7 @@ int conv2d_simt(const otvm_conv_params* p, cudaStream_t s) {
   if (a.M <= 0 || a.Cout <= 0) return OTVM_OK;
   if (p->gn_stats) {
     if (p->N != 1 || p->Cout % 32 != 0) return OTVM_ERR_UNSUPPORTED;
-    OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
+    if (!p->gn_stats_zeroed) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
   }
   if (p->dtype == OTVM_F32) return launch_conv_simt<float>(a, s);
   if (p->dtype == OTVM_BF16) {

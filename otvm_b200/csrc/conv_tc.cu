@@ -104,6 +104,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barriers, TMEM, tensor-map prefetch, bias = constant weights) overlapped the previous
+  // kernel's tail; this CTA now owns all its resources, so dependents may be scheduled, and from here on it
+  // touches activations produced by earlier kernels
+  pdl_trigger();
+  pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   // NOTE on the single-thread loops below: one thread issuing a dependent scalar chain is the pipeline's critical
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             int64_t res_ld, int act, void* __restrict__ out, int64_t out_ps,
                                                             int64_t out_cs, int out_f32, bf16* __restrict__ out_relu,
                                                             int64_t out_relu_ld, double* __restrict__ gn_stats) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ float sstat[32][2];
   const int c4n = Cout >> 2;
   const int64_t total = M * c4n;
@@ -451,7 +457,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
-  conv_tc_kernel<BN, GN, EPI><<<grid, kConvThreads, smem, s>>>(tmA, tmB, tmO, tmR, a);
+  launch_k(conv_tc_kernel<BN, GN, EPI>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -516,7 +522,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
   a.dbg = g_conv_dbg;
-  if (p->gn_stats) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
+  if (p->gn_stats && !p->gn_stats_zeroed) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
 
   const CUtensorMapSwizzle swz = a.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : a.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -574,7 +580,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     if (rc) return rc;
     const int64_t total = Mtot * (p->Cout / 4);
     int g = (int)((total + 255) / 256); if (g > sm_count() * 8) g = sm_count() * 8;
-    splitk_finish_kernel<<<g, 256, 0, s>>>(static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout, p->bias,
+    launch_k(splitk_finish_kernel, g, 256, 0, s, static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout, p->bias,
                                            static_cast<const bf16*>(p->res), p->res_ld, p->act, p->out, p->out_ps,
                                            p->out_cs, p->out_f32, static_cast<bf16*>(p->out_relu), p->out_relu_ld,
                                            p->gn_stats);

@@ -22,6 +22,7 @@ static inline int grid1d(int64_t n, int block) {
 __global__ void composite_kernel(const float* __restrict__ a, const float* __restrict__ fg,
                                  const float* __restrict__ bg, int H, int W, int Wp, int pad_top, int pad_left,
                                  float* __restrict__ img, float* __restrict__ scaled, uint8_t* __restrict__ unk) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)H * W;
   const float kScale = 1.f / 255;                     // IMG_SCALE, models/alpha/model.py:27
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
@@ -41,6 +42,7 @@ __global__ void composite_kernel(const float* __restrict__ a, const float* __res
 
 // separable (2r+1)^2 max filter == F.max_pool2d(k=2r+1, s=1, p=r) on a {0,1} mask (:353)
 __global__ void dilate_rows_kernel(const uint8_t* __restrict__ in, int H, int W, int r, uint8_t* __restrict__ out) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)H * W;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     int y = (int)(p / W), x = (int)(p - (int64_t)y * W);
@@ -56,6 +58,7 @@ __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, cons
                                           int Hp, int Wp, int pad_top, int pad_left, int r,
                                           float* __restrict__ img, float* __restrict__ tri3, MeanStd ms,
                                           T* __restrict__ imgn, int64_t imgn_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)Hp * Wp;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     int yp = (int)(p / Wp), xp = (int)(p - (int64_t)yp * Wp);
@@ -89,6 +92,7 @@ __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, cons
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) edt_rowscan_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask,
                                                           int* __restrict__ g2) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= H * nmask) return;
   const uint8_t* s = seed + (int64_t)warp * W;        // rows of all masks are contiguous
@@ -122,6 +126,7 @@ __global__ void __launch_bounds__(256) edt_rowscan_kernel(const uint8_t* __restr
 }
 
 __global__ void __launch_bounds__(256) edt_cols_kernel(const int* __restrict__ g2, int H, int W, int* __restrict__ d2) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   extern __shared__ int strip[];                      // [H][32]
   const int x0 = blockIdx.x * 32, m = blockIdx.y;
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5, nwy = blockDim.x >> 5;
@@ -151,7 +156,7 @@ __global__ void __launch_bounds__(256) edt_cols_kernel(const int* __restrict__ g
 }
 
 static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int* scratch, cudaStream_t s) {
-  edt_rowscan_kernel<<<ceil_div((int64_t)H * nmask * 32, 256), 256, 0, s>>>(seed, H, W, nmask, scratch);
+  launch_k(edt_rowscan_kernel, ceil_div((int64_t)H * nmask * 32, 256), 256, 0, s, seed, H, W, nmask, scratch);
   OTVM_LAUNCH_CHECK();
   const size_t smem = (size_t)H * 32 * sizeof(int);
   if (smem > 200 * 1024) return OTVM_ERR_UNSUPPORTED;
@@ -163,7 +168,7 @@ static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int
   int ysplit = ceil_div(2 * sm_count(), ceil_div(W, 32) * nmask);
   if (ysplit > 32) ysplit = 32;
   if (ysplit < 1) ysplit = 1;
-  edt_cols_kernel<<<dim3(ceil_div(W, 32), nmask, ysplit), 256, smem, s>>>(scratch, H, W, d2);
+  launch_k(edt_cols_kernel, dim3(ceil_div(W, 32), nmask, ysplit), 256, smem, s, scratch, H, W, d2);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -175,6 +180,7 @@ static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int
 __global__ void trimap_classes_kernel(const float* __restrict__ tri, int64_t tri_ld, int is_logit,
                                       const float* __restrict__ img, int64_t P, float* __restrict__ extras,
                                       uint8_t* __restrict__ seeds) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     float t0 = tri[p * tri_ld], t1 = tri[p * tri_ld + 1], t2 = tri[p * tri_ld + 2];
     if (is_logit) {                                   // F.softmax(_logit_trimap, dim=1)  (:440)
@@ -199,6 +205,7 @@ template <typename T>
 __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* __restrict__ d2, int64_t P,
                                    MeanStd ms, T* __restrict__ x11, int64_t x11_ld, T* __restrict__ cat_dst,
                                    int64_t cat_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   // trimap_transform, utils/utils.py:25-39: exp(-d^2 / (2 (sigma L)^2)), sigma in {.02,.08,.16}, L = 320
   const float den0 = (float)(2.0 * (0.02 * 320) * (0.02 * 320));
   const float den1 = (float)(2.0 * (0.08 * 320) * (0.08 * 320));
@@ -238,6 +245,7 @@ __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* 
 template <typename TR, typename TA>
 __global__ void fba_head_kernel(const TR* __restrict__ raw, int64_t raw_ld, const float* __restrict__ extras,
                                 int64_t P, float* __restrict__ out7, TA* __restrict__ alpha_dst, int64_t alpha_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     const TR* r = raw + p * raw_ld;
     float al = fminf(fmaxf(to_f(r[0]), 0.f), 1.f);
@@ -277,6 +285,7 @@ __global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t ra
                                      int Hp, int Wp, int H, int W, int pad_top, int pad_left, MeanStd ms,
                                      T* __restrict__ mem_in, int64_t mem_ld, float* __restrict__ alpha_out,
                                      float* __restrict__ trimap_out) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)Hp * Wp, Pc = (int64_t)H * W;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     const float* r = raw10 + p * raw_ld;
@@ -333,15 +342,15 @@ extern "C" int otvm_preprocess(const float* a, const float* fg, const float* bg,
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t P = (int64_t)H * W;
   uint8_t* unk = scratch; uint8_t* rows = scratch + P;
-  composite_kernel<<<grid1d(P, 256), 256, 0, s>>>(a, fg, bg, H, W, Wp, pad_top, pad_left, img, scaled_img, unk);
+  launch_k(composite_kernel, grid1d(P, 256), 256, 0, s, a, fg, bg, H, W, Wp, pad_top, pad_left, img, scaled_img, unk);
   OTVM_LAUNCH_CHECK();
-  dilate_rows_kernel<<<grid1d(P, 256), 256, 0, s>>>(unk, H, W, radius, rows);
+  launch_k(dilate_rows_kernel, grid1d(P, 256), 256, 0, s, unk, H, W, radius, rows);
   OTVM_LAUNCH_CHECK();
   if (dtype == OTVM_F32)
-    dilate_cols_onehot_kernel<float><<<grid1d((int64_t)Hp * Wp, 256), 256, 0, s>>>(
+    launch_k(dilate_cols_onehot_kernel<float>, grid1d((int64_t)Hp * Wp, 256), 256, 0, s, 
         rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<float*>(imgn), imgn_ld);
   else if (dtype == OTVM_BF16)
-    dilate_cols_onehot_kernel<bf16><<<grid1d((int64_t)Hp * Wp, 256), 256, 0, s>>>(
+    launch_k(dilate_cols_onehot_kernel<bf16>, grid1d((int64_t)Hp * Wp, 256), 256, 0, s, 
         rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<bf16*>(imgn), imgn_ld);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();
@@ -363,16 +372,16 @@ extern "C" int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t i
     return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int64_t P = (int64_t)Hp * Wp;
-  trimap_classes_kernel<<<grid1d(P, 256), 256, 0, s>>>(tri_in, tri_ld, is_logit, img, P, extras, seeds);
+  launch_k(trimap_classes_kernel, grid1d(P, 256), 256, 0, s, tri_in, tri_ld, is_logit, img, P, extras, seeds);
   OTVM_LAUNCH_CHECK();
   int rc = edt_launch(seeds, Hp, Wp, 2, d2, scratch, s);
   if (rc) return rc;
   MeanStd ms = make_ms(mean_std);
   if (dtype == OTVM_F32)
-    trimap_pack_kernel<float><<<grid1d(P, 256), 256, 0, s>>>(extras, d2, P, ms, static_cast<float*>(x11), x11_ld,
+    launch_k(trimap_pack_kernel<float>, grid1d(P, 256), 256, 0, s, extras, d2, P, ms, static_cast<float*>(x11), x11_ld,
                                                              static_cast<float*>(cat_dst), cat_ld);
   else if (dtype == OTVM_BF16)
-    trimap_pack_kernel<bf16><<<grid1d(P, 256), 256, 0, s>>>(extras, d2, P, ms, static_cast<bf16*>(x11), x11_ld,
+    launch_k(trimap_pack_kernel<bf16>, grid1d(P, 256), 256, 0, s, extras, d2, P, ms, static_cast<bf16*>(x11), x11_ld,
                                                             static_cast<bf16*>(cat_dst), cat_ld);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();
@@ -386,11 +395,11 @@ extern "C" int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int
   int g = grid1d(P, 256);
   const bool rf = raw_f32 || dtype == OTVM_F32;
   if (dtype == OTVM_F32)
-    fba_head_kernel<float, float><<<g, 256, 0, s>>>((const float*)raw, raw_ld, extras, P, out7, (float*)alpha_dst, alpha_ld);
+    launch_k(fba_head_kernel<float, float>, g, 256, 0, s, (const float*)raw, raw_ld, extras, P, out7, (float*)alpha_dst, alpha_ld);
   else if (dtype == OTVM_BF16 && rf)
-    fba_head_kernel<float, bf16><<<g, 256, 0, s>>>((const float*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
+    launch_k(fba_head_kernel<float, bf16>, g, 256, 0, s, (const float*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
   else if (dtype == OTVM_BF16)
-    fba_head_kernel<bf16, bf16><<<g, 256, 0, s>>>((const bf16*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
+    launch_k(fba_head_kernel<bf16, bf16>, g, 256, 0, s, (const bf16*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -406,10 +415,10 @@ extern "C" int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const floa
   MeanStd ms = make_ms(mean_std);
   int g = grid1d((int64_t)Hp * Wp, 256);
   if (dtype == OTVM_F32)
-    frame_outputs_kernel<float><<<g, 256, 0, s>>>(raw10, raw_ld, fused, (const float*)hid, hid_ld, extras, Hp, Wp, H, W,
+    launch_k(frame_outputs_kernel<float>, g, 256, 0, s, raw10, raw_ld, fused, (const float*)hid, hid_ld, extras, Hp, Wp, H, W,
                                                   pad_top, pad_left, ms, (float*)mem_in, mem_ld, alpha_out, trimap_out);
   else if (dtype == OTVM_BF16)
-    frame_outputs_kernel<bf16><<<g, 256, 0, s>>>(raw10, raw_ld, fused, (const bf16*)hid, hid_ld, extras, Hp, Wp, H, W,
+    launch_k(frame_outputs_kernel<bf16>, g, 256, 0, s, raw10, raw_ld, fused, (const bf16*)hid, hid_ld, extras, Hp, Wp, H, W,
                                                  pad_top, pad_left, ms, (bf16*)mem_in, mem_ld, alpha_out, trimap_out);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();

@@ -30,6 +30,7 @@ struct ReadArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(256) memory_read_simt_kernel(const ReadArgs a) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;                      // [RQ][QP]
   float* Ks = Qs + RQ * QP;              // [RK][QP]
@@ -173,6 +174,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* __restrict__ o_part,
                                                                   const float* __restrict__ ml_part, int nsplit,
                                                                   int HW, int Do, T* __restrict__ out, int64_t out_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = Do >> 2;
   const int64_t total = (int64_t)HW * c4n;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -222,10 +224,10 @@ int read_combine(const otvm_read_params* p, int nsplit, cudaStream_t s) {
   int64_t total = (int64_t)p->HW * (p->Do / 4);
   int g = ceil_div(total, 256);
   if (p->dtype == OTVM_F32)
-    memory_read_combine_kernel<float><<<g, 256, 0, s>>>(o_part, ml_part, nsplit, p->HW, p->Do,
+    launch_k(memory_read_combine_kernel<float>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do,
                                                         static_cast<float*>(p->out), p->out_ld);
   else
-    memory_read_combine_kernel<bf16><<<g, 256, 0, s>>>(o_part, ml_part, nsplit, p->HW, p->Do,
+    launch_k(memory_read_combine_kernel<bf16>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do,
                                                        static_cast<bf16*>(p->out), p->out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -249,7 +251,7 @@ static int read_simt_t(const otvm_read_params* p, cudaStream_t s) {
     attr_set = true;
   }
   dim3 grid(ceil_div(p->HW, RQ), p->Do / RDV, a.nsplit);
-  memory_read_simt_kernel<T><<<grid, 256, smem, s>>>(a);
+  launch_k(memory_read_simt_kernel<T>, grid, 256, smem, s, a);
   OTVM_LAUNCH_CHECK();
   return read_combine(p, a.nsplit, s);
 }

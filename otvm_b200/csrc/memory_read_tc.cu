@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + TDV;
+  pdl_trigger();                                       // PDL contract (common.cuh): resources held, then wait
+  pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
 
   if (warp == 0) {
@@ -344,7 +346,7 @@ int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
     int rc = make_tmap(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.o_part, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  memory_read_tc_kernel<<<grid, kReadThreads, kReadSmem, s>>>(tmQ, tmK, tmV, tmO, a);
+  launch_k(memory_read_tc_kernel, grid, kReadThreads, kReadSmem, s, tmQ, tmK, tmV, tmO, a);
   OTVM_LAUNCH_CHECK();
   return read_combine(p, a.nsplit, s);
 }

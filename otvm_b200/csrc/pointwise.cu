@@ -39,6 +39,7 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
 template <typename T>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
                                                        double* __restrict__ stats) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ float part[32][2];
   const int n = blockIdx.y;
   const int c4n = C >> 2;                        // channel quads per pixel
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ beta, float eps,
                                                        const T* __restrict__ res, int64_t res_ld, int act,
                                                        T* __restrict__ out, int64_t out_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int n = blockIdx.y;
   const int tpp = C >> 3;                         // threads per pixel (divides 256)
   const int cv = (threadIdx.x % tpp) * 8;
@@ -136,7 +138,7 @@ static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* s
   int64_t want = (int64_t)sm_count() * 4 * 256;
   int64_t threads = ((total < want ? total : want) + lcm - 1) / lcm * lcm;
   dim3 grid((unsigned)(threads / 256), N);
-  gn_stats_kernel<T><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats);
+  launch_k(gn_stats_kernel<T>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -152,10 +154,10 @@ static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const dou
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, N);
   if (res)
-    gn_apply_kernel<T, true><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
+    launch_k(gn_apply_kernel<T, true>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
                                                   static_cast<const T*>(res), res_ld, act, static_cast<T*>(out), out_ld);
   else
-    gn_apply_kernel<T, false><<<grid, 256, 0, s>>>(static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
+    launch_k(gn_apply_kernel<T, false>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
                                                    nullptr, 0, act, static_cast<T*>(out), out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
                                                        const T* __restrict__ add, int64_t add_ld,
                                                        T* __restrict__ out, int64_t out_ld,
                                                        T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * c4n;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -220,6 +223,7 @@ __global__ void __launch_bounds__(256) upsample8_kernel(const T* __restrict__ in
                                                         const T* __restrict__ add, int64_t add_ld,
                                                         T* __restrict__ out, int64_t out_ld,
                                                         T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * Ho * Wo * c8n;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -258,6 +262,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restrict__ in, int64_t in_ld, int Hi,
                                                               int Wi, int C, int Ho, int Wo, float sy, float sx,
                                                               float* __restrict__ out, int64_t out_ld, int nchw) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t total = (int64_t)Ho * Wo;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t pix = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += nthreads) {
@@ -281,6 +286,7 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, int64_t in_ld, int N, int H, int W,
                                                       int C, int Ho, int Wo, T* __restrict__ out, int64_t out_ld) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * c4n;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -319,6 +325,7 @@ __device__ __forceinline__ int bin_end(int b, int s, int L) { return ((b + 1) * 
 template <typename T>
 __global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in, int64_t in_ld, int H, int W, int C,
                                                        float* __restrict__ rows) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int y = blockIdx.x, n = blockIdx.z;
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c >= C) return;
@@ -352,6 +359,7 @@ __global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in,
 template <typename T>
 __global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict__ rows, int H, int W, int C,
                                                         T* __restrict__ out) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int cell = blockIdx.x, n = blockIdx.z;          // 0..49: scale-major, row-major inside a scale
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
   if (c >= C) return;
@@ -379,6 +387,7 @@ __global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict_
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t HW, T* __restrict__ out,
                                     int64_t out_ld, int N) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t total = (int64_t)N * HW * C;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
@@ -390,6 +399,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t in_ld, int C, int64_t HW,
                                     float* __restrict__ out, int N) {
+  pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t total = (int64_t)N * HW * C;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
@@ -433,7 +443,7 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
   float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
   if (out_nchw_f32 || C % 4 != 0) {
     if (add || out_relu || N != 1) return OTVM_ERR_UNSUPPORTED;
-    upsample_scalar_kernel<T><<<grid_for((int64_t)Ho * Wo, 256), 256, 0, s>>>(
+    launch_k(upsample_scalar_kernel<T>, grid_for((int64_t)Ho * Wo, 256), 256, 0, s, 
         static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo, sy, sx, static_cast<float*>(out), out_ld,
         out_nchw_f32 == 1);
   } else {
@@ -444,7 +454,7 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
                          reinterpret_cast<uintptr_t>(out_relu)) & 15);
     if (wide) {
       int64_t total8 = (int64_t)N * Ho * Wo * (C / 8);
-      upsample8_kernel<T><<<grid_for(total8, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
+      launch_k(upsample8_kernel<T>, grid_for(total8, 256), 256, 0, s, static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
                                                                 sy, sx, static_cast<const T*>(add), add_ld,
                                                                 static_cast<T*>(out), out_ld,
                                                                 static_cast<T*>(out_relu), out_relu_ld, N);
@@ -452,7 +462,7 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
       return OTVM_OK;
     }
     int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-    upsample_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
+    launch_k(upsample_kernel<T>, grid_for(total, 256), 256, 0, s, static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
                                                            sy, sx, static_cast<const T*>(add), add_ld,
                                                            static_cast<T*>(out), out_ld,
                                                            static_cast<T*>(out_relu), out_relu_ld, N);
@@ -479,7 +489,7 @@ static int maxpool_t(const void* in, int64_t in_ld, int N, int H, int W, int C, 
                      cudaStream_t s) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-  maxpool_kernel<T><<<grid_for(total, 256), 256, 0, s>>>(static_cast<const T*>(in), in_ld, N, H, W, C, Ho, Wo,
+  launch_k(maxpool_kernel<T>, grid_for(total, 256), 256, 0, s, static_cast<const T*>(in), in_ld, N, H, W, C, Ho, Wo,
                                                         static_cast<T*>(out), out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -497,9 +507,9 @@ template <typename T>
 static int ppm_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, float* scratch,
                  cudaStream_t s) {
   dim3 g1(H, ceil_div(C / 4, 128), N), g2(50, ceil_div(C / 4, 128), N);
-  ppm_rows_kernel<T><<<g1, 128, 0, s>>>(static_cast<const T*>(in), in_ld, H, W, C, scratch);
+  launch_k(ppm_rows_kernel<T>, g1, 128, 0, s, static_cast<const T*>(in), in_ld, H, W, C, scratch);
   OTVM_LAUNCH_CHECK();
-  ppm_cells_kernel<T><<<g2, 128, 0, s>>>(scratch, H, W, C, static_cast<T*>(out));
+  launch_k(ppm_cells_kernel<T>, g2, 128, 0, s, scratch, H, W, C, static_cast<T*>(out));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -516,8 +526,8 @@ extern "C" int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t 
                                  int32_t dtype, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int g = grid_for((int64_t)N * HW * C, 256);
-  if (dtype == OTVM_F32) nchw_to_nhwc_kernel<float><<<g, 256, 0, s>>>(in, C, HW, static_cast<float*>(out), out_ld, N);
-  else if (dtype == OTVM_BF16) nchw_to_nhwc_kernel<bf16><<<g, 256, 0, s>>>(in, C, HW, static_cast<bf16*>(out), out_ld, N);
+  if (dtype == OTVM_F32) launch_k(nchw_to_nhwc_kernel<float>, g, 256, 0, s, in, C, HW, static_cast<float*>(out), out_ld, N);
+  else if (dtype == OTVM_BF16) launch_k(nchw_to_nhwc_kernel<bf16>, g, 256, 0, s, in, C, HW, static_cast<bf16*>(out), out_ld, N);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -527,8 +537,8 @@ extern "C" int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32
                                  int32_t dtype, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int g = grid_for((int64_t)N * HW * C, 256);
-  if (dtype == OTVM_F32) nhwc_to_nchw_kernel<float><<<g, 256, 0, s>>>(static_cast<const float*>(in), in_ld, C, HW, out, N);
-  else if (dtype == OTVM_BF16) nhwc_to_nchw_kernel<bf16><<<g, 256, 0, s>>>(static_cast<const bf16*>(in), in_ld, C, HW, out, N);
+  if (dtype == OTVM_F32) launch_k(nhwc_to_nchw_kernel<float>, g, 256, 0, s, static_cast<const float*>(in), in_ld, C, HW, out, N);
+  else if (dtype == OTVM_BF16) launch_k(nhwc_to_nchw_kernel<bf16>, g, 256, 0, s, static_cast<const bf16*>(in), in_ld, C, HW, out, N);
   else return OTVM_ERR_ARG;
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;

@@ -133,6 +133,15 @@ class FramePlan:
         self.pad_top, self.pad_left = (self.Hp - H) // 2, (self.Wp - W) // 2     # models/alpha/common.py:17-19
         self.dtype, self.device = dtype, device
         self.bufs: Dict[str, torch.Tensor] = {}
+        # GroupNorm statistics arena: one [32][2] fp64 slot per normalised convolution, zeroed ONCE per frame
+        # (one memset node instead of one in front of each of the 66 convolutions)
+        self.gn_arena = torch.zeros(128, 64, dtype=torch.float64, device=device)
+        self.gn_slots: Dict[str, int] = {}
+        self.pending: Optional[int] = None          # bank slot whose memorize pass is deferred to the next frame
+
+    def gn_slot(self, name):
+        i = self.gn_slots.setdefault(name, len(self.gn_slots))
+        return self.gn_arena[i]
 
     def buf(self, name, shape, dtype=None, zero=False):
         t = self.bufs.get(name)
@@ -199,6 +208,11 @@ class Engine:
         self.plans: Dict[tuple, FramePlan] = {}
         self.banks: Dict[tuple, MemoryBank] = {}
         self.use_graphs = os.environ.get("OTVM_CUDA_GRAPHS", "1") != "0"
+        # deferred memorize: frame t's Encoder_M / KV_M pass (STM.py:201-228) only feeds frame t+1's Memory.read, so
+        # it is issued at the START of frame t+1 on a side stream, concurrently with Encoder_Q / KV_Q of t+1 (both
+        # are chains of small-grid convolutions that leave most SMs idle on their own), and joined before the read
+        self.defer_memorize = os.environ.get("OTVM_OVERLAP", "1") != "0"
+        self.side_stream = None
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
         self.warm, self.seen = set(), set()
         self.graph_launches: Dict[tuple, int] = {}
@@ -218,7 +232,8 @@ class Engine:
         return self.banks[k]
 
     # ---- building blocks ---------------------------------------------------------------------------
-    def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, **kw):
+    def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, ws_name="conv_splitk_ws",
+              **kw):
         w, b = self.w.conv[name]
         N, H, W, _ = x.shape
         kh = w.shape[1]
@@ -226,24 +241,25 @@ class Engine:
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         if out is None:
             out = pl.buf(out_name or name, (N, Ho, Wo, w.shape[0]))
-        ws = pl.buf("conv_splitk_ws", (16 << 20,), torch.float32)       # 64 MB fp32 scratch for split-K partial tiles
+        ws = pl.buf(ws_name, (16 << 20,), torch.float32)       # 64 MB fp32 scratch for split-K partial tiles (per stream)
         return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, workspace=ws, **kw)
 
-    def _tv_bottleneck(self, pl, p, x, stride, out=None):
+    def _tv_bottleneck(self, pl, p, x, stride, out=None, ws_name="conv_splitk_ws"):
         """torchvision Bottleneck with BN folded; ReLUs and the residual add live in the conv epilogues."""
-        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU)
-        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU)
-        idn = self._conv(pl, p + ".downsample", x, stride=stride) if (p + ".downsample") in self.w.conv else x
-        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU)
+        kw = dict(ws_name=ws_name)
+        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU, **kw)
+        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU, **kw)
+        idn = self._conv(pl, p + ".downsample", x, stride=stride, **kw) if (p + ".downsample") in self.w.conv else x
+        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU, **kw)
 
-    def _tv_encoder(self, pl, enc, x):
-        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU)
+    def _tv_encoder(self, pl, enc, x, ws_name="conv_splitk_ws"):
+        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU, ws_name=ws_name)
         N, H, W, C = c1.shape
         x = ops.maxpool3x3s2(c1, pl.buf(enc + ".pool", (N, (H + 1) // 2, (W + 1) // 2, C)))
         feats = []
         for lname, blocks, stride in (("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2)):
             for b in range(blocks):
-                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1)
+                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1, ws_name=ws_name)
             feats.append(x)
         return feats       # r2, r3, r4
 
@@ -257,8 +273,8 @@ class Engine:
     def _ws_gn(self, pl, conv, norm, x, *, act, res=None, out=None, stride=1, pad=0, dil=1, raw_name=None):
         """WS-conv -> GroupNorm(32) -> activation (+residual).  GN statistics are accumulated by the conv
         epilogue; the normalise/affine/activation pass runs in place unless ``out`` is given."""
-        stats = pl.buf("gn_stats." + conv, (64,), torch.float64)
-        raw = self._conv(pl, conv, x, raw_name, stride=stride, pad=pad, dil=dil, gn_stats=stats)
+        stats = pl.gn_slot(conv)                    # zeroed by _frame_body (one memset per frame)
+        raw = self._conv(pl, conv, x, raw_name, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True)
         return self._gn(pl, norm, raw, act=act, res=res, out=out, stats=stats)
 
     def _gn_bottleneck(self, pl, p, x, stride, dil, out=None):
@@ -281,7 +297,7 @@ class Engine:
         return y, yr
 
     # ---- STM ---------------------------------------------------------------------------------------
-    def segment(self, pl: FramePlan, bank: MemoryBank):
+    def segment(self, pl: FramePlan, bank: MemoryBank, join=None):
         """Propagated trimap logits [Hp*Wp][4] fp32 for the current frame (imgn must be ready)."""
         imgn = pl.bufs["imgn"]                      # [1,Hp,Wp,cin_img]: 3 normalised channels + zeros
         r2, r3, r4 = self._tv_encoder(pl, "trimap.model.Encoder_Q", imgn)
@@ -292,6 +308,8 @@ class Engine:
         M = bank.T * bank.hw
         ws_bytes = ops.memory_read_workspace(self.bank_capacity * bank.hw, h * w, DE, DO, self.dtype)
         ws = pl.buf("read_ws", (ws_bytes // 4,), torch.float32)
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)      # deferred memorize of the previous frame has landed
         ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws)
         return self._stm_decoder(pl, m4in, r3, r2)
 
@@ -317,15 +335,22 @@ class Engine:
         ops.upsample(p2[..., :3], logits[..., :3])                                    # STM.py:136
         return logits
 
-    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int):
+    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int, ws_name="conv_splitk_ws"):
         """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``."""
         mem_in = pl.bufs["mem_in"]                  # [1,Hp,Wp,cin_mem]: 22 channels + zeros
-        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in)
+        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in, ws_name=ws_name)
         N, h, w, _ = r4.shape
         kdst = bank.key_slot(slot).view(1, h, w, DE)
-        self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1)
+        self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1, ws_name=ws_name)
         vdst = bank.vals[:, slot * bank.hw:]
-        self._conv(pl, "trimap.model.KV_M_r4.Value", r4, out=vdst, pad=1, out_strides=(1, bank.vals.shape[1]))
+        self._conv(pl, "trimap.model.KV_M_r4.Value", r4, out=vdst, pad=1, out_strides=(1, bank.vals.shape[1]),
+                   ws_name=ws_name)
+
+    def flush(self, pl: FramePlan):
+        """Run a deferred memorize pass now (anything that looks at the bank outside ``frame`` calls this)."""
+        if pl.pending is not None:
+            self.memorize(pl, self.bank(pl), pl.pending)
+            pl.pending = None
 
     # ---- FBA ---------------------------------------------------------------------------------------
     def matting(self, pl: FramePlan):
@@ -387,10 +412,23 @@ class Engine:
         return dict(raw7=raw7, out7=out7, raw10=raw10, fused=fused, hid=hid, conv5=conv5)
 
     # ---- one frame (EvalModel.forward with tri=None, tri_gt=None) ------------------------------------
-    def _frame_body(self, pl, bank, *, first_frame, slot, radius, user_tri=None):
-        """Issue every kernel of one frame on the current stream (inputs already in the plan's static buffers)."""
+    def _frame_body(self, pl, bank, *, first_frame, slot, radius, user_tri=None, pending=None):
+        """Issue every kernel of one frame on the current stream (inputs already in the plan's static buffers).
+        ``pending``: bank slot of the previous frame's deferred memorize pass, run first on the side stream."""
         H, W, Hp, Wp, P = pl.H, pl.W, pl.Hp, pl.Wp, pl.Hp * pl.Wp
         f32 = torch.float32
+        join = None
+        if pending is not None:
+            if ops.PROFILER is None:
+                if self.side_stream is None:
+                    self.side_stream = torch.cuda.Stream(device=self.device)
+                join = self.side_stream
+                join.wait_stream(torch.cuda.current_stream())          # fork (also inside a graph capture)
+                with torch.cuda.stream(join):
+                    self.memorize(pl, bank, pending, ws_name="conv_splitk_ws.side")
+            else:
+                self.memorize(pl, bank, pending)                         # instrumented pass: one stream, no overlap
+        ops.zero_(pl.gn_arena)
         a, fg, bg = pl.bufs["in_a"], pl.bufs["in_fg"], pl.bufs["in_bg"]
         img = pl.buf("img", (P, 4), f32)
         scaled = pl.buf("scaled_img", (3, H, W), f32)
@@ -412,7 +450,8 @@ class Engine:
                 tri_first[pl.pad_top:pl.pad_top + H, pl.pad_left:pl.pad_left + W, :3] = user_tri.permute(1, 2, 0)
             ops.trimap_encode(tri_first, 4, False, *enc_args)                   # preds_trimap = tri_ (:429)
         else:
-            logits = self.segment(pl, bank)
+            logits = self.segment(pl, bank, join)
+            join = None
             ops.trimap_encode(logits, 4, True, *enc_args)                       # softmax + make_trimap (:440-442)
         net = self.matting(pl)
         alpha = pl.buf("alpha_out", (H, W), f32)
@@ -420,7 +459,9 @@ class Engine:
         mem_in = pl.buf("mem_in", (1, Hp, Wp, self.w.cin_mem), zero=True)[..., :24] if slot is not None else None
         ops.frame_outputs(net["raw10"], 12, net["fused"], net["hid"], extras, Hp, Wp, H, W, pl.pad_top, pl.pad_left,
                           self.w.ms_m, mem_in, alpha, trimap)
-        if slot is not None:
+        if join is not None:                          # (first frames never carry a pending pass; kept for safety)
+            torch.cuda.current_stream().wait_stream(join)
+        if slot is not None and not self.defer_memorize:
             self.memorize(pl, bank, slot)
 
     def frame(self, a, fg, bg, *, first_frame, last_frame, memorize, max_memory_num, radius, user_tri=None):
@@ -438,11 +479,14 @@ class Engine:
         pl.buf("in_bg", (3, H, W), f32).copy_(bg, non_blocking=True)
         if first_frame:
             bank.reset()
+            pl.pending = None                        # the reference drops the old memories too (:425-429)
         slot, order = (None, bank.order)
         if not last_frame:
             slot, order = bank.next_slot(first_frame, memorize, max_memory_num)
-        key = (H, W, bank.T, slot, radius)
-        body = lambda: self._frame_body(pl, bank, first_frame=first_frame, slot=slot, radius=radius, user_tri=user_tri)
+        pending, pl.pending = pl.pending, None
+        key = (H, W, bank.T, pending, slot if not self.defer_memorize else slot is not None, radius)
+        body = lambda: self._frame_body(pl, bank, first_frame=first_frame, slot=slot, radius=radius, user_tri=user_tri,
+                                        pending=pending)
         steady = slot is not None and bank.T >= max(2, max_memory_num)      # bank full: keys repeat from now on
         if not self.use_graphs or first_frame or ops.PROFILER is not None:
             body()
@@ -464,5 +508,7 @@ class Engine:
             self.replayed_launches += self.graph_launches[key]
         if slot is not None:
             bank.order = order
+            if self.defer_memorize:
+                pl.pending = slot
         b = pl.bufs
         return b["scaled_img"], b["trimap_out"], b["tri3"], b["alpha_out"]

@@ -76,7 +76,7 @@ def _p(t):
 
 
 def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=False, res=None, out_relu=None,
-           gn_stats=None, out_strides=None, cin=None, workspace=None):
+           gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None):
     """x [N,H,W,Cin(view)], w [Cout,KH,KW,Cin] packed, out NHWC view (or any buffer with ``out_strides`` =
     (pixel_stride, channel_stride) in elements, used for the channel-major value bank)."""
     lib = _lib.load()
@@ -98,6 +98,7 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     p.act, p.relu_in, p.dtype = act, int(relu_in), _DT[x.dtype]
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
+    p.gn_stats_zeroed = int(gn_stats_zeroed)
     if workspace is not None:
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     assert w.dtype == x.dtype and (bias is None or bias.dtype == torch.float32)
@@ -114,6 +115,13 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     _timed(key, lambda: check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d"),
            2.0 * N * Ho * Wo * Cout * KH * KW * Cin, float(nb))
     return out
+
+
+def zero_(t):
+    """cudaMemsetAsync of a contiguous tensor on the current stream (GroupNorm statistics arena)"""
+    assert t.is_contiguous()
+    check(_lib.load().otvm_zero_async(_p(t), t.numel() * t.element_size(), _stream()), "otvm_zero_async")
+    return t
 
 
 def gn_stats(x, stats):

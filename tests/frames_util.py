@@ -33,6 +33,7 @@ def force_bank(model, oracle, H, W):
     eng = model.engine
     pl = eng.plan(H, W)
     bank = eng.bank(pl)
+    eng.flush(pl)                                  # a deferred memorize pass must not land after the overwrite
     key, val = oracle.memories["key"][0, 0], oracle.memories["val"][0, 0]       # [C,T,h,w]
     T = key.shape[1]
     bank.keys[:T * bank.hw] = key.permute(1, 2, 3, 0).reshape(T * bank.hw, -1).to(bank.keys)
@@ -59,6 +60,8 @@ def compare_frame(model, oracle, out, ref, H, W, first, rel_err=rel_err):
     e["hid"] = rel_err(nchw(b["hid"]), tr["hid"])
     e["refine_fused"] = rel_err(b["fused"].view(1, Hp, Wp, 8)[..., :7].permute(0, 3, 1, 2).cpu(), tr["refine_output"])
     bank = eng.bank(pl)
+    eng.flush(pl)                                  # the frame's memorize pass is deferred to the next frame: run it now
+    torch.cuda.synchronize()
     s = bank.order[-1]
     h, w = Hp // 16, Wp // 16
     e["mem_key"] = rel_err(bank.key_slot(s).float().cpu().view(h, w, -1).permute(2, 0, 1), tr["mem_k"][0, :, 0])
