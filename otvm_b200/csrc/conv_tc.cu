@@ -14,6 +14,7 @@
 // Ring of NSTAGE {A,B} stages with full/empty mbarriers; tcgen05.commit releases stages and publishes the
 // accumulator.  Up to two CTAs per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps
 // another's main loop.
+#include <stdlib.h>
 #include "tc_common.cuh"
 
 namespace otvm {
@@ -28,6 +29,11 @@ struct ConvTcArgs {
   int64_t split_stride;        // elements between the fp32 partial outputs of consecutive K slices
   uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
   uint32_t a_bytes, b_bytes, sbo, layout_type;
+  // halo mode (3x3 stride-1): ONE input patch {KC, TW+2d, TH+2d} per K-chunk feeds all 9 taps; the tap (ky,kx) operand is
+  // the same shared-memory copy read through a descriptor whose start is shifted by whole pixel rows
+  int halo, na;                // na = patch ring slots
+  uint32_t patch_bytes, b_off; // patch slot size (1024-aligned); byte offset of the B ring behind the patch ring
+  uint32_t row_bytes;          // KC * 2
   const float* bias;
   void* out; int64_t out_ps, out_cs;
   const bf16* res; int64_t res_ld;
@@ -58,7 +64,7 @@ __device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int r, float* sr
 
 enum { EPI_RES = 1, EPI_RELU2 = 2, EPI_DIRECT = 4 };
 
-template <int BN, bool GN, int EPI>
+template <int BN, bool GN, int EPI, bool HALO>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
@@ -72,7 +78,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + a.aux_off);
   uint64_t* empty_bar = full_bar + a.nstage;
   uint64_t* accum_bar = empty_bar + a.nstage;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* a_empty = accum_bar + 1;                                  // [4] patch ring (halo mode)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 4);
   float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
 
@@ -95,6 +102,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < a.nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&a_empty[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -115,66 +123,126 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   // path (measured ~830 cycles per K iteration with runtime div/mod for the stage / tap / chunk indices, and ~430
   // when all 32 lanes polled the mbarrier, vs 256 cycles of MMA work), so indices are carried incrementally and
   // exactly one thread per role runs its loop.
+  if constexpr (HALO) {
+    // iteration order: K-chunk major, the 9 taps inner; `it0`/`num_k` are multiples of 9 (whole chunks per K slice)
+    const int d = a.dil, pw = a.TW + 2 * a.dil;                 // patch width in pixels
+    if (warp == 0) {
+      // ===== single TMA producer: per chunk one input patch (into the patch ring), per tap one weight box =====
+      int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
+      int tap = 0, chunk = it0 / 9;
+      const int cx = x0 - a.pad, cy = y0 - a.pad;
+      const uint32_t b_tx = (uint32_t)(BN * a.KC * 2);
+      const uint32_t a_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes;
+      for (int it = 0; it < num_k; ++it) {
+        if (tap == 0) mbar_wait(&a_empty[as], aph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* sb = smem + a.b_off + (size_t)s * a.b_bytes;
+          if (tap == 0) {
+            mbar_arrive_expect_tx(&full_bar[s], b_tx + a_tx);
+            tma_load_4d(smem + (size_t)as * a.patch_bytes, &tmA, &full_bar[s], chunk * a.KC, cx, cy, n_img);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], b_tx);
+          }
+          tma_load_2d(sb, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+        }
+        __syncwarp();
+        if (++s == a.nstage) { s = 0; ph ^= 1; }
+        if (++tap == 9) { tap = 0; ++chunk; if (++as == a.na) { as = 0; aph ^= 1; } }
+      }
+    } else if (warp == 1) {
+      // ===== MMA issuer: A descriptor = patch slot + (ky*d*pw + kx*d) pixel rows; 8-row groups are tile rows (TW = 8),
+      // SBO = pw pixel rows.  Row-shifted SWIZZLE_* operands are valid because the hardware swizzles on absolute
+      // shared-memory address bits (probed on B200: csrc/umma_probe.cu) =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+      const int ksteps = a.KC / 16;
+      const uint64_t adesc0 = make_smem_desc(base, (uint32_t)pw * a.row_bytes, a.layout_type);
+      const uint64_t bdesc0 = make_smem_desc(base + a.b_off, a.sbo, a.layout_type);
+      const uint32_t bstage16 = a.b_bytes >> 4, patch16 = a.patch_bytes >> 4;
+      const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
+      int s = 0; uint32_t ph = 0, soff = 0, aoff = 0, toff = 0; int as = 0, kx = 0, ky = 0;
+      for (int it = 0; it < num_k; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_after_sync();
+        const bool last_tap = kx == 2 && ky == 2;
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + aoff + toff, bd = bdesc0 + soff;
+          umma_bf16(tmem_base, ad, bd, idesc, it != 0);
+          for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+          umma_commit(&empty_bar[s]);
+          if (last_tap) umma_commit(&a_empty[as]);             // all 9 taps of this chunk have read the patch
+          if (it == num_k - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+        soff += bstage16;
+        if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
+        if (last_tap) { kx = 0; ky = 0; toff = 0; aoff += patch16; if (++as == a.na) { as = 0; aoff = 0; } }
+        else if (++kx == 3) { kx = 0; ++ky; toff += ky16 - 2 * kx16; }
+        else toff += kx16;
+      }
+    }
+  } else {
   if (warp == 0 || warp == 2) {
-    // ===== TMA producers: warp 0 loads the activation boxes, warp 2 the weight boxes (it joins the epilogue
-    // afterwards).  Each ring slot ("group") holds KSUB K-chunks behind ONE full/empty barrier pair, so the
-    // ~400-cycle wait/arrive/issue latency of a single thread is paid once per KSUB chunks.  The A-side thread posts
-    // the expected byte count of the whole group; a B box landing first only makes the transaction count
-    // transiently negative, the phase cannot complete before the A-side arrival. =====
-    const bool load_a = warp == 0;
-    int s = 0; uint32_t ph = 0;
-    int tap = it0 / a.nchunk, chunk = it0 - tap * a.nchunk;
-    int ky = tap / a.KW, kx = tap - ky * a.KW;
-    const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
-    const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
-    // The loop body is kept minimal and warp-uniform (elected lane issues): the serial instruction stream of this
-    // warp is the pipeline's critical path.  Measured per-iteration periods of variants of this loop: runtime
-    // div/mod indices 830 cycles, coordinate table in smem 700, nested K-chunk groups 870, this form 425.
-    for (int it = 0; it < num_k; ++it) {
-      mbar_wait(&empty_bar[s], ph ^ 1);
-      if (elect_one()) {
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        if (load_a) {
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, cx + kx * a.dil, cy + ky * a.dil, n_img);
-          if (dbg && it == 0) dbg[2] = clock64();
-          if (dbg && it < 16) dbg[32 + it] = clock64();
-        } else {
-          tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+      // ===== TMA producers: warp 0 loads the activation boxes, warp 2 the weight boxes (it joins the epilogue
+      // afterwards).  Each ring slot ("group") holds KSUB K-chunks behind ONE full/empty barrier pair, so the
+      // ~400-cycle wait/arrive/issue latency of a single thread is paid once per KSUB chunks.  The A-side thread posts
+      // the expected byte count of the whole group; a B box landing first only makes the transaction count
+      // transiently negative, the phase cannot complete before the A-side arrival. =====
+      const bool load_a = warp == 0;
+      int s = 0; uint32_t ph = 0;
+      int tap = it0 / a.nchunk, chunk = it0 - tap * a.nchunk;
+      int ky = tap / a.KW, kx = tap - ky * a.KW;
+      const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
+      const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
+      // The loop body is kept minimal and warp-uniform (elected lane issues): the serial instruction stream of this
+      // warp is the pipeline's critical path.  Measured per-iteration periods of variants of this loop: runtime
+      // div/mod indices 830 cycles, coordinate table in smem 700, nested K-chunk groups 870, this form 425.
+      for (int it = 0; it < num_k; ++it) {
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          if (load_a) {
+            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, cx + kx * a.dil, cy + ky * a.dil, n_img);
+            if (dbg && it == 0) dbg[2] = clock64();
+            if (dbg && it < 16) dbg[32 + it] = clock64();
+          } else {
+            tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+          }
         }
+        __syncwarp();
+        if (++s == a.nstage) { s = 0; ph ^= 1; }
+        if (++chunk == a.nchunk) { chunk = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
       }
-      __syncwarp();
-      if (++s == a.nstage) { s = 0; ph ^= 1; }
-      if (++chunk == a.nchunk) { chunk = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (one elected thread); descriptors are advanced by adding byte offsets >> 4 to the low word =====
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
-    const int ksteps = a.KC / 16;
-    const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
-    const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
-    const uint32_t stage16 = stage_bytes >> 4;
-    int s = 0; uint32_t ph = 0, soff = 0;
-    for (int it = 0; it < num_k; ++it) {
-      mbar_wait(&full_bar[s], ph);
-      tcgen05_after_sync();
-      if (elect_one()) {
-        if (dbg && it == 0) dbg[3] = clock64();
-        if (dbg && it < 16) dbg[16 + it] = clock64();
-        const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
-        umma_bf16(tmem_base, ad, bd, idesc, it != 0);
-        for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
-        umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
-        if (it == num_k - 1) {
-          umma_commit(accum_bar);                            // accumulator complete
-          if (dbg) dbg[4] = clock64();
+    } else if (warp == 1) {
+      // ===== MMA issuer (one elected thread); descriptors are advanced by adding byte offsets >> 4 to the low word =====
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+      const int ksteps = a.KC / 16;
+      const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
+      const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
+      const uint32_t stage16 = stage_bytes >> 4;
+      int s = 0; uint32_t ph = 0, soff = 0;
+      for (int it = 0; it < num_k; ++it) {
+        mbar_wait(&full_bar[s], ph);
+        tcgen05_after_sync();
+        if (elect_one()) {
+          if (dbg && it == 0) dbg[3] = clock64();
+          if (dbg && it < 16) dbg[16 + it] = clock64();
+          const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
+          umma_bf16(tmem_base, ad, bd, idesc, it != 0);
+          for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+          umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
+          if (it == num_k - 1) {
+            umma_commit(accum_bar);                            // accumulator complete
+            if (dbg) dbg[4] = clock64();
+          }
         }
+        __syncwarp();
+        soff += stage16;
+        if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
       }
-      __syncwarp();
-      soff += stage16;
-      if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
     }
-  }
+}
   if (warp >= 2) {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
     // Compile-time variants (EPI) keep the per-element instruction count low: the three store paths and the
@@ -399,6 +467,12 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 long long* g_conv_dbg = nullptr;   // dev hook (otvm_debug_set_conv_timestamps)
 
 // ---------------------------------------------------------------------------------------------------------
+static int g_conv_halo = -1;
+static bool conv_halo_enabled() {
+  if (g_conv_halo < 0) { const char* e = getenv("OTVM_CONV_HALO"); g_conv_halo = (e && e[0] == '0') ? 0 : 1; }
+  return g_conv_halo == 1;
+}
+
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16; }
 
 static bool aligned_view(const void* ptr, int64_t ld) {
@@ -449,15 +523,15 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   return sm100 == 1;
 }
 
-template <int BN, bool GN, int EPI>
+template <int BN, bool GN, int EPI, bool HALO>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
-  launch_k(conv_tc_kernel<BN, GN, EPI>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
+  launch_k(conv_tc_kernel<BN, GN, EPI, HALO>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -465,7 +539,10 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 template <int BN>
 static int dispatch_conv_tc(bool gn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                             const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
-#define OTVM_CASE(G, E) if (gn == G && epi == (E)) return launch_conv_tc<BN, G, (E)>(tmA, tmB, tmO, tmR, a, grid, smem, s);
+#define OTVM_CASE(G, E)                                                                                     \
+  if (gn == G && epi == (E))                                                                                \
+    return a.halo ? launch_conv_tc<BN, G, (E), true>(tmA, tmB, tmO, tmR, a, grid, smem, s)                  \
+                  : launch_conv_tc<BN, G, (E), false>(tmA, tmB, tmO, tmR, a, grid, smem, s);
   OTVM_CASE(false, 0) OTVM_CASE(false, EPI_RES) OTVM_CASE(false, EPI_RELU2) OTVM_CASE(false, EPI_RES | EPI_RELU2)
   OTVM_CASE(false, EPI_DIRECT)
   if constexpr (BN >= 32) { OTVM_CASE(true, 0) OTVM_CASE(true, EPI_RES) }
@@ -479,28 +556,42 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.pad = p->pad; a.dil = p->dil; a.stride = p->stride;
   a.Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
   a.Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
-  int tw = 8; while (tw * 2 <= a.Wo && tw < 128) tw *= 2;
-  a.TW = tw; a.TH = 128 / tw;
-  a.tiles_x = ceil_div(a.Wo, a.TW); a.tiles_y = ceil_div(a.Ho, a.TH);
   a.KC = p->Cin % 64 == 0 ? 64 : p->Cin % 32 == 0 ? 32 : 16;
   a.nchunk = p->Cin / a.KC;
+  a.row_bytes = (uint32_t)a.KC * 2;
+  // halo mode: 3x3 stride-1 convolutions read ONE input patch per K-chunk for all 9 taps (16 x 8 output tile, so that
+  // every 8-row core-matrix group of the UMMA operand is one tile row and SBO = patch row pitch)
+  a.halo = conv_halo_enabled() && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->dil <= 4;
+  if (a.halo) {
+    a.TW = 8; a.TH = 16;
+    a.patch_bytes = (((uint32_t)(a.TW + 2 * p->dil) * (a.TH + 2 * p->dil) * a.row_bytes) + 1023u) & ~1023u;
+    a.na = a.nchunk > 1 ? 2 : 1;
+  } else {
+    int tw = 8; while (tw * 2 <= a.Wo && tw < 128) tw *= 2;
+    a.TW = tw; a.TH = 128 / tw;
+    a.patch_bytes = 0; a.na = 0;
+  }
+  a.tiles_x = ceil_div(a.Wo, a.TW); a.tiles_y = ceil_div(a.Ho, a.TH);
   const int bn = pick_bn(p->Cout);
-  a.a_bytes = 128u * a.KC * 2;
+  a.a_bytes = a.halo ? 0u : 128u * a.KC * 2;
   a.b_bytes = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
+  a.b_off = (uint32_t)a.na * a.patch_bytes;
   a.sbo = 8u * a.KC * 2;
   a.layout_type = a.KC == 64 ? 2u : a.KC == 32 ? 4u : 6u;
   const uint32_t stage = a.a_bytes + a.b_bytes;
   // two CTAs per SM (<= 96 KB of ring each) when the grid is larger than one wave; a grid that fits in one
   // wave is latency-bound instead, so it gets a deeper ring (up to ~190 KB, one CTA per SM)
   const int64_t ctas = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
-  const uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
+  uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
+  if (a.halo && a.b_off + 3 * a.b_bytes > budget) budget = 190u * 1024u;
   const int num_k = a.KH * a.KW * a.nchunk;
   int ksub = 1;                            // (K-chunk groups per barrier were measured slower; kept at 1)
   a.ksub = ksub;
-  int nstage = (int)(budget / (stage * ksub));
+  int nstage = (int)((budget - a.b_off) / (stage * ksub));
   if (nstage > 8) nstage = 8;
   const int ngroups_total = ceil_div(num_k, ksub);
   if (nstage > ngroups_total) nstage = ngroups_total < 2 ? 2 : ngroups_total;
+  if (nstage < 2) nstage = 2;
   a.nstage = nstage;
   // split-K: a grid that fills less than half of the SMs walks K serially at TMA/L2 latency; slice K across
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
@@ -513,7 +604,12 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     if (nsplit > 16) nsplit = 16;
     while (nsplit > 1 && (int64_t)nsplit * Mtot * p->Cout * 4 > p->workspace_bytes) --nsplit;
   }
-  a.k_per_split = ceil_div(num_k, nsplit);
+  if (a.halo) {                            // halo mode slices whole K-chunks (9 taps each)
+    const int cps = ceil_div(a.nchunk, nsplit);
+    a.k_per_split = cps * 9;
+  } else {
+    a.k_per_split = ceil_div(num_k, nsplit);
+  }
   nsplit = ceil_div(num_k, a.k_per_split);
   a.split_stride = Mtot * p->Cout;
   { const int gps = ceil_div(a.k_per_split, a.ksub); if (a.nstage > gps) a.nstage = gps < 2 ? 2 : gps; }
@@ -532,6 +628,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     uint64_t str[3] = {(uint64_t)p->in_ld * 2, (uint64_t)p->W * p->in_ld * 2, (uint64_t)p->H * p->W * p->in_ld * 2};
     // stride-2 convolutions: TMA traversal stride 2 along W and H (a box of 2*TW x 2*TH input pixels yields TW x TH)
     uint32_t box[4] = {(uint32_t)a.KC, (uint32_t)(a.TW * p->stride), (uint32_t)(a.TH * p->stride), 1};
+    if (a.halo) { box[1] = (uint32_t)(a.TW + 2 * p->dil); box[2] = (uint32_t)(a.TH + 2 * p->dil); }
     uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
     int rc = make_tmap_bf16(&tmA, p->in, 4, dims, str, box, swz, es);
     if (rc) return rc;
@@ -568,8 +665,9 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     ConvTcArgs b = a;                       // raw fp32 partial tiles into the workspace, epilogue deferred
     b.bias = nullptr; b.out = p->workspace; b.out_ps = p->Cout; b.out_cs = 1; b.res = nullptr; b.out_relu = nullptr;
     b.act = OTVM_ACT_NONE; b.out_f32 = 1; b.gn_stats = nullptr;
-    const size_t smem_s = (size_t)a.nstage * a.ksub * stage + 1024 + 16 * 8 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)a.k_per_split * 16;
-    b.aux_off = (uint32_t)((size_t)a.nstage * a.ksub * stage);
+    const size_t pipe_s = (size_t)a.b_off + (size_t)a.nstage * a.ksub * stage;
+    const size_t smem_s = pipe_s + 1024 + 16 * 8 + 64 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)a.k_per_split * 16;
+    b.aux_off = (uint32_t)pipe_s;
     int rc;
     switch (bn) {
       case 128: rc = dispatch_conv_tc<128>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
@@ -587,12 +685,12 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     OTVM_LAUNCH_CHECK();
     return OTVM_OK;
   }
-  size_t pipe = (size_t)nstage * ksub * stage;
+  size_t pipe = (size_t)a.b_off + (size_t)a.nstage * ksub * stage;
   const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
   size_t need = tma_store ? staging : 0;
   if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
-  const size_t smem = pipe + 1024 + 16 * 8 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
+  const size_t smem = pipe + 1024 + 16 * 8 + 64 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
   a.aux_off = (uint32_t)pipe;
   const bool gn = p->gn_stats != nullptr;
   const int epi = conv_tc_epi(p, bn);
@@ -639,4 +737,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 // dev hook (not part of the documented ABI): per-CTA clock64 timestamps of the next tcgen05 conv launches
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_timestamps(long long* buf) {
   otvm::g_conv_dbg = buf;
+}
+// dev hook: 3x3 halo-patch mode on/off (default on; env OTVM_CONV_HALO=0)
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_halo(int enabled) {
+  otvm::g_conv_halo = enabled ? 1 : 0;
 }

@@ -276,9 +276,23 @@ TC_CASES = [
 ]
 
 
+@pytest.fixture(params=[1, 0], ids=["halo", "per_tap"])
+def conv_halo(request):
+    """3x3 stride-1 convs: one shared-memory input patch for all 9 taps (default) vs one TMA box per tap"""
+    import ctypes
+    from otvm_b200 import _lib
+    lib = _lib.load()
+    lib.otvm_debug_set_conv_halo.argtypes = [ctypes.c_int]
+    lib.otvm_debug_set_conv_halo(request.param)
+    yield request.param
+    lib.otvm_debug_set_conv_halo(1)
+
+
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv2d_tcgen05(case):
+def test_conv2d_tcgen05(case, conv_halo):
     """bf16 stride-1 convs must run on the tcgen05 kernel and match fp32 math on the bf16-rounded operands"""
+    if conv_halo == 0 and case[2] != 3:
+        pytest.skip("per-tap mode only differs for 3x3 convolutions")
     ops = _ops()
     dtype = torch.bfloat16
     Cin, Cout, k, p, d, H, W = case
