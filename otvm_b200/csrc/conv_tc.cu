@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   uint64_t* empty_bar = full_bar + a.nstage;
   uint64_t* accum_bar = empty_bar + a.nstage;
   uint64_t* a_empty = accum_bar + 1;                                  // [4] patch ring (halo mode)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 4);
+  uint64_t* a_full = a_empty + 4;                                     // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 4);
   float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
 
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
     for (int s = 0; s < a.nstage; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(accum_bar, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(&a_empty[i], 1);
+    for (int i = 0; i < 4; ++i) { mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -126,29 +127,36 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if constexpr (HALO) {
     // iteration order: K-chunk major, the 9 taps inner; `it0`/`num_k` are multiples of 9 (whole chunks per K slice)
     const int d = a.dil, pw = a.TW + 2 * a.dil;                 // patch width in pixels
-    if (warp == 0) {
-      // ===== single TMA producer: per chunk one input patch (into the patch ring), per tap one weight box =====
-      int s = 0; uint32_t ph = 0; int as = 0; uint32_t aph = 0;
-      int tap = 0, chunk = it0 / 9;
+    if (warp == 2) {
+      // ===== patch producer (joins the epilogue afterwards): one input patch per K-chunk into the patch ring; it runs
+      // up to `na` chunks ahead of the MMAs, independent of the depth of the weight ring =====
+      int as = 0; uint32_t aph = 0;
       const int cx = x0 - a.pad, cy = y0 - a.pad;
-      const uint32_t b_tx = (uint32_t)(BN * a.KC * 2);
       const uint32_t a_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes;
+      const int c0 = it0 / 9, c1 = c0 + num_k / 9;
+      for (int chunk = c0; chunk < c1; ++chunk) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&a_full[as], a_tx);
+          tma_load_4d(smem + (size_t)as * a.patch_bytes, &tmA, &a_full[as], chunk * a.KC, cx, cy, n_img);
+        }
+        __syncwarp();
+        if (++as == a.na) { as = 0; aph ^= 1; }
+      }
+    } else if (warp == 0) {
+      // ===== weight producer: one [BN x KC] box per (chunk, tap) =====
+      int s = 0; uint32_t ph = 0;
+      int tap = 0, chunk = it0 / 9;
+      const uint32_t b_tx = (uint32_t)(BN * a.KC * 2);
       for (int it = 0; it < num_k; ++it) {
-        if (tap == 0) mbar_wait(&a_empty[as], aph ^ 1);
         mbar_wait(&empty_bar[s], ph ^ 1);
         if (elect_one()) {
-          uint8_t* sb = smem + a.b_off + (size_t)s * a.b_bytes;
-          if (tap == 0) {
-            mbar_arrive_expect_tx(&full_bar[s], b_tx + a_tx);
-            tma_load_4d(smem + (size_t)as * a.patch_bytes, &tmA, &full_bar[s], chunk * a.KC, cx, cy, n_img);
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], b_tx);
-          }
-          tma_load_2d(sb, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+          mbar_arrive_expect_tx(&full_bar[s], b_tx);
+          tma_load_2d(smem + a.b_off + (size_t)s * a.b_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1; }
-        if (++tap == 9) { tap = 0; ++chunk; if (++as == a.na) { as = 0; aph ^= 1; } }
+        if (++tap == 9) { tap = 0; ++chunk; }
       }
     } else if (warp == 1) {
       // ===== MMA issuer: A descriptor = patch slot + (ky*d*pw + kx*d) pixel rows; 8-row groups are tile rows (TW = 8),
@@ -160,8 +168,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       const uint64_t bdesc0 = make_smem_desc(base + a.b_off, a.sbo, a.layout_type);
       const uint32_t bstage16 = a.b_bytes >> 4, patch16 = a.patch_bytes >> 4;
       const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
-      int s = 0; uint32_t ph = 0, soff = 0, aoff = 0, toff = 0; int as = 0, kx = 0, ky = 0;
+      int s = 0; uint32_t ph = 0, soff = 0, aoff = 0, toff = 0, aph = 0; int as = 0, kx = 0, ky = 0;
       for (int it = 0; it < num_k; ++it) {
+        if ((kx | ky) == 0) mbar_wait(&a_full[as], aph);
         mbar_wait(&full_bar[s], ph);
         tcgen05_after_sync();
         const bool last_tap = kx == 2 && ky == 2;
@@ -176,7 +185,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         __syncwarp();
         soff += bstage16;
         if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
-        if (last_tap) { kx = 0; ky = 0; toff = 0; aoff += patch16; if (++as == a.na) { as = 0; aoff = 0; } }
+        if (last_tap) { kx = 0; ky = 0; toff = 0; aoff += patch16; if (++as == a.na) { as = 0; aoff = 0; aph ^= 1; } }
         else if (++kx == 3) { kx = 0; ++ky; toff += ky16 - 2 * kx16; }
         else toff += kx16;
       }
@@ -467,10 +476,11 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 long long* g_conv_dbg = nullptr;   // dev hook (otvm_debug_set_conv_timestamps)
 
 // ---------------------------------------------------------------------------------------------------------
-static int g_conv_halo = -1;
-static bool conv_halo_enabled() {
-  if (g_conv_halo < 0) { const char* e = getenv("OTVM_CONV_HALO"); g_conv_halo = (e && e[0] == '0') ? 0 : 1; }
-  return g_conv_halo == 1;
+static int g_conv_budget_kb = 0;
+static int g_conv_halo = -2;              // -2 unset, -1 auto (default), 0 off, 1 forced on
+static int conv_halo_mode() {
+  if (g_conv_halo == -2) { const char* e = getenv("OTVM_CONV_HALO"); g_conv_halo = e ? atoi(e) : -1; }
+  return g_conv_halo;
 }
 
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16; }
@@ -561,7 +571,12 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.row_bytes = (uint32_t)a.KC * 2;
   // halo mode: 3x3 stride-1 convolutions read ONE input patch per K-chunk for all 9 taps (16 x 8 output tile, so that
   // every 8-row core-matrix group of the UMMA operand is one tile row and SBO = patch row pitch)
-  a.halo = conv_halo_enabled() && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->dil <= 4;
+  // Measured on B200 (scripts/bench_conv2.py, profiles/r01c_conv_sweep.txt): the patch mode wins where the per-tap
+  // boxes are small and numerous (Cout <= 64, Cin <= 128: the full-resolution decoder / refinement layers, 1.4-1.8x);
+  // with BN = 128 or many K-chunks the 9-tap granularity of the patch ring costs more than the saved L2 traffic.
+  const int halo_mode = conv_halo_mode();              // -1 auto, 0 never, 1 whenever the shape allows
+  a.halo = halo_mode != 0 && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->dil <= 4 &&
+           (halo_mode == 1 || (p->Cout <= 64 && p->Cin <= 128));
   if (a.halo) {
     a.TW = 8; a.TH = 16;
     a.patch_bytes = (((uint32_t)(a.TW + 2 * p->dil) * (a.TH + 2 * p->dil) * a.row_bytes) + 1023u) & ~1023u;
@@ -582,7 +597,13 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   // two CTAs per SM (<= 96 KB of ring each) when the grid is larger than one wave; a grid that fits in one
   // wave is latency-bound instead, so it gets a deeper ring (up to ~190 KB, one CTA per SM)
   const int64_t ctas = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
-  uint32_t budget = ctas <= sm_count() ? 190u * 1024u : 96u * 1024u;
+  const int budget_kb = g_conv_budget_kb;   // dev override of the multi-wave ring budget (KB)
+  // multi-wave grids: narrow tiles (BN <= 64) have short K loops and are bound by per-CTA latency, so they trade ring
+  // depth for residency (4+ CTAs per SM); patch mode keeps 3 weight stages behind the patch ring
+  uint32_t budget = ctas <= sm_count() ? 190u * 1024u
+                  : budget_kb > 0 ? (uint32_t)budget_kb * 1024u
+                  : a.halo ? a.b_off + 3 * a.b_bytes
+                  : bn <= 64 ? 48u * 1024u : 96u * 1024u;
   if (a.halo && a.b_off + 3 * a.b_bytes > budget) budget = 190u * 1024u;
   const int num_k = a.KH * a.KW * a.nchunk;
   int ksub = 1;                            // (K-chunk groups per barrier were measured slower; kept at 1)
@@ -666,7 +687,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     b.bias = nullptr; b.out = p->workspace; b.out_ps = p->Cout; b.out_cs = 1; b.res = nullptr; b.out_relu = nullptr;
     b.act = OTVM_ACT_NONE; b.out_f32 = 1; b.gn_stats = nullptr;
     const size_t pipe_s = (size_t)a.b_off + (size_t)a.nstage * a.ksub * stage;
-    const size_t smem_s = pipe_s + 1024 + 16 * 8 + 64 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)a.k_per_split * 16;
+    const size_t smem_s = pipe_s + 1024 + 16 * 8 + 128 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)a.k_per_split * 16;
     b.aux_off = (uint32_t)pipe_s;
     int rc;
     switch (bn) {
@@ -690,7 +711,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   size_t need = tma_store ? staging : 0;
   if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
-  const size_t smem = pipe + 1024 + 16 * 8 + 64 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
+  const size_t smem = pipe + 1024 + 16 * 8 + 128 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
   a.aux_off = (uint32_t)pipe;
   const bool gn = p->gn_stats != nullptr;
   const int epi = conv_tc_epi(p, bn);
@@ -738,7 +759,8 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* d
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_timestamps(long long* buf) {
   otvm::g_conv_dbg = buf;
 }
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_budget_kb(int kb) { otvm::g_conv_budget_kb = kb; }
 // dev hook: 3x3 halo-patch mode on/off (default on; env OTVM_CONV_HALO=0)
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_halo(int enabled) {
-  otvm::g_conv_halo = enabled ? 1 : 0;
+  otvm::g_conv_halo = enabled;              // -1 auto, 0 off, 1 forced on
 }

@@ -285,7 +285,7 @@ def conv_halo(request):
     lib.otvm_debug_set_conv_halo.argtypes = [ctypes.c_int]
     lib.otvm_debug_set_conv_halo(request.param)
     yield request.param
-    lib.otvm_debug_set_conv_halo(1)
+    lib.otvm_debug_set_conv_halo(-1)
 
 
 @pytest.mark.parametrize("case", TC_CASES)
