@@ -29,8 +29,8 @@ constexpr uint32_t kKBytes = TKB * TDE * 2;           // 16 KB
 constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB
 constexpr uint32_t kPBytes = TQ * TKB * 2;            // 16 KB
 constexpr uint32_t kStage = kKBytes + kVBytes;
-constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256;
-constexpr int kReadThreads = 192;
+constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256 + 4 * TQ * 4;
+constexpr int kReadThreads = 320;        // TMA warp, MMA warp, 8 softmax warps
 constexpr float kLazyLog2 = 8.f;
 
 // 2^x on the SFU (ex2.approx.ftz): relative error ~2^-22, far below the bf16 rounding of P
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   uint64_t* p_empty = p_full + 2;          // 2
   uint64_t* o_done = p_empty + 2;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  float* xmax = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);      // [2 S buffers][2 halves][128 rows] row-max exchange
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -82,8 +83,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     mbar_init(q_full, 1);
     for (int s = 0; s < TNS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 4);
-      mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8);
+      mbar_init(&p_full[b], 8); mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_done, 1);
     fence_barrier_init();
@@ -154,51 +155,55 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       umma_commit(o_done);
     }
   } else {
-    // ===== softmax / correction / epilogue: thread = query row =====
-    const int qd = warp & 3;
+    // ===== softmax / correction / epilogue: 8 warps, TWO threads per query row =====
+    // Warps w and w+4 own the same TMEM lane quarter (w % 4); each takes 32 of the 64 keys of a block, so the
+    // per-block softmax (the stage that paced the kernel: one thread per row needed ~2000 cycles per block against
+    // 768 cycles of MMA) runs with twice the issue slots and overlaps one warp's ALU work with the other's MUFU.
+    // The pair agrees on the row maximum through shared memory + a 64-thread named barrier.
+    const int qd = warp & 3, half = (warp - 2) >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float m_used = -CUDART_INF_F, l_sum = 0.f;
+    const float scale = a.scale_log2;
     for (int j = 0; j < nb; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tcgen05_after_sync();
       if (dbg && threadIdx.x == 64 && j < 24) dbg[8 + j] = clock64();
-      uint32_t raw[2][32];
-      tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB, raw[0]);
-      tmem_ld32(tmem_s + lane_base + (uint32_t)b * TKB + 32, raw[1]);
+      uint32_t raw[32];
+      tmem_ld32(tmem_s + lane_base + (uint32_t)(b * TKB + half * 32), raw);
       tmem_wait_ld();
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);             // S[b] may be overwritten by block j+2
-      const int key0 = (kb0 + j) * TKB;
-      float sc[64];
-      float mx = -CUDART_INF_F;
+      if (lane == 0) mbar_arrive(&s_empty[b]);             // S[b] may be overwritten by block j+2 (8 arrivals)
+      const int key0 = (kb0 + j) * TKB + half * 32;
+      if (key0 + 32 > a.M) {                               // ragged last block only (warp-uniform branch)
 #pragma unroll
-      for (int i = 0; i < 64; ++i) { sc[i] = __uint_as_float(raw[i >> 5][i & 31]) * a.scale_log2; }
-      if (key0 + TKB > a.M) {                              // ragged last block only (block-uniform branch)
-#pragma unroll
-        for (int i = 0; i < 64; ++i) sc[i] = (key0 + i < a.M) ? sc[i] : -CUDART_INF_F;
+        for (int i = 0; i < 32; ++i) if (key0 + i >= a.M) raw[i] = 0xff800000u;    // -inf
       }
-      {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
-        float m8[8];
+      float mx;
+      {   // 4 independent chains instead of one 32-deep dependent FMNMX chain
+        float m4[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m8[i] = sc[i];
+        for (int i = 0; i < 4; ++i) m4[i] = __uint_as_float(raw[i]);
 #pragma unroll
-        for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], sc[i]);
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
+      xmax[(b * 2 + half) * TQ + r] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");          // the two warps of this lane quarter
+      mx = fmaxf(mx, xmax[(b * 2 + (half ^ 1)) * TQ + r]) * scale;       // scale > 0: max commutes with the scaling
       // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
       const bool grow = mx > m_used + kLazyLog2;
       if (j == 0) {
         m_used = mx;                                       // O not written yet: nothing to rescale
-      } else if (__any_sync(0xffffffffu, grow)) {
+      } else if (__any_sync(0xffffffffu, grow)) {          // both warps of a pair see the same rows -> same decision
         const float m_new = grow ? mx : m_used;
         const float alpha = exp2f(m_used - m_new);
         mbar_wait(&p_empty[b ^ 1], ((j - 1) >> 1) & 1);    // PV of block j-1 (and all earlier) complete
         tcgen05_after_sync();
 #pragma unroll 1
-        for (int c = 0; c < TDV; c += 32) {
+        for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {     // each warp rescales half of the columns
           uint32_t o[32];
           tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
           tmem_wait_ld();
@@ -213,25 +218,26 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       }
       if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);   // PV of block j-2 finished reading P[b]
       uint8_t* prow = sP + (size_t)b * kPBytes;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial sums (no 64-deep FADD chain)
+      float l4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial sums
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {                     // 8 chunks of 8 keys (16 bytes)
+      for (int ch = 0; ch < 4; ++ch) {                     // 4 chunks of 8 keys (16 bytes) of this thread's half row
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(sc[ch * 8 + 2 * e] - m_used), p1 = fast_exp2(sc[ch * 8 + 2 * e + 1] - m_used);
+          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch * 8 + 2 * e]), scale, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch * 8 + 2 * e + 1]), scale, -m_used));
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
           l4[e] += __low2float(h) + __high2float(h);       // the sum uses the rounded weights the MMA will see
           pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint32_t off = (uint32_t)r * 128u + (uint32_t)ch * 16u;
+        uint32_t off = (uint32_t)r * 128u + (uint32_t)(half * 4 + ch) * 16u;
         off ^= ((off >> 7) & 7u) << 4;
         *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       }
       l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);
+      if (lane == 0) mbar_arrive(&p_full[b]);              // 8 arrivals
       if (dbg && threadIdx.x == 64 && j < 24) dbg[32 + j] = clock64();
     }
     // ---- partial results of this split
@@ -239,10 +245,12 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     tcgen05_after_sync();
     if (dbg && threadIdx.x == 64) dbg[2] = clock64();
     const int q = q0 + r;
+    if (half == 1) xmax[r] = l_sum;                        // (all pair barriers of the loop are behind both warps)
     // partial O: TMEM -> swizzled fp32 tiles [8 chunks][128 rows][32 floats] in the drained K/V stages -> TMA store
-    // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction)
+    // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction); each warp of a pair
+    // drains half of the 256 columns
 #pragma unroll 1
-    for (int c = 0; c < TDV; c += 32) {
+    for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {
       uint32_t o[32];
       tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
       tmem_wait_ld();
@@ -255,15 +263,15 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       }
     }
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x == 64) {
 #pragma unroll 1
       for (int c = 0; c < TDV; c += 32) tma_store_3d(&tmO, sKV + (size_t)(c >> 5) * (TQ * 128), c0 + c, q0, split);
       tma_store_commit_and_wait();
     }
-    if (q < a.HW && blockIdx.y == 0) {
+    if (half == 0 && q < a.HW && blockIdx.y == 0) {
       a.ml_part[((int64_t)split * a.HW + q) * 2 + 0] = m_used;
-      a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum;
+      a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum + xmax[r];
     }
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     tcgen05_before_sync();
