@@ -30,7 +30,7 @@ constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB
 constexpr uint32_t kPBytes = TQ * TKB * 2;            // 16 KB
 constexpr uint32_t kStage = kKBytes + kVBytes;
 constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256 + 4 * TQ * 4;
-constexpr int kReadThreads = 320;        // TMA warp, MMA warp, 8 softmax warps
+constexpr int kReadThreads = 352;        // TMA warp, S-MMA warp, 8 softmax warps, PV-MMA warp
 constexpr float kLazyLog2 = 8.f;
 
 // 2^x on the SFU (ex2.approx.ftz): relative error ~2^-22, far below the bf16 rounding of P
@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   uint8_t* sP = sKV + TNS * kStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // TNS
-  uint64_t* kv_empty = kv_full + TNS;      // TNS
-  uint64_t* s_full = kv_empty + TNS;       // 2
+  uint64_t* k_full = bars + 1;             // TNS   K and V tiles of a block travel separately: K_j is needed one
+  uint64_t* k_empty = k_full + TNS;        // TNS   block earlier (S_j is issued before P_{j-1} V_{j-1}) and its slot is
+  uint64_t* v_full = k_empty + TNS;        // TNS   free again as soon as S_j has been computed
+  uint64_t* v_empty = v_full + TNS;        // TNS
+  uint64_t* s_full = v_empty + TNS;        // 2
   uint64_t* s_empty = s_full + 2;          // 2
   uint64_t* p_full = s_empty + 2;          // 2
   uint64_t* p_empty = p_full + 2;          // 2
@@ -81,7 +83,9 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < TNS; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < TNS; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8);
       mbar_init(&p_full[b], 8); mbar_init(&p_empty[b], 1);
@@ -105,41 +109,39 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(sQ, &tmQ, q_full, 0, q0);
       tma_load_2d(sQ + kQBytes / 2, &tmQ, q_full, 64, q0);
-      for (int j = 0; j < nb; ++j) {
+      auto load_k = [&](int j) {
         const int s = j % TNS;
-        mbar_wait(&kv_empty[s], ((j / TNS) & 1) ^ 1);
+        mbar_wait(&k_empty[s], ((j / TNS) & 1) ^ 1);
         uint8_t* st = sKV + (size_t)s * kStage;
         const int key0 = (kb0 + j) * TKB;
-        mbar_arrive_expect_tx(&kv_full[s], kStage);
-        tma_load_2d(st, &tmK, &kv_full[s], 0, key0);
-        tma_load_2d(st + kKBytes / 2, &tmK, &kv_full[s], 64, key0);
-        tma_load_2d(st + kKBytes, &tmV, &kv_full[s], key0, c0);
+        mbar_arrive_expect_tx(&k_full[s], kKBytes);
+        tma_load_2d(st, &tmK, &k_full[s], 0, key0);
+        tma_load_2d(st + kKBytes / 2, &tmK, &k_full[s], 64, key0);
+      };
+      load_k(0);
+      for (int j = 0; j < nb; ++j) {                       // issue order K_0, K_1, V_0, K_2, V_1, ...
+        if (j + 1 < nb) load_k(j + 1);
+        const int s = j % TNS;
+        mbar_wait(&v_empty[s], ((j / TNS) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], kVBytes);
+        tma_load_2d(sKV + (size_t)s * kStage + kKBytes, &tmV, &v_full[s], (kb0 + j) * TKB, c0);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== S issuer: S_j = Q K_j^T into the TMEM S buffer j & 1 =====
+    // Two issuing threads (this one and the PV issuer, warp 10): a single thread walking wait -> issue -> commit for
+    // both products was the pipeline's critical path (measured ~100 cycles per mbarrier operation and ~70 cycles
+    // per N=64 MMA issue: ~2000 cycles per block against 768 of tensor work).
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, TKB);
-      constexpr uint32_t idesc_o = make_idesc_bf16(128, TDV);
       const uint32_t q_addr = base;
-      auto issue_pv = [&](int j) {                         // O += P_j V_j
-        const int s = j % TNS, b = j & 1;
-        mbar_wait(&p_full[b], (j >> 1) & 1);
-        tcgen05_after_sync();
-        const uint64_t pdesc = make_smem_desc(base + kQBytes + TNS * kStage + (uint32_t)b * kPBytes, 1024, 2);
-        const uint64_t vdesc = make_smem_desc(base + kQBytes + (uint32_t)s * kStage + kKBytes, 1024, 2);
-#pragma unroll
-        for (int k = 0; k < TKB / 16; ++k)
-          umma_bf16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (j | k) != 0);
-        umma_commit(&kv_empty[s]);                         // K_j / V_j stage free
-        umma_commit(&p_empty[b]);                          // P buffer free, O holds blocks 0..j
-      };
       mbar_wait(q_full, 0);
       for (int j = 0; j < nb; ++j) {
         const int s = j % TNS, b = j & 1;
-        mbar_wait(&kv_full[s], (j / TNS) & 1);
         if (j >= 2) mbar_wait(&s_empty[b], ((j >> 1) - 1) & 1);      // softmax finished reading S[b] of block j-2
+        mbar_wait(&k_full[s], (j / TNS) & 1);
         tcgen05_after_sync();
+        if (dbg && j < 12) dbg[32 + j] = clock64();
         const uint32_t k_addr = base + kQBytes + (uint32_t)s * kStage;
 #pragma unroll
         for (int k = 0; k < TDE / 16; ++k) {               // two 64-wide atoms, 4 K-steps each
@@ -149,9 +151,27 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
           umma_bf16(tmem_s + (uint32_t)b * TKB, qd, kd, idesc_s, k != 0);
         }
         umma_commit(&s_full[b]);
-        if (j > 0) issue_pv(j - 1);
+        umma_commit(&k_empty[s]);                          // K_j slot free once S_j has been computed
       }
-      issue_pv(nb - 1);
+    }
+  } else if (warp == 10) {
+    // ===== PV issuer: O += P_j V_j =====
+    if (lane == 0) {
+      constexpr uint32_t idesc_o = make_idesc_bf16(128, TDV);
+      for (int j = 0; j < nb; ++j) {
+        const int s = j % TNS, b = j & 1;
+        mbar_wait(&v_full[s], (j / TNS) & 1);
+        mbar_wait(&p_full[b], (j >> 1) & 1);
+        tcgen05_after_sync();
+        if (dbg && j < 12) dbg[44 + j] = clock64();
+        const uint64_t pdesc = make_smem_desc(base + kQBytes + TNS * kStage + (uint32_t)b * kPBytes, 1024, 2);
+        const uint64_t vdesc = make_smem_desc(base + kQBytes + (uint32_t)s * kStage + kKBytes, 1024, 2);
+#pragma unroll
+        for (int k = 0; k < TKB / 16; ++k)
+          umma_bf16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (j | k) != 0);
+        umma_commit(&p_empty[b]);                          // P buffer free, O holds blocks 0..j
+        umma_commit(&v_empty[s]);                          // V_j slot free
+      }
       umma_commit(o_done);
     }
   } else {
@@ -169,7 +189,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       tcgen05_after_sync();
-      if (dbg && threadIdx.x == 64 && j < 24) dbg[8 + j] = clock64();
+      if (dbg && threadIdx.x == 64 && j < 12) dbg[8 + j] = clock64();
       uint32_t raw[32];
       tmem_ld32(tmem_s + lane_base + (uint32_t)(b * TKB + half * 32), raw);
       tmem_wait_ld();
@@ -216,29 +236,29 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         l_sum *= alpha;
         m_used = m_new;
       }
-      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);   // PV of block j-2 finished reading P[b]
       uint8_t* prow = sP + (size_t)b * kPBytes;
       float l4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial sums
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * e]), scale, -m_used));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * e + 1]), scale, -m_used));
+        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+        l4[e & 3] += __low2float(h) + __high2float(h);     // the sum uses the rounded weights the MMA will see
+        pk[e] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);   // PV of block j-2 finished reading P[b]
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {                     // 4 chunks of 8 keys (16 bytes) of this thread's half row
-        uint32_t pk[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[ch * 8 + 2 * e]), scale, -m_used));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[ch * 8 + 2 * e + 1]), scale, -m_used));
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          l4[e] += __low2float(h) + __high2float(h);       // the sum uses the rounded weights the MMA will see
-          pk[e] = *reinterpret_cast<uint32_t*>(&h);
-        }
         uint32_t off = (uint32_t)r * 128u + (uint32_t)(half * 4 + ch) * 16u;
         off ^= ((off >> 7) & 7u) << 4;
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
       }
       l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);              // 8 arrivals
-      if (dbg && threadIdx.x == 64 && j < 24) dbg[32 + j] = clock64();
+      if (dbg && threadIdx.x == 64 && j < 12) dbg[20 + j] = clock64();
     }
     // ---- partial results of this split
     mbar_wait(o_done, 0);

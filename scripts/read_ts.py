@@ -15,5 +15,8 @@ for hw_side, T in [(32, 8), (32, 16)]:
     lib.otvm_debug_set_read_timestamps(None)
     t = dbg[dbg[:, 0] > 0].cpu(); rel = (t - t[:, :1])
     print(f"T={T}: ctas={len(t)} start spread={(t[:,0]-t[:,0].min()).max().item()} setup={rel[:,1].median().item()} o_done={rel[:,2].median().item()} end={rel[:,3].median().item()}")
-    print("   s_full seen :", [int(x) for x in rel[0, 8:8+20]])
-    print("   p written   :", [int(x) for x in rel[0, 32:32+20]])
+    c = 5  # some CTA
+    print("   s_full seen :", [int(x) for x in rel[c, 8:20]])
+    print("   p written   :", [int(x) for x in rel[c, 20:32]])
+    print("   mma k_full  :", [int(x) for x in rel[c, 32:44]])
+    print("   mma p_full  :", [int(x) for x in rel[c, 44:56]])
