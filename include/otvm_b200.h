@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OTVM_ABI_VERSION 2
+#define OTVM_ABI_VERSION 3
 #if defined(__GNUC__)
 #define OTVM_API __attribute__((visibility("default")))
 #else
@@ -77,9 +77,19 @@ typedef struct {
   double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
   void* workspace;     int64_t workspace_bytes;   /* optional fp32 scratch: enables split-K for small grids */
   int32_t gn_stats_zeroed;                        /* 1: caller already zeroed gn_stats on this stream (one   */
-  int32_t reserved;                               /*    otvm_zero_async over an arena instead of a memset    */
-} otvm_conv_params;                               /*    node in front of every convolution)                  */
+  float gn_eps;                                   /*    otvm_zero_async over an arena instead of a memset    */
+                                                  /*    node in front of every convolution)                  */
+  /* Fused GroupNorm(32, Cout) (optional): with gn_gamma/gn_beta set the kernel normalises its own output,
+   * out = act(GN(conv + bias) * gamma + beta + res), replacing the otvm_gn_apply pass: statistics in the epilogue,
+   * a grid-wide barrier, then normalise from the accumulators still in tensor memory.  Requires a tcgen05 shape
+   * whose grid is one co-resident wave, gn_stats = a zeroed slot of >= 65 doubles ([32][2] sums + barrier counter,
+   * gn_stats_zeroed = 1) and no out_relu; ask otvm_conv2d_can_fuse_gn first (otvm_conv2d returns
+   * OTVM_ERR_UNSUPPORTED otherwise and launches nothing). */
+  const float* gn_gamma; const float* gn_beta;
+} otvm_conv_params;
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
+/* 1 when otvm_conv2d can run this problem with the GroupNorm fused into the convolution kernel (see gn_gamma) */
+OTVM_API int otvm_conv2d_can_fuse_gn(const otvm_conv_params* p);
 /* 1 when otvm_conv2d would run this problem on the tcgen05 implicit-GEMM kernel (else the FFMA kernel) */
 OTVM_API int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p);
 

@@ -28,7 +28,8 @@ class ConvParams(C.Structure):
         ("act", c_i32), ("relu_in", c_i32), ("dtype", c_i32), ("out_f32", c_i32),
         ("gn_stats", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
-        ("gn_stats_zeroed", c_i32), ("reserved", c_i32),
+        ("gn_stats_zeroed", c_i32), ("gn_eps", c_f),
+        ("gn_gamma", c_vp), ("gn_beta", c_vp),
     ]
 
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     "otvm_zero_async": (C.c_int, [c_vp, c_i64, c_vp]),
     "otvm_conv2d": (C.c_int, [C.POINTER(ConvParams), c_vp]),
     "otvm_conv2d_uses_tensor_cores": (C.c_int, [C.POINTER(ConvParams)]),
+    "otvm_conv2d_can_fuse_gn": (C.c_int, [C.POINTER(ConvParams)]),
     "otvm_gn_stats": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "otvm_gn_apply": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_f,
                                 c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
@@ -95,7 +97,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
-    if lib.otvm_version() != 2:
+    if lib.otvm_version() != 3:
         raise OtvmError("ABI version mismatch")
     _lib = lib
     return lib

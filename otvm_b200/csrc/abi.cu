@@ -34,7 +34,7 @@ int sm_count() {
 }
 
 int conv2d_simt(const otvm_conv_params* p, cudaStream_t s);
-int conv2d_tc(const otvm_conv_params* p, cudaStream_t s);
+int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run = false);
 bool conv2d_tc_supported(const otvm_conv_params* p);
 int memory_read_simt(const otvm_read_params* p, cudaStream_t s);
 int memory_read_tc(const otvm_read_params* p, cudaStream_t s);
@@ -90,11 +90,17 @@ extern "C" int otvm_conv2d_uses_tensor_cores(const otvm_conv_params* p) {
   return conv_check(p) == OTVM_OK && conv2d_tc_supported(p) ? 1 : 0;
 }
 
+extern "C" int otvm_conv2d_can_fuse_gn(const otvm_conv_params* p) {
+  if (conv_check(p) != OTVM_OK || !p->gn_gamma || !conv2d_tc_supported(p)) return 0;
+  return conv2d_tc(p, nullptr, /*dry_run=*/true) == OTVM_OK ? 1 : 0;
+}
+
 extern "C" int otvm_conv2d(const otvm_conv_params* p, void* stream) {
   int rc = conv_check(p);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (conv2d_tc_supported(p)) return conv2d_tc(p, s);
+  if (p->gn_gamma) return OTVM_ERR_UNSUPPORTED;            // only the tcgen05 kernel normalises in its epilogue
   return conv2d_simt(p, s);
 }
 

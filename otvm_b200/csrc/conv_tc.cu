@@ -40,6 +40,7 @@ struct ConvTcArgs {
   bf16* out_relu; int64_t out_relu_ld;
   int act, out_f32;
   double* gn_stats;
+  const float* gn_gamma; const float* gn_beta; float gn_eps;   // GN == 2: normalise in this kernel (grid barrier)
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
 };
 
@@ -63,8 +64,15 @@ __device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int r, float* sr
 }
 
 enum { EPI_RES = 1, EPI_RELU2 = 2, EPI_DIRECT = 4 };
+enum { GN_NONE = 0, GN_STATS = 1, GN_FUSED = 2 };   // GN_FUSED: statistics -> grid barrier -> normalise + affine in the epilogue
 
-template <int BN, bool GN, int EPI, bool HALO>
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BN, int GN, int EPI, bool HALO>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const bool valid = oy < a.Ho && ox < a.Wo;
     const int64_t pix = ((int64_t)n_img * a.Ho + oy) * a.Wo + ox;
     constexpr int CH = BN >= 32 ? 32 : 16;                   // columns per TMEM load
-    const int cg = GN ? a.Cout / 32 : 0;                     // channels per GroupNorm group
+    const int cg = GN != GN_NONE ? a.Cout / 32 : 0;          // channels per GroupNorm group
     const int cgc = cg < CH ? cg : CH;
     float* sred = reinterpret_cast<float*>(smem + 128u * BN * 2u);   // behind the staging tile, inside the drained stages
     // act(v) = max(v,0) + slope*min(v,0): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
@@ -273,6 +281,71 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     mbar_wait(accum_bar, 0);
     tcgen05_after_sync();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
+    if constexpr (GN == GN_FUSED) {
+      // ---- fused GroupNorm: pass 1 accumulates the statistics of the fp32 convolution output (the accumulator
+      // stays in TMEM), a grid-wide barrier makes every CTA's contribution visible, pass 2 (the loop below)
+      // normalises.  The host only selects this variant when the whole grid is co-resident (one wave).
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CH) {
+        if (n0 + c >= a.Cout) break;
+        uint32_t raw[CH];
+        if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+        else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+        tmem_wait_ld();
+        float qv[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) qv[j] = valid ? __uint_as_float(raw[j]) + sbias[c + j] : 0.f;
+        const int slot0 = c / cgc;
+        switch (cgc) {
+          case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
+          case 2: gn_chunk<CH, 2>(qv, r, sred, slot0); break;
+          case 4: gn_chunk<CH, 4>(qv, r, sred, slot0); break;
+          case 8: gn_chunk<CH, 8>(qv, r, sred, slot0); break;
+          case 16: gn_chunk<CH, 16>(qv, r, sred, slot0); break;
+          default: gn_chunk<CH, CH>(qv, r, sred, slot0); break;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int e = threadIdx.x - 64;
+      {
+        const int nslot = BN / cgc;
+        if (e < 2 * nslot) {
+          const int which = e / nslot, slot = e - which * nslot;
+          if (n0 + slot * cgc < a.Cout) {
+            const float* row = sred + (which * 32 + slot) * kSredPitch;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int i = 0; i < 128; ++i) acc += row[i];
+            atomicAdd(&a.gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");          // this CTA's atomics are issued
+      if (e == 0) {
+        unsigned int* ctr = reinterpret_cast<unsigned int*>(a.gn_stats + 64);     // zeroed with the statistics arena
+        const unsigned int total = gridDim.x * gridDim.y;
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(ctr) < total) {
+          __nanosleep(40);
+          if (++spins > (1u << 24)) __trap();                 // a missing CTA traps instead of hanging the GPU
+        }
+        __threadfence();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (e < BN && n0 + e < a.Cout) {
+        const int ch = n0 + e, g = ch / cg;
+        const double cnt = (double)a.Ho * a.Wo * cg;
+        const double mean = __ldcg(&a.gn_stats[g * 2]) / cnt;
+        const double var = __ldcg(&a.gn_stats[g * 2 + 1]) / cnt - mean * mean;
+        const float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)a.gn_eps));
+        const float sc = rstd * a.gn_gamma[ch];
+        sstat[e] = sc;
+        sstat[128 + e] = a.gn_beta[ch] - (float)mean * sc;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
 #pragma unroll 1
     for (int c = 0; c < BN; c += CH) {
       const int cbase = n0 + c;
@@ -297,7 +370,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         v[j] = __uint_as_float(raw[j]) + b4.x; v[j + 1] = __uint_as_float(raw[j + 1]) + b4.y;
         v[j + 2] = __uint_as_float(raw[j + 2]) + b4.z; v[j + 3] = __uint_as_float(raw[j + 3]) + b4.w;
       }
-      if constexpr (GN) {
+      if constexpr (GN == GN_FUSED) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = fmaf(v[j], sstat[c + j], sstat[128 + c + j]);
+      }
+      if constexpr (GN == GN_STATS) {
         // statistics of the values GroupNorm will read back (rounded to bf16); rows outside the image count 0
         float qv[CH];
 #pragma unroll
@@ -377,7 +454,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         tma_store_commit_and_wait();
       }
     }
-    if constexpr (GN) {
+    if constexpr (GN == GN_STATS) {
       asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
       const int e = threadIdx.x - 64;                         // 0..127: (which, slot) = (e / 32.., e % nslot)
       const int nslot = BN / cgc;                             // <= 32 (host-checked)
@@ -533,7 +610,7 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   return sm100 == 1;
 }
 
-template <int BN, bool GN, int EPI, bool HALO>
+template <int BN, int GN, int EPI, bool HALO>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr = false;
@@ -547,20 +624,22 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 }
 
 template <int BN>
-static int dispatch_conv_tc(bool gn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+static int dispatch_conv_tc(int gn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                             const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
 #define OTVM_CASE(G, E)                                                                                     \
   if (gn == G && epi == (E))                                                                                \
     return a.halo ? launch_conv_tc<BN, G, (E), true>(tmA, tmB, tmO, tmR, a, grid, smem, s)                  \
                   : launch_conv_tc<BN, G, (E), false>(tmA, tmB, tmO, tmR, a, grid, smem, s);
-  OTVM_CASE(false, 0) OTVM_CASE(false, EPI_RES) OTVM_CASE(false, EPI_RELU2) OTVM_CASE(false, EPI_RES | EPI_RELU2)
-  OTVM_CASE(false, EPI_DIRECT)
-  if constexpr (BN >= 32) { OTVM_CASE(true, 0) OTVM_CASE(true, EPI_RES) }
+  OTVM_CASE(GN_NONE, 0) OTVM_CASE(GN_NONE, EPI_RES) OTVM_CASE(GN_NONE, EPI_RELU2) OTVM_CASE(GN_NONE, EPI_RES | EPI_RELU2)
+  OTVM_CASE(GN_NONE, EPI_DIRECT)
+  if constexpr (BN >= 32) {
+    OTVM_CASE(GN_STATS, 0) OTVM_CASE(GN_STATS, EPI_RES) OTVM_CASE(GN_FUSED, 0) OTVM_CASE(GN_FUSED, EPI_RES)
+  }
 #undef OTVM_CASE
   return OTVM_ERR_UNSUPPORTED;
 }
 
-int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
+int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   ConvTcArgs a;
   a.N = p->N; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
   a.pad = p->pad; a.dil = p->dil; a.stride = p->stride;
@@ -638,8 +717,14 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   a.res = static_cast<const bf16*>(p->res); a.res_ld = p->res_ld;
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
+  a.gn_gamma = p->gn_gamma; a.gn_beta = p->gn_beta; a.gn_eps = p->gn_eps;
   a.dbg = g_conv_dbg;
-  if (p->gn_stats && !p->gn_stats_zeroed) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
+  const bool fuse_gn = p->gn_gamma != nullptr;
+  if (fuse_gn) {
+    // the in-kernel GroupNorm needs: statistics slot (+ barrier counter) already zeroed, one co-resident wave, no split-K
+    if (!p->gn_stats || !p->gn_stats_zeroed || !p->gn_beta || nsplit > 1 || p->out_relu) return OTVM_ERR_UNSUPPORTED;
+  }
+  if (p->gn_stats && !p->gn_stats_zeroed && !dry_run) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
 
   const CUtensorMapSwizzle swz = a.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : a.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -691,10 +776,10 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
     b.aux_off = (uint32_t)pipe_s;
     int rc;
     switch (bn) {
-      case 128: rc = dispatch_conv_tc<128>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
-      case 64: rc = dispatch_conv_tc<64>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
-      case 32: rc = dispatch_conv_tc<32>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
-      default: rc = dispatch_conv_tc<16>(false, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      case 128: rc = dispatch_conv_tc<128>(GN_NONE, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      case 64: rc = dispatch_conv_tc<64>(GN_NONE, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      case 32: rc = dispatch_conv_tc<32>(GN_NONE, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
+      default: rc = dispatch_conv_tc<16>(GN_NONE, EPI_DIRECT, tmA, tmB, tmA, tmA, b, grid, smem_s, s); break;
     }
     if (rc) return rc;
     const int64_t total = Mtot * (p->Cout / 4);
@@ -713,8 +798,16 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s) {
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
   const size_t smem = pipe + 1024 + 16 * 8 + 128 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
   a.aux_off = (uint32_t)pipe;
-  const bool gn = p->gn_stats != nullptr;
+  const int gn = fuse_gn ? GN_FUSED : p->gn_stats != nullptr ? GN_STATS : GN_NONE;
   const int epi = conv_tc_epi(p, bn);
+  if (fuse_gn) {
+    const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
+    const int64_t resident = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);
+    if (ctas > resident || (epi & ~EPI_RES) != 0) return OTVM_ERR_UNSUPPORTED;
+    if (dry_run) return OTVM_OK;
+  } else if (dry_run) {
+    return OTVM_ERR_UNSUPPORTED;
+  }
   switch (bn) {
     case 128: return dispatch_conv_tc<128>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
     case 64: return dispatch_conv_tc<64>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);

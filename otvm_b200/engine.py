@@ -135,7 +135,7 @@ class FramePlan:
         self.bufs: Dict[str, torch.Tensor] = {}
         # GroupNorm statistics arena: one [32][2] fp64 slot per normalised convolution, zeroed ONCE per frame
         # (one memset node instead of one in front of each of the 66 convolutions)
-        self.gn_arena = torch.zeros(128, 64, dtype=torch.float64, device=device)
+        self.gn_arena = torch.zeros(128, 72, dtype=torch.float64, device=device)   # [32][2] sums + barrier counter + pad
         self.gn_slots: Dict[str, int] = {}
         self.pending: Optional[int] = None          # bank slot whose memorize pass is deferred to the next frame
 
@@ -274,7 +274,18 @@ class Engine:
         """WS-conv -> GroupNorm(32) -> activation (+residual).  GN statistics are accumulated by the conv
         epilogue; the normalise/affine/activation pass runs in place unless ``out`` is given."""
         stats = pl.gn_slot(conv)                    # zeroed by _frame_body (one memset per frame)
-        raw = self._conv(pl, conv, x, raw_name, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True)
+        g, b = self.w.norm[norm]
+        w = self.w.conv[conv][0]
+        N, H, W, _ = x.shape
+        kh = w.shape[1]
+        Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
+        raw = pl.buf(raw_name or conv, (N, Ho, Wo, w.shape[0]))
+        dst = out if out is not None else raw
+        # one kernel when the grid is a single co-resident wave: statistics, grid barrier, normalise from TMEM
+        if self._conv(pl, conv, x, out=dst, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True,
+                      gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res):
+            return dst
         return self._gn(pl, norm, raw, act=act, res=res, out=out, stats=stats)
 
     def _gn_bottleneck(self, pl, p, x, stride, dil, out=None):

@@ -7,6 +7,7 @@ stream and raises :class:`otvm_b200._lib.OtvmError` on failure.  No wrapper comp
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -36,6 +37,7 @@ class Profiler:
         return out
 
 
+GN_FUSE = os.environ.get("OTVM_GN_FUSE", "1") != "0"      # GroupNorm inside the convolution kernel where possible
 PROFILER: "Profiler | None" = None
 PROFILE_SHAPES = False          # dev: one profiler key per conv shape
 
@@ -76,9 +78,15 @@ def _p(t):
 
 
 def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=False, res=None, out_relu=None,
-           gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None):
+           gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None, gn_fuse=None, gn_raw_out=None):
     """x [N,H,W,Cin(view)], w [Cout,KH,KW,Cin] packed, out NHWC view (or any buffer with ``out_strides`` =
-    (pixel_stride, channel_stride) in elements, used for the channel-major value bank)."""
+    (pixel_stride, channel_stride) in elements, used for the channel-major value bank).
+
+    ``gn_fuse=(gamma, beta, eps)``: GroupNorm(32) + affine (+res, +act) inside the convolution kernel when the
+    library can (one co-resident wave, see include/otvm_b200.h); the call then returns ``True``.  When it cannot,
+    nothing of the normalisation is done, the raw convolution (+ statistics) is written to ``gn_raw_out`` and
+    ``False`` is returned (the caller follows with :func:`gn_apply`).  Without ``gn_fuse`` the function returns
+    ``out``."""
     lib = _lib.load()
     N, H, W, Cx = x.shape
     Cout, KH, KW, Cin = w.shape
@@ -99,12 +107,23 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
     p.gn_stats_zeroed = int(gn_stats_zeroed)
+    fused = None
+    if gn_fuse is not None:
+        gamma, beta, eps = gn_fuse
+        p.gn_gamma, p.gn_beta, p.gn_eps = gamma.data_ptr(), beta.data_ptr(), eps
+        if workspace is not None:
+            p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+        fused = GN_FUSE and bool(lib.otvm_conv2d_can_fuse_gn(C.byref(p)))
+        if not fused:                     # plain convolution + statistics; residual / activation belong to gn_apply
+            p.gn_gamma = p.gn_beta = None
+            p.res, p.res_ld, p.act = None, 0, ACT_NONE
+            p.out, p.out_ps, p.out_cs = gn_raw_out.data_ptr(), _ld(gn_raw_out), 1
     if workspace is not None:
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     assert w.dtype == x.dtype and (bias is None or bias.dtype == torch.float32)
     if PROFILER is None:
         check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d")
-        return out
+        return out if fused is None else fused
     Ho = (H + 2 * pad - dil * (KH - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (KW - 1) - 1) // stride + 1
     key = "conv_tcgen05" if lib.otvm_conv2d_uses_tensor_cores(C.byref(p)) else "conv_ffma"
@@ -114,7 +133,7 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     nb = (N * H * W * Cin + Cout * KH * KW * Cin) * es + N * Ho * Wo * Cout * out.element_size()
     _timed(key, lambda: check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d"),
            2.0 * N * Ho * Wo * Cout * KH * KW * Cin, float(nb))
-    return out
+    return out if fused is None else fused
 
 
 def zero_(t):

@@ -342,6 +342,48 @@ def test_conv2d_tcgen05(case, conv_halo):
         assert rel_err(nchw(out4), want2) < 1e-2 and rel_err(nchw(outr4), want2) < 1e-2
 
 
+FUSED_GN_CASES = [
+    # Cin, Cout, k, pad, dil, H, W, with_res, act
+    (64, 64, 1, 0, 1, 32, 32, False, "relu"),
+    (64, 256, 1, 0, 1, 32, 32, True, "relu"),
+    (256, 256, 3, 2, 2, 24, 40, False, "relu"),
+    (512, 2048, 1, 0, 1, 16, 16, True, "relu"),
+    (256, 256, 3, 1, 1, 32, 32, False, "leaky"),
+    (128, 128, 3, 1, 1, 64, 64, False, "none"),
+    (64, 64, 3, 1, 1, 64, 64, True, "relu"),
+]
+
+
+@pytest.mark.parametrize("case", FUSED_GN_CASES)
+def test_conv2d_fused_groupnorm(case):
+    """conv -> GroupNorm(32) -> (+res) -> act in ONE kernel (statistics, grid barrier, normalise from tensor memory)
+    against F.conv2d + F.group_norm in fp32 on the bf16-rounded operands (layers_WS.py:26-27, resnet_GN_WS.py:69-88)"""
+    ops = _ops()
+    dtype = torch.bfloat16
+    Cin, Cout, k, p, d, H, W, with_res, act = case
+    g = torch.Generator().manual_seed(sum(case[:7]))
+    x = torch.randn(1, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    gamma, beta = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    y = F.group_norm(F.conv2d(rnd(dtype, x), rnd(dtype, w), b, 1, p, d), 32, gamma, beta, 1e-5)
+    res = torch.randn_like(y)
+    if with_res:
+        y = y + rnd(dtype, res)
+    y = {"relu": F.relu, "leaky": lambda t: F.leaky_relu(t, 0.01), "none": lambda t: t}[act](y)
+    actc = {"relu": ops.ACT_RELU, "leaky": ops.ACT_LEAKY, "none": ops.ACT_NONE}[act]
+    for trial in range(2):                         # second call on a re-zeroed slot: the barrier counter is reusable
+        arena = torch.zeros(72, dtype=torch.float64, device=DEV)
+        out = torch.zeros(1, H, W, Cout + 8, dtype=dtype, device=DEV)[..., :Cout]
+        raw = torch.zeros(1, H, W, Cout, dtype=dtype, device=DEV)
+        fused = ops.conv2d(nhwc(x, dtype), w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype), b.to(DEV), out, pad=p, dil=d,
+                           gn_stats=arena, gn_stats_zeroed=True, gn_fuse=(gamma.to(DEV), beta.to(DEV), 1e-5), gn_raw_out=raw,
+                           res=nhwc(res, dtype) if with_res else None, act=actc)
+        assert fused is True, "these shapes are single-wave tcgen05 grids"
+        torch.cuda.synchronize()
+        assert rel_err(nchw(out), y) < 1e-2
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("s", [1, 2, 3, 6])
 def test_conv1x1_on_ppm_cells(s, dtype):
