@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ __align__(16) float As[2][BK][BM + LDS_PAD];
   __shared__ __align__(16) float Bs[2][BK][BN + LDS_PAD];
-  __shared__ float gsum[BN][2];
+  __shared__ double gsum[BN][2];   // fp64: sums of fp32 partials are exact -> order-independent
 
   const int t = threadIdx.x;
   const T* __restrict__ in = static_cast<const T*>(a.in);
@@ -168,15 +168,15 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   }
   if (a.gn_stats) {
     // per-channel partial sums of this 64-pixel x 64-channel tile -> one fp64 atomic per channel
-    if (t < BN) { gsum[t][0] = 0.f; gsum[t][1] = 0.f; }
+    if (t < BN) { gsum[t][0] = 0.0; gsum[t][1] = 0.0; }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { atomicAdd(&gsum[tx * 4 + j][0], s1[j]); atomicAdd(&gsum[tx * 4 + j][1], s2[j]); }
+    for (int j = 0; j < 4; ++j) { atomicAdd(&gsum[tx * 4 + j][0], (double)s1[j]); atomicAdd(&gsum[tx * 4 + j][1], (double)s2[j]); }
     __syncthreads();
     if (t < BN && n0 + t < a.Cout) {
       int g = (n0 + t) / (a.Cout / 32);
-      atomicAdd(&a.gn_stats[g * 2 + 0], (double)gsum[t][0]);
-      atomicAdd(&a.gn_stats[g * 2 + 1], (double)gsum[t][1]);
+      atomicAdd(&a.gn_stats[g * 2 + 0], gsum[t][0]);
+      atomicAdd(&a.gn_stats[g * 2 + 1], gsum[t][1]);
     }
   }
 }

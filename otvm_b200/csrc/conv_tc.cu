@@ -488,12 +488,12 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             int64_t out_cs, int out_f32, bf16* __restrict__ out_relu,
                                                             int64_t out_relu_ld, double* __restrict__ gn_stats) {
   pdl_sync();                                  // PDL contract (common.cuh)
-  __shared__ float sstat[32][2];
+  __shared__ double sstat[32][2];      // fp64 partials: (near-)exact sums, so the atomic order does not change the result
   const int c4n = Cout >> 2;
   const int64_t total = M * c4n;
   const int cg = gn_stats ? Cout / 32 : 1;
   if (gn_stats) {
-    if (threadIdx.x < 32) { sstat[threadIdx.x][0] = 0.f; sstat[threadIdx.x][1] = 0.f; }
+    if (threadIdx.x < 32) { sstat[threadIdx.x][0] = 0.0; sstat[threadIdx.x][1] = 0.0; }
     __syncthreads();
   }
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -509,10 +509,11 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
       for (int h = 0; h < 2; ++h) {
         const float q0 = __bfloat162float(__float2bfloat16_rn(v[2 * h])), q1 = __bfloat162float(__float2bfloat16_rn(v[2 * h + 1]));
         if (cg >= 2) {
-          atomicAdd(&sstat[(c + 2 * h) / cg][0], q0 + q1); atomicAdd(&sstat[(c + 2 * h) / cg][1], q0 * q0 + q1 * q1);
+          atomicAdd(&sstat[(c + 2 * h) / cg][0], (double)q0 + (double)q1);
+          atomicAdd(&sstat[(c + 2 * h) / cg][1], (double)q0 * q0 + (double)q1 * q1);
         } else {
-          atomicAdd(&sstat[c + 2 * h][0], q0); atomicAdd(&sstat[c + 2 * h][1], q0 * q0);
-          atomicAdd(&sstat[c + 2 * h + 1][0], q1); atomicAdd(&sstat[c + 2 * h + 1][1], q1 * q1);
+          atomicAdd(&sstat[c + 2 * h][0], (double)q0); atomicAdd(&sstat[c + 2 * h][1], (double)q0 * q0);
+          atomicAdd(&sstat[c + 2 * h + 1][0], (double)q1); atomicAdd(&sstat[c + 2 * h + 1][1], (double)q1 * q1);
         }
       }
     }
@@ -544,8 +545,8 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   if (gn_stats) {
     __syncthreads();
     if (threadIdx.x < 32) {
-      atomicAdd(&gn_stats[threadIdx.x * 2 + 0], (double)sstat[threadIdx.x][0]);
-      atomicAdd(&gn_stats[threadIdx.x * 2 + 1], (double)sstat[threadIdx.x][1]);
+      atomicAdd(&gn_stats[threadIdx.x * 2 + 0], sstat[threadIdx.x][0]);
+      atomicAdd(&gn_stats[threadIdx.x * 2 + 1], sstat[threadIdx.x][1]);
     }
   }
 }

@@ -148,6 +148,8 @@ class FramePlan:
         if t is None:
             alloc = torch.zeros if zero else torch.empty
             t = alloc(shape, dtype=dtype or self.dtype, device=self.device)
+            if not zero and t.is_floating_point() and os.environ.get("OTVM_DEBUG_POISON") == "1":
+                t.fill_(float("nan"))               # dev: a kernel reading bytes nobody wrote shows up as NaN
             self.bufs[name] = t
         assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
         return t
