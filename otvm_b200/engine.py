@@ -202,6 +202,42 @@ class MemoryBank:
         return s * self.hw
 
 
+class _Fork:
+    """``with eng.fork("tag") as f: ...`` issues the body on a side stream forked from the current one (also inside a
+    CUDA-graph capture, where it becomes a parallel branch of the graph); ``f.join()`` makes the current stream wait
+    for it.  Independent chains of small-grid kernels (downsample branch of a bottleneck, the four pyramid-pooling
+    branches, the skip-connection halves of the STM decoder, Key / Value projections) fill SMs the main chain
+    leaves idle.  Every branch gets its own split-K workspace; buffers are keyed by layer name, so branches never
+    share outputs."""
+
+    def __init__(self, eng, tag):
+        self.eng, self.tag, self.stream = eng, f"{eng._ws_tag}.{tag}", None
+
+    def __enter__(self):
+        eng = self.eng
+        if eng.fork_enabled and ops.PROFILER is None:
+            self.stream = eng.streams.get(self.tag)
+            if self.stream is None:
+                self.stream = eng.streams[self.tag] = torch.cuda.Stream(device=eng.device)
+            self.stream.wait_stream(torch.cuda.current_stream())
+            self.ctx = torch.cuda.stream(self.stream)
+            self.ctx.__enter__()
+            self.prev_tag, eng._ws_tag = eng._ws_tag, self.tag
+            eng._open_forks += 1
+        return self
+
+    def __exit__(self, *exc):
+        if self.stream is not None:
+            self.eng._ws_tag = self.prev_tag
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+            self.eng._open_forks -= 1
+
+
 class Engine:
     def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16):
         self.dtype, self.device = dtype, torch.device(device)
@@ -214,7 +250,10 @@ class Engine:
         # it is issued at the START of frame t+1 on a side stream, concurrently with Encoder_Q / KV_Q of t+1 (both
         # are chains of small-grid convolutions that leave most SMs idle on their own), and joined before the read
         self.defer_memorize = os.environ.get("OTVM_OVERLAP", "1") != "0"
-        self.side_stream = None
+        self.fork_enabled = os.environ.get("OTVM_FORK", "1") != "0"     # parallel graph branches inside a frame
+        self.streams: Dict[str, "torch.cuda.Stream"] = {}
+        self._ws_tag = "main"
+        self._open_forks = 0                       # branches issued and not yet joined
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
         self.warm, self.seen = set(), set()
         self.graph_launches: Dict[tuple, int] = {}
@@ -233,9 +272,11 @@ class Engine:
             self.banks[k] = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), self.bank_capacity, self.dtype, self.device)
         return self.banks[k]
 
+    def fork(self, tag):
+        return _Fork(self, tag)
+
     # ---- building blocks ---------------------------------------------------------------------------
-    def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, ws_name="conv_splitk_ws",
-              **kw):
+    def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, **kw):
         w, b = self.w.conv[name]
         N, H, W, _ = x.shape
         kh = w.shape[1]
@@ -243,25 +284,29 @@ class Engine:
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         if out is None:
             out = pl.buf(out_name or name, (N, Ho, Wo, w.shape[0]))
-        ws = pl.buf(ws_name, (16 << 20,), torch.float32)       # 64 MB fp32 scratch for split-K partial tiles (per stream)
+        ws = pl.buf("conv_splitk_ws." + self._ws_tag, (16 << 20,), torch.float32)   # 64 MB split-K scratch per stream
         return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, workspace=ws, **kw)
 
-    def _tv_bottleneck(self, pl, p, x, stride, out=None, ws_name="conv_splitk_ws"):
+    def _tv_bottleneck(self, pl, p, x, stride, out=None):
         """torchvision Bottleneck with BN folded; ReLUs and the residual add live in the conv epilogues."""
-        kw = dict(ws_name=ws_name)
-        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU, **kw)
-        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU, **kw)
-        idn = self._conv(pl, p + ".downsample", x, stride=stride, **kw) if (p + ".downsample") in self.w.conv else x
-        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU, **kw)
+        idn, f = x, None
+        if (p + ".downsample") in self.w.conv:
+            with self.fork("ds") as f:
+                idn = self._conv(pl, p + ".downsample", x, stride=stride)
+        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU)
+        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU)
+        if f is not None:
+            f.join()
+        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU)
 
-    def _tv_encoder(self, pl, enc, x, ws_name="conv_splitk_ws"):
-        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU, ws_name=ws_name)
+    def _tv_encoder(self, pl, enc, x):
+        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU)
         N, H, W, C = c1.shape
         x = ops.maxpool3x3s2(c1, pl.buf(enc + ".pool", (N, (H + 1) // 2, (W + 1) // 2, C)))
         feats = []
         for lname, blocks, stride in (("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2)):
             for b in range(blocks):
-                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1, ws_name=ws_name)
+                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1)
             feats.append(x)
         return feats       # r2, r3, r4
 
@@ -284,13 +329,20 @@ class Engine:
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         raw = pl.buf(raw_name or conv, (N, Ho, Wo, w.shape[0]))
         dst = out if out is not None else raw
-        # one kernel when the grid is a single co-resident wave: statistics, grid barrier, normalise from TMEM
-        if self._conv(pl, conv, x, out=dst, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True,
-                      gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res):
+        # one kernel when the grid is a single co-resident wave: statistics, grid barrier, normalise from TMEM.
+        # Only while nothing else is in flight on another stream: two grid-synchronising kernels sharing the SMs
+        # could each hold slots the other needs to become fully resident.
+        alone = self._ws_tag == "main" and self._open_forks == 0
+        if alone and self._conv(pl, conv, x, out=dst, stride=stride, pad=pad, dil=dil, gn_stats=stats,
+                                gn_stats_zeroed=True, gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res):
             return dst
+        if not alone:
+            self._conv(pl, conv, x, out=raw, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True)
         return self._gn(pl, norm, raw, act=act, res=res, out=out, stats=stats)
 
     def _gn_bottleneck(self, pl, p, x, stride, dil, out=None):
+        # (no parallel downsample branch here: the GroupNorm-fused kernels synchronise their whole grid and must never
+        # share the GPU with another grid-synchronising kernel, see _ws_gn)
         t = self._ws_gn(pl, p + ".conv1", p + ".bn1", x, act=ACT_RELU)
         t = self._ws_gn(pl, p + ".conv2", p + ".bn2", t, act=ACT_RELU, stride=stride, pad=dil, dil=dil)
         if (p + ".downsample.0") in self.w.conv:
@@ -316,27 +368,43 @@ class Engine:
         r2, r3, r4 = self._tv_encoder(pl, "trimap.model.Encoder_Q", imgn)
         N, h, w, _ = r4.shape
         m4in = pl.buf("m4in", (1, h, w, 2 * DO))
+        # parallel branches: the skip-connection halves of the decoder (STM.py:113-114 only need r3 / r2) and the
+        # Value projection run beside Key -> Memory.read -> convFM -> ResMM
+        skips = {}
+        for rf, f in (("RF3", r3), ("RF2", r2)):
+            with self.fork(rf) as fk:
+                skips[rf] = (self._stm_skip(pl, rf, f), fk)
+        with self.fork("val") as fv:
+            self._conv(pl, "trimap.model.KV_Q_r4.Value", r4, out=m4in[..., DO:], pad=1)
         qk = self._conv(pl, "trimap.model.KV_Q_r4.Key", r4, "q_key", pad=1)
-        self._conv(pl, "trimap.model.KV_Q_r4.Value", r4, out=m4in[..., DO:], pad=1)
         M = bank.T * bank.hw
         ws_bytes = ops.memory_read_workspace(self.bank_capacity * bank.hw, h * w, DE, DO, self.dtype)
         ws = pl.buf("read_ws", (ws_bytes // 4,), torch.float32)
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)      # deferred memorize of the previous frame has landed
         ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws)
-        return self._stm_decoder(pl, m4in, r3, r2)
+        fv.join()
+        return self._stm_decoder(pl, m4in, skips)
 
-    def _stm_decoder(self, pl, m4in, r3, r2):
+    def _stm_skip(self, pl, rf, f):
+        """Refine.forward's skip half, STM.py:113-114: ResFS(convFS(f))"""
+        d = "trimap.model.Decoder"
+        N, H, W, _ = f.shape
+        s0 = pl.buf(f"dec.{rf}.s0", (1, H, W, 256)); s0r = pl.buf(f"dec.{rf}.s0r", (1, H, W, 256))
+        self._conv(pl, f"{d}.{rf}.convFS", f, out=s0, pad=1, out_relu=s0r)
+        s, _ = self._resblock(pl, f"{d}.{rf}.ResFS", s0, s0r, out_name=f"dec.{rf}.s")
+        return s
+
+    def _stm_decoder(self, pl, m4in, skips):
         d = "trimap.model.Decoder"
         N, h, w, _ = m4in.shape
         x0 = pl.buf("dec.x0", (1, h, w, 256)); x0r = pl.buf("dec.x0r", (1, h, w, 256))
         self._conv(pl, d + ".convFM", m4in, out=x0, pad=1, out_relu=x0r)
         m, _ = self._resblock(pl, d + ".ResMM", x0, x0r, out_name="dec.m4")
-        for rf, f in (("RF3", r3), ("RF2", r2)):
-            N, H, W, _ = f.shape
-            s0 = pl.buf(f"dec.{rf}.s0", (1, H, W, 256)); s0r = pl.buf(f"dec.{rf}.s0r", (1, H, W, 256))
-            self._conv(pl, f"{d}.{rf}.convFS", f, out=s0, pad=1, out_relu=s0r)
-            s, _ = self._resblock(pl, f"{d}.{rf}.ResFS", s0, s0r, out_name=f"dec.{rf}.s")
+        for rf in ("RF3", "RF2"):
+            s, fk = skips[rf]
+            fk.join()
+            N, H, W, _ = s.shape
             mmr = pl.buf(f"dec.{rf}.mmr", (1, H, W, 256))
             mm = ops.upsample(m, pl.buf(f"dec.{rf}.mm", (1, H, W, 256)), add=s, out_relu=mmr)     # STM.py:115
             # the last block's output is only read through F.relu (STM.py:134) -> fold it into the epilogue
@@ -348,16 +416,17 @@ class Engine:
         ops.upsample(p2[..., :3], logits[..., :3])                                    # STM.py:136
         return logits
 
-    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int, ws_name="conv_splitk_ws"):
+    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int):
         """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``."""
         mem_in = pl.bufs["mem_in"]                  # [1,Hp,Wp,cin_mem]: 22 channels + zeros
-        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in, ws_name=ws_name)
+        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in)
         N, h, w, _ = r4.shape
         kdst = bank.key_slot(slot).view(1, h, w, DE)
-        self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1, ws_name=ws_name)
         vdst = bank.vals[:, slot * bank.hw:]
-        self._conv(pl, "trimap.model.KV_M_r4.Value", r4, out=vdst, pad=1, out_strides=(1, bank.vals.shape[1]),
-                   ws_name=ws_name)
+        with self.fork("val") as fv:
+            self._conv(pl, "trimap.model.KV_M_r4.Value", r4, out=vdst, pad=1, out_strides=(1, bank.vals.shape[1]))
+        self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1)
+        fv.join()
 
     def flush(self, pl: FramePlan):
         """Run a deferred memorize pass now (anything that looks at the bank outside ``frame`` calls this)."""
@@ -389,10 +458,15 @@ class Engine:
         pooled = pl.buf("ppm.pooled", (50, 2048))
         ops.ppm_pool(conv5, pooled, pl.buf("ppm.rows", (h8 * 12 * 2048,), torch.float32))
         off = 0
-        for i, s in enumerate((1, 2, 3, 6)):
+        forks = []
+        for i, s in enumerate((1, 2, 3, 6)):                # four independent branches
             cells = pooled[off:off + s * s].view(1, s, s, 2048); off += s * s
-            y = self._ws_gn(pl, f"NET.decoder.ppm.{i}.1", f"NET.decoder.ppm.{i}.2", cells, act=ACT_LEAKY)
-            ops.upsample(y, cat1[..., 2048 + 256 * i: 2304 + 256 * i])
+            with self.fork(f"ppm{i}") as fk:
+                y = self._ws_gn(pl, f"NET.decoder.ppm.{i}.1", f"NET.decoder.ppm.{i}.2", cells, act=ACT_LEAKY)
+                ops.upsample(y, cat1[..., 2048 + 256 * i: 2304 + 256 * i])
+            forks.append(fk)
+        for fk in forks:
+            fk.join()
         dn = "NET.decoder"
         x = self._ws_gn(pl, dn + ".conv_up1.0", dn + ".conv_up1.1", cat1, act=ACT_LEAKY, pad=1)
         x = self._ws_gn(pl, dn + ".conv_up1.3", dn + ".conv_up1.4", x, act=ACT_LEAKY, pad=1)
@@ -433,12 +507,16 @@ class Engine:
         join = None
         if pending is not None:
             if ops.PROFILER is None:
-                if self.side_stream is None:
-                    self.side_stream = torch.cuda.Stream(device=self.device)
-                join = self.side_stream
+                if "memorize" not in self.streams:
+                    self.streams["memorize"] = torch.cuda.Stream(device=self.device)
+                join = self.streams["memorize"]
                 join.wait_stream(torch.cuda.current_stream())          # fork (also inside a graph capture)
                 with torch.cuda.stream(join):
-                    self.memorize(pl, bank, pending, ws_name="conv_splitk_ws.side")
+                    self._ws_tag = "memorize"
+                    try:
+                        self.memorize(pl, bank, pending)
+                    finally:
+                        self._ws_tag = "main"
             else:
                 self.memorize(pl, bank, pending)                         # instrumented pass: one stream, no overlap
         ops.zero_(pl.gn_arena)
