@@ -202,8 +202,17 @@ def run_b200(args):
                  algorithmic_mb_per_frame=round(v["bytes"] / prof_frames / 1e6, 2))
         return r
 
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):                      # DRAM bytes per frame per family from the committed ncu pass
+        traffic = json.load(open(tp)).get("per_frame", {})
     rl = roof(top)
     rl_read = roof("memory_read")
+    for r_ in (rl, rl_read):
+        t = traffic.get(r_["kernel"])
+        if t:
+            r_["traffic"] = t["dram_bytes"]
+            r_["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum per frame over this family's launches (profiles/ncu_traffic.json)"
     rl_read["hbm_gbs"] = round(fam["memory_read"]["bytes"] / prof_frames / (rl_read["ms_per_frame"] * 1e-3) / 1e9, 1)
     rl_read["hbm_frac"] = round(rl_read["hbm_gbs"] / pk["hbm"], 4)
 
