@@ -24,6 +24,8 @@ using namespace tc;
 struct ConvTcArgs {
   int N, H, W, Cin, Ho, Wo, Cout, KH, KW, pad, dil, stride;
   int TW, TH, tiles_x, tiles_y;
+  int tw_shift;                // TW = 1 << tw_shift
+  uint32_t tiles_x_magic, tiles_y_magic;   // ceil(2^32 / d) for the tile-coordinate divisions (0: d == 1)
   int KC, nchunk, nstage, ksub; // nstage ring groups of ksub K-chunks each
   int k_per_split;             // K iterations per blockIdx.z slice (split-K); == num_k without split
   int64_t split_stride;        // elements between the fp32 partial outputs of consecutive K slices
@@ -99,8 +101,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 
   // tile coordinates
   int bx = blockIdx.x;
-  const int tx_i = bx % a.tiles_x; bx /= a.tiles_x;
-  const int ty_i = bx % a.tiles_y; const int n_img = bx / a.tiles_y;
+  // (runtime integer division costs ~100 cycles a piece in every CTA's prologue: magic-number reciprocals instead)
+  const int bq = a.tiles_x_magic ? (int)__umulhi((uint32_t)bx, a.tiles_x_magic) : bx;
+  const int tx_i = bx - bq * a.tiles_x;
+  const int n_img = a.tiles_y_magic ? (int)__umulhi((uint32_t)bq, a.tiles_y_magic) : bq;
+  const int ty_i = bq - n_img * a.tiles_y;
   const int x0 = tx_i * a.TW, y0 = ty_i * a.TH;
   const int n0 = blockIdx.y * BN;
   const int num_k_all = a.KH * a.KW * a.nchunk;
@@ -207,8 +212,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       // transiently negative, the phase cannot complete before the A-side arrival. =====
       const bool load_a = warp == 0;
       int s = 0; uint32_t ph = 0;
-      int tap = it0 / a.nchunk, chunk = it0 - tap * a.nchunk;
-      int ky = tap / a.KW, kx = tap - ky * a.KW;
+      int tap = 0, chunk = 0, ky = 0, kx = 0;
+      if (it0 != 0) { tap = it0 / a.nchunk; chunk = it0 - tap * a.nchunk; ky = tap / a.KW; kx = tap - ky * a.KW; }   // split-K slices only
       const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
       const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
       // The loop body is kept minimal and warp-uniform (elected lane issues): the serial instruction stream of this
@@ -268,7 +273,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     constexpr bool kRes = (EPI & EPI_RES) != 0, kRelu2 = (EPI & EPI_RELU2) != 0, kDirect = (EPI & EPI_DIRECT) != 0;
     const int q = warp & 3;
     const int r = q * 32 + lane;                             // tile row = pixel
-    const int ty = r / a.TW, tx = r - ty * a.TW;
+    const int ty = r >> a.tw_shift, tx = r - (ty << a.tw_shift);
     const int oy = y0 + ty, ox = x0 + tx;
     const bool valid = oy < a.Ho && ox < a.Wo;
     const int64_t pix = ((int64_t)n_img * a.Ho + oy) * a.Wo + ox;
@@ -346,23 +351,23 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-#pragma unroll 1
-    for (int c = 0; c < BN; c += CH) {
-      const int cbase = n0 + c;
-      if (cbase >= a.Cout) break;                            // warp-uniform
-      uint32_t raw[CH];
+    // TMEM load (+ residual fetch) of one CH-column chunk, and its processing, as two steps so that the wide tiles can
+    // keep the next chunk's tcgen05.ld in flight while the current one is processed
+    auto issue = [&](int c, uint32_t (&raw)[CH], uint4 (&rr)[CH / 8]) {
+      if (n0 + c >= a.Cout) return;                          // warp-uniform
       if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       // residual for this chunk is fetched while the TMEM load is in flight (host guarantees 16-byte alignment
       // and Cout % CH == 0 whenever EPI_RES is selected)
-      uint4 rr[CH / 8];
       if constexpr (kRes) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + cbase);
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n0 + c);
 #pragma unroll
         for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
-      tmem_wait_ld();
-      if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
+    };
+    auto finish = [&](int c, uint32_t (&raw)[CH], uint4 (&rr)[CH / 8]) {
+      const int cbase = n0 + c;
+      if (cbase >= a.Cout) return;                           // warp-uniform
       float v[CH];
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
@@ -436,6 +441,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = __float2bfloat16_rn(v[j]);
         }
+      }
+    };
+    if constexpr (BN == 128) {
+      uint32_t ra[CH], rb[CH]; uint4 qa[CH / 8], qb[CH / 8];
+      issue(0, ra, qa); tmem_wait_ld();
+      if (dbg && threadIdx.x == 64) dbg[8] = clock64();
+      issue(32, rb, qb); finish(0, ra, qa); tmem_wait_ld();
+      issue(64, ra, qa); finish(32, rb, qb); tmem_wait_ld();
+      issue(96, rb, qb); finish(64, ra, qa); tmem_wait_ld();
+      finish(96, rb, qb);
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN; c += CH) {
+        uint32_t raw[CH]; uint4 rr[CH / 8];
+        issue(c, raw, rr);
+        tmem_wait_ld();
+        if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
+        finish(c, raw, rr);
       }
     }
     if (dbg && threadIdx.x == 64) dbg[9] = clock64();
@@ -613,12 +636,22 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
 
 template <int BN, int GN, int EPI, bool HALO>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                          const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+                          const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s, bool dry_run) {
   static bool attr = false;
   if (!attr) {
     OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<BN, GN, EPI, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
+  if constexpr (GN == GN_FUSED) {
+    // the grid barrier needs every CTA resident at once: ask the runtime what this exact variant (registers, shared
+    // memory, threads) can keep on an SM
+    int occ = 0;
+    OTVM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_kernel<BN, GN, EPI, HALO>, kConvThreads, smem));
+    const int tmem_cols = BN < 32 ? 32 : BN;
+    if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
+    if ((int64_t)grid.x * grid.y * grid.z > (int64_t)occ * sm_count()) return OTVM_ERR_UNSUPPORTED;
+  }
+  if (dry_run) return OTVM_OK;
   launch_k(conv_tc_kernel<BN, GN, EPI, HALO>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -626,11 +659,12 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 
 template <int BN>
 static int dispatch_conv_tc(int gn, int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                            const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+                            const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s,
+                            bool dry_run = false) {
 #define OTVM_CASE(G, E)                                                                                     \
   if (gn == G && epi == (E))                                                                                \
-    return a.halo ? launch_conv_tc<BN, G, (E), true>(tmA, tmB, tmO, tmR, a, grid, smem, s)                  \
-                  : launch_conv_tc<BN, G, (E), false>(tmA, tmB, tmO, tmR, a, grid, smem, s);
+    return a.halo ? launch_conv_tc<BN, G, (E), true>(tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run)         \
+                  : launch_conv_tc<BN, G, (E), false>(tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
   OTVM_CASE(GN_NONE, 0) OTVM_CASE(GN_NONE, EPI_RES) OTVM_CASE(GN_NONE, EPI_RELU2) OTVM_CASE(GN_NONE, EPI_RES | EPI_RELU2)
   OTVM_CASE(GN_NONE, EPI_DIRECT)
   if constexpr (BN >= 32) {
@@ -667,6 +701,9 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     a.patch_bytes = 0; a.na = 0;
   }
   a.tiles_x = ceil_div(a.Wo, a.TW); a.tiles_y = ceil_div(a.Ho, a.TH);
+  a.tw_shift = 0; while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
+  auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
+  a.tiles_x_magic = magic(a.tiles_x); a.tiles_y_magic = magic(a.tiles_y);     // exact for n * d < 2^32 (n < 2^16 tiles)
   const int bn = pick_bn(p->Cout);
   a.a_bytes = a.halo ? 0u : 128u * a.KC * 2;
   a.b_bytes = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
@@ -805,15 +842,14 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
     const int64_t resident = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);
     if (ctas > resident || (epi & ~EPI_RES) != 0) return OTVM_ERR_UNSUPPORTED;
-    if (dry_run) return OTVM_OK;
   } else if (dry_run) {
     return OTVM_ERR_UNSUPPORTED;
   }
   switch (bn) {
-    case 128: return dispatch_conv_tc<128>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
-    case 64: return dispatch_conv_tc<64>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
-    case 32: return dispatch_conv_tc<32>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
-    default: return dispatch_conv_tc<16>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s);
+    case 128: return dispatch_conv_tc<128>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
+    case 64: return dispatch_conv_tc<64>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
+    case 32: return dispatch_conv_tc<32>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
+    default: return dispatch_conv_tc<16>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
   }
 }
 
