@@ -351,23 +351,23 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    // TMEM load (+ residual fetch) of one CH-column chunk, and its processing, as two steps so that the wide tiles can
-    // keep the next chunk's tcgen05.ld in flight while the current one is processed
-    auto issue = [&](int c, uint32_t (&raw)[CH], uint4 (&rr)[CH / 8]) {
-      if (n0 + c >= a.Cout) return;                          // warp-uniform
+#pragma unroll 1
+    for (int c = 0; c < BN; c += CH) {
+      const int cbase = n0 + c;
+      if (cbase >= a.Cout) break;                            // warp-uniform
+      uint32_t raw[CH];
       if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       // residual for this chunk is fetched while the TMEM load is in flight (host guarantees 16-byte alignment
       // and Cout % CH == 0 whenever EPI_RES is selected)
+      uint4 rr[CH / 8];
       if constexpr (kRes) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + n0 + c);
+        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + cbase);
 #pragma unroll
         for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
-    };
-    auto finish = [&](int c, uint32_t (&raw)[CH], uint4 (&rr)[CH / 8]) {
-      const int cbase = n0 + c;
-      if (cbase >= a.Cout) return;                           // warp-uniform
+      tmem_wait_ld();
+      if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
       float v[CH];
 #pragma unroll
       for (int j = 0; j < CH; j += 4) {
@@ -441,24 +441,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = __float2bfloat16_rn(v[j]);
         }
-      }
-    };
-    if constexpr (BN == 128) {
-      uint32_t ra[CH], rb[CH]; uint4 qa[CH / 8], qb[CH / 8];
-      issue(0, ra, qa); tmem_wait_ld();
-      if (dbg && threadIdx.x == 64) dbg[8] = clock64();
-      issue(32, rb, qb); finish(0, ra, qa); tmem_wait_ld();
-      issue(64, ra, qa); finish(32, rb, qb); tmem_wait_ld();
-      issue(96, rb, qb); finish(64, ra, qa); tmem_wait_ld();
-      finish(96, rb, qb);
-    } else {
-#pragma unroll 1
-      for (int c = 0; c < BN; c += CH) {
-        uint32_t raw[CH]; uint4 rr[CH / 8];
-        issue(c, raw, rr);
-        tmem_wait_ld();
-        if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
-        finish(c, raw, rr);
       }
     }
     if (dbg && threadIdx.x == 64) dbg[9] = clock64();
