@@ -14,6 +14,7 @@
 // Ring of NSTAGE {A,B} stages with full/empty mbarriers; tcgen05.commit releases stages and publishes the
 // accumulator.  Up to two CTAs per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps
 // another's main loop.
+#include <stdio.h>
 #include <stdlib.h>
 #include "tc_common.cuh"
 
@@ -625,12 +626,23 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     attr = true;
   }
   if constexpr (GN == GN_FUSED) {
-    // the grid barrier needs every CTA resident at once: ask the runtime what this exact variant (registers, shared
-    // memory, threads) can keep on an SM
-    int occ = 0;
-    OTVM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_tc_kernel<BN, GN, EPI, HALO>, kConvThreads, smem));
+    // the grid barrier needs every CTA resident at once.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
+    // every tcgen05 kernel on this toolkit, whatever its footprint -- ncu shows 2-4 resident CTAs -- so residency is
+    // derived from the variant's own registers / shared memory / TMEM columns, capped at 2 for margin.)
+    static int regs = 0;
+    if (regs == 0) {
+      cudaFuncAttributes fa;
+      OTVM_CUDA_CHECK(cudaFuncGetAttributes(&fa, conv_tc_kernel<BN, GN, EPI, HALO>));
+      regs = fa.numRegs > 0 ? fa.numRegs : 255;
+    }
+    const int regs_per_warp = ((regs * 32 + 255) / 256) * 256;
+    const int by_regs = 65536 / (regs_per_warp * (kConvThreads / 32));
+    const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     const int tmem_cols = BN < 32 ? 32 : BN;
+    int occ = by_regs < by_smem ? by_regs : by_smem;
     if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
+    if (occ > 2) occ = 2;
+    if (getenv("OTVM_DEBUG_OCC")) fprintf(stderr, "conv_tc<%d,%d,%d,%d> smem=%zu regs=%d grid=(%u,%u,%u) occ=%d\n", BN, GN, EPI, (int)HALO, smem, regs, grid.x, grid.y, grid.z, occ);
     if ((int64_t)grid.x * grid.y * grid.z > (int64_t)occ * sm_count()) return OTVM_ERR_UNSUPPORTED;
   }
   if (dry_run) return OTVM_OK;
