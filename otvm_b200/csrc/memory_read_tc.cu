@@ -23,13 +23,17 @@ int read_pick_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, 
 int read_max_splits(int M, int HW, int Do, int rows_per_cta, int cols_per_cta, int keys_per_block);
 int read_combine(const otvm_read_params* p, int nsplit, cudaStream_t s);
 
-constexpr int TQ = 128, TKB = 64, TDV = 256, TDE = 128, TNS = 3;
+constexpr int TQ = 128, TKB = 64, TDV = 256, TDE = 128;
+constexpr int TNK = 2, TNV = 3;                       // K ring: 128-key slots; V ring: 64-key slots
 constexpr uint32_t kQBytes = TQ * TDE * 2;            // 32 KB (two 64-wide swizzle atoms)
-constexpr uint32_t kKBytes = TKB * TDE * 2;           // 16 KB
-constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB
+constexpr uint32_t kKBytes = 2 * TKB * TDE * 2;       // 32 KB: 128 keys (one super-block), two 64-dim atoms of 16 KB
+constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB: 256 channels x 64 keys
 constexpr uint32_t kPBytes = TQ * TKB * 2;            // 16 KB
-constexpr uint32_t kStage = kKBytes + kVBytes;
-constexpr uint32_t kReadSmem = kQBytes + TNS * kStage + 2 * kPBytes + 1024 + 256 + 4 * TQ * 4;
+constexpr uint32_t kOffK = kQBytes, kOffV = kOffK + TNK * kKBytes, kOffP = kOffV + TNV * kVBytes;
+constexpr uint32_t kOffAux = kOffP + 2 * kPBytes;     // 224 KB: barriers (256 B) + row-max exchange (2 KB)
+constexpr uint32_t kAlignSlack = 512;                 // the dynamic window is 1024-aligned in practice; checked at run time
+constexpr uint32_t kReadSmem = kOffAux + 256 + 4 * TQ * 4 + kAlignSlack;
+static_assert(kReadSmem <= 227 * 1024, "shared memory budget");
 constexpr int kReadThreads = 352;        // TMA warp, S-MMA warp, 8 softmax warps, PV-MMA warp
 constexpr float kLazyLog2 = 8.f;
 
@@ -47,30 +51,39 @@ struct ReadTcArgs {
   long long* dbg;             // dev: per-CTA clock64 timestamps (NULL in production)
 };
 
+// Pipeline (per CTA: 128 queries x 256 value channels x one slice of the memory axis):
+//   super-block J = keys [128J, 128J+128): S_J = Q K_J^T is ONE N=128 product (an N=64 tcgen05.mma costs the same
+//   64 cycles as N=128, measured) into TMEM S buffer J&1;  blocks j = 2J, 2J+1 (64 keys each): O += P_j V_j.
+//   softmax: warps 2-5 (half 0) own block 2J, warps 6-9 (half 1) own block 2J+1 of the SAME 128 rows (warps w and
+//   w+4 share a TMEM lane quarter); the pair exchanges the row maximum once per super-block, so the barrier /
+//   TMEM / fence latencies of the softmax are paid per 128 keys while its MUFU work (64 ex2 per thread) overlaps
+//   the partner's.  P_j goes to shared-memory buffer j&1 (= half), written by that half's 4 warps only.
 __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                                                                          const __grid_constant__ CUtensorMap tmK,
                                                                          const __grid_constant__ CUtensorMap tmV,
                                                                          const __grid_constant__ CUtensorMap tmO,
                                                                          const ReadTcArgs a) {
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (base - smem_u32(smem_raw) > kAlignSlack) __trap();
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + kQBytes;
-  uint8_t* sP = sKV + TNS * kStage;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * kPBytes);
+  uint8_t* sK = smem + kOffK;
+  uint8_t* sV = smem + kOffV;
+  uint8_t* sP = smem + kOffP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffAux);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // TNS   K and V tiles of a block travel separately: K_j is needed one
-  uint64_t* k_empty = k_full + TNS;        // TNS   block earlier (S_j is issued before P_{j-1} V_{j-1}) and its slot is
-  uint64_t* v_full = k_empty + TNS;        // TNS   free again as soon as S_j has been computed
-  uint64_t* v_empty = v_full + TNS;        // TNS
-  uint64_t* s_full = v_empty + TNS;        // 2
+  uint64_t* k_full = bars + 1;             // TNK
+  uint64_t* k_empty = k_full + TNK;        // TNK
+  uint64_t* v_full = k_empty + TNK;        // TNV
+  uint64_t* v_empty = v_full + TNV;        // TNV
+  uint64_t* s_full = v_empty + TNV;        // 2
   uint64_t* s_empty = s_full + 2;          // 2
   uint64_t* p_full = s_empty + 2;          // 2
   uint64_t* p_empty = p_full + 2;          // 2
   uint64_t* o_done = p_empty + 2;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
-  float* xmax = reinterpret_cast<float*>(sP + 2 * kPBytes + 256);      // [2 S buffers][2 halves][128 rows] row-max exchange
+  float* xmax = reinterpret_cast<float*>(smem + kOffAux + 256);        // [2 S buffers][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -78,17 +91,17 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   const int q0 = blockIdx.x * TQ, c0 = blockIdx.y * TDV, split = blockIdx.z;
   const int nb_total = (a.M + TKB - 1) / TKB;
   const int kb0 = split * a.blocks_per_split;
-  const int nb = min(a.blocks_per_split, nb_total - kb0);
+  const int nb = min(a.blocks_per_split, nb_total - kb0);          // 64-key blocks of this CTA
+  const int nsb = (nb + 1) >> 1;                                   // 128-key super-blocks
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < TNS; ++s) {
-      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-    }
+    for (int s = 0; s < TNK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
+    for (int s = 0; s < TNV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8);
-      mbar_init(&p_full[b], 8); mbar_init(&p_empty[b], 1);
+      mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_done, 1);
     fence_barrier_init();
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + TDV;
+  const uint32_t tmem_o = tmem_base, tmem_s = tmem_base + TDV;     // S buffers: 2 x 128 columns
   pdl_trigger();                                       // PDL contract (common.cuh): resources held, then wait
   pdl_wait();
   if (dbg && threadIdx.x == 0) dbg[1] = clock64();
@@ -109,118 +122,114 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(sQ, &tmQ, q_full, 0, q0);
       tma_load_2d(sQ + kQBytes / 2, &tmQ, q_full, 64, q0);
-      auto load_k = [&](int j) {
-        const int s = j % TNS;
-        mbar_wait(&k_empty[s], ((j / TNS) & 1) ^ 1);
-        uint8_t* st = sKV + (size_t)s * kStage;
-        const int key0 = (kb0 + j) * TKB;
+      auto load_k = [&](int J) {                           // 128 keys x 128 dims (rows beyond M are zero-filled)
+        const int s = J % TNK;
+        mbar_wait(&k_empty[s], ((J / TNK) & 1) ^ 1);
+        uint8_t* st = sK + (size_t)s * kKBytes;
+        const int key0 = (kb0 + 2 * J) * TKB;
         mbar_arrive_expect_tx(&k_full[s], kKBytes);
         tma_load_2d(st, &tmK, &k_full[s], 0, key0);
         tma_load_2d(st + kKBytes / 2, &tmK, &k_full[s], 64, key0);
       };
       load_k(0);
-      for (int j = 0; j < nb; ++j) {                       // issue order K_0, K_1, V_0, K_2, V_1, ...
-        if (j + 1 < nb) load_k(j + 1);
-        const int s = j % TNS;
-        mbar_wait(&v_empty[s], ((j / TNS) & 1) ^ 1);
+      for (int j = 0; j < nb; ++j) {                       // issue order K_0, K_1, V_0, V_1, K_2, V_2, V_3, ...
+        if ((j & 1) == 0 && (j >> 1) + 1 < nsb) load_k((j >> 1) + 1);
+        const int s = j % TNV;
+        mbar_wait(&v_empty[s], ((j / TNV) & 1) ^ 1);
         mbar_arrive_expect_tx(&v_full[s], kVBytes);
-        tma_load_2d(sKV + (size_t)s * kStage + kKBytes, &tmV, &v_full[s], (kb0 + j) * TKB, c0);
+        tma_load_2d(sV + (size_t)s * kVBytes, &tmV, &v_full[s], (kb0 + j) * TKB, c0);
       }
     }
   } else if (warp == 1) {
-    // ===== S issuer: S_j = Q K_j^T into the TMEM S buffer j & 1 =====
+    // ===== S issuer: S_J = Q K_J^T (M128 N128 K128) into TMEM S buffer J & 1 =====
     // Two issuing threads (this one and the PV issuer, warp 10): a single thread walking wait -> issue -> commit for
-    // both products was the pipeline's critical path (measured ~100 cycles per mbarrier operation and ~70 cycles
-    // per N=64 MMA issue: ~2000 cycles per block against 768 of tensor work).
+    // both products was the pipeline's critical path (measured ~100 cycles per mbarrier operation).
     if (lane == 0) {
-      constexpr uint32_t idesc_s = make_idesc_bf16(128, TKB);
-      const uint32_t q_addr = base;
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 2 * TKB);
       mbar_wait(q_full, 0);
-      for (int j = 0; j < nb; ++j) {
-        const int s = j % TNS, b = j & 1;
-        if (j >= 2) mbar_wait(&s_empty[b], ((j >> 1) - 1) & 1);      // softmax finished reading S[b] of block j-2
-        mbar_wait(&k_full[s], (j / TNS) & 1);
+      for (int J = 0; J < nsb; ++J) {
+        const int s = J % TNK, sb = J & 1;
+        if (J >= 2) mbar_wait(&s_empty[sb], ((J >> 1) - 1) & 1);     // softmax finished reading S of super-block J-2
+        mbar_wait(&k_full[s], (J / TNK) & 1);
         tcgen05_after_sync();
-        if (dbg && j < 12) dbg[32 + j] = clock64();
-        const uint32_t k_addr = base + kQBytes + (uint32_t)s * kStage;
+        if (dbg && J < 12) dbg[32 + J] = clock64();
+        const uint32_t k_addr = base + kOffK + (uint32_t)s * kKBytes;
 #pragma unroll
-        for (int k = 0; k < TDE / 16; ++k) {               // two 64-wide atoms, 4 K-steps each
+        for (int k = 0; k < TDE / 16; ++k) {               // two 64-dim atoms, 4 K-steps each
           const uint32_t atom = (k >> 2), kk = (k & 3);
-          const uint64_t qd = make_smem_desc(q_addr + atom * (kQBytes / 2), 1024, 2) + (uint64_t)(2 * kk);
+          const uint64_t qd = make_smem_desc(base + atom * (kQBytes / 2), 1024, 2) + (uint64_t)(2 * kk);
           const uint64_t kd = make_smem_desc(k_addr + atom * (kKBytes / 2), 1024, 2) + (uint64_t)(2 * kk);
-          umma_bf16(tmem_s + (uint32_t)b * TKB, qd, kd, idesc_s, k != 0);
+          umma_bf16(tmem_s + (uint32_t)sb * (2 * TKB), qd, kd, idesc_s, k != 0);
         }
-        umma_commit(&s_full[b]);
-        umma_commit(&k_empty[s]);                          // K_j slot free once S_j has been computed
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[s]);                          // K slot free once S_J has been computed
       }
     }
   } else if (warp == 10) {
-    // ===== PV issuer: O += P_j V_j =====
+    // ===== PV issuer: O += P_j V_j (M128 N256 K64) =====
     if (lane == 0) {
       constexpr uint32_t idesc_o = make_idesc_bf16(128, TDV);
       for (int j = 0; j < nb; ++j) {
-        const int s = j % TNS, b = j & 1;
-        mbar_wait(&v_full[s], (j / TNS) & 1);
+        const int s = j % TNV, b = j & 1;
+        mbar_wait(&v_full[s], (j / TNV) & 1);
         mbar_wait(&p_full[b], (j >> 1) & 1);
         tcgen05_after_sync();
         if (dbg && j < 12) dbg[44 + j] = clock64();
-        const uint64_t pdesc = make_smem_desc(base + kQBytes + TNS * kStage + (uint32_t)b * kPBytes, 1024, 2);
-        const uint64_t vdesc = make_smem_desc(base + kQBytes + (uint32_t)s * kStage + kKBytes, 1024, 2);
+        const uint64_t pdesc = make_smem_desc(base + kOffP + (uint32_t)b * kPBytes, 1024, 2);
+        const uint64_t vdesc = make_smem_desc(base + kOffV + (uint32_t)s * kVBytes, 1024, 2);
 #pragma unroll
         for (int k = 0; k < TKB / 16; ++k)
           umma_bf16(tmem_o, pdesc + (uint64_t)(2 * k), vdesc + (uint64_t)(2 * k), idesc_o, (j | k) != 0);
         umma_commit(&p_empty[b]);                          // P buffer free, O holds blocks 0..j
-        umma_commit(&v_empty[s]);                          // V_j slot free
+        umma_commit(&v_empty[s]);                          // V slot free
       }
       umma_commit(o_done);
     }
   } else {
-    // ===== softmax / correction / epilogue: 8 warps, TWO threads per query row =====
-    // Warps w and w+4 own the same TMEM lane quarter (w % 4); each takes 32 of the 64 keys of a block, so the
-    // per-block softmax (the stage that paced the kernel: one thread per row needed ~2000 cycles per block against
-    // 768 cycles of MMA) runs with twice the issue slots and overlaps one warp's ALU work with the other's MUFU.
-    // The pair agrees on the row maximum through shared memory + a 64-thread named barrier.
+    // ===== softmax / correction / epilogue: 8 warps; half 0 (warps 2-5) owns block 2J, half 1 (6-9) block 2J+1 =====
     const int qd = warp & 3, half = (warp - 2) >> 2;
     const int r = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float m_used = -CUDART_INF_F, l_sum = 0.f;
     const float scale = a.scale_log2;
-    for (int j = 0; j < nb; ++j) {
-      const int b = j & 1;
-      mbar_wait(&s_full[b], (j >> 1) & 1);
+    for (int J = 0; J < nsb; ++J) {
+      const int sb = J & 1, j = 2 * J + half;
+      const bool has = j < nb;                             // (only the last super-block can lack its second block)
+      mbar_wait(&s_full[sb], (J >> 1) & 1);
       tcgen05_after_sync();
-      if (dbg && threadIdx.x == 64 && j < 12) dbg[8 + j] = clock64();
-      uint32_t raw[32];
-      tmem_ld32(tmem_s + lane_base + (uint32_t)(b * TKB + half * 32), raw);
+      if (dbg && threadIdx.x == 64 && J < 12) dbg[8 + J] = clock64();
+      uint32_t raw[2][32];
+      tmem_ld32(tmem_s + lane_base + (uint32_t)(sb * 2 * TKB + half * TKB), raw[0]);
+      tmem_ld32(tmem_s + lane_base + (uint32_t)(sb * 2 * TKB + half * TKB + 32), raw[1]);
       tmem_wait_ld();
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[b]);             // S[b] may be overwritten by block j+2 (8 arrivals)
-      const int key0 = (kb0 + j) * TKB + half * 32;
-      if (key0 + 32 > a.M) {                               // ragged last block only (warp-uniform branch)
+      if (lane == 0) mbar_arrive(&s_empty[sb]);            // 8 arrivals: S buffer may be overwritten by super-block J+2
+      const int key0 = (kb0 + j) * TKB;
+      if (!has || key0 + TKB > a.M) {                      // absent block / ragged last block (warp-uniform branch)
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (key0 + i >= a.M) raw[i] = 0xff800000u;    // -inf
+        for (int i = 0; i < 64; ++i) if (!has || key0 + i >= a.M) raw[i >> 5][i & 31] = 0xff800000u;    // -inf
       }
       float mx;
-      {   // 4 independent chains instead of one 32-deep dependent FMNMX chain
-        float m4[4];
+      {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
+        float m8[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) m4[i] = __uint_as_float(raw[i]);
+        for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(raw[0][i]);
 #pragma unroll
-        for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[i]));
-        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(raw[i >> 5][i & 31]));
+        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
       }
-      xmax[(b * 2 + half) * TQ + r] = mx;
+      xmax[(sb * 2 + half) * TQ + r] = mx;
       asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");          // the two warps of this lane quarter
-      mx = fmaxf(mx, xmax[(b * 2 + (half ^ 1)) * TQ + r]) * scale;       // scale > 0: max commutes with the scaling
+      mx = fmaxf(mx, xmax[(sb * 2 + (half ^ 1)) * TQ + r]) * scale;       // scale > 0: max commutes with the scaling
       // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
       const bool grow = mx > m_used + kLazyLog2;
-      if (j == 0) {
+      if (J == 0) {
         m_used = mx;                                       // O not written yet: nothing to rescale
       } else if (__any_sync(0xffffffffu, grow)) {          // both warps of a pair see the same rows -> same decision
         const float m_new = grow ? mx : m_used;
         const float alpha = exp2f(m_used - m_new);
-        mbar_wait(&p_empty[b ^ 1], ((j - 1) >> 1) & 1);    // PV of block j-1 (and all earlier) complete
+        mbar_wait(&p_empty[1], (J - 1) & 1);               // PV of block 2J-1 (and, in issue order, all earlier) complete
         tcgen05_after_sync();
 #pragma unroll 1
         for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {     // each warp rescales half of the columns
@@ -233,32 +242,37 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         }
         tmem_wait_st();
         tcgen05_before_sync();
+        // P_2J is published by half 0 alone and P_2J+1 by half 1 alone: neither may release its PV product before the
+        // partner warp has finished rescaling its half of these rows' columns
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
         l_sum *= alpha;
         m_used = m_new;
       }
-      uint8_t* prow = sP + (size_t)b * kPBytes;
-      float l4[4] = {0.f, 0.f, 0.f, 0.f};                  // independent partial sums
-      uint32_t pk[16];
+      if (has) {
+        float l4[4] = {0.f, 0.f, 0.f, 0.f};                // independent partial sums
+        uint32_t pk[32];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * e]), scale, -m_used));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * e + 1]), scale, -m_used));
-        __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-        l4[e & 3] += __low2float(h) + __high2float(h);     // the sum uses the rounded weights the MMA will see
-        pk[e] = *reinterpret_cast<uint32_t*>(&h);
-      }
-      if (j >= 2) mbar_wait(&p_empty[b], ((j >> 1) - 1) & 1);   // PV of block j-2 finished reading P[b]
+        for (int e = 0; e < 32; ++e) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e) & 31]), scale, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e + 1) & 31]), scale, -m_used));
+          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
+          l4[e & 3] += __low2float(h) + __high2float(h);   // the sum uses the rounded weights the MMA will see
+          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (J >= 1) mbar_wait(&p_empty[half], (J - 1) & 1);     // PV of block j-2 finished reading P[half]
+        uint8_t* prow = sP + (size_t)half * kPBytes;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {                     // 4 chunks of 8 keys (16 bytes) of this thread's half row
-        uint32_t off = (uint32_t)r * 128u + (uint32_t)(half * 4 + ch) * 16u;
-        off ^= ((off >> 7) & 7u) << 4;
-        *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        for (int ch = 0; ch < 8; ++ch) {                   // the full 128-byte row: 8 chunks of 8 keys
+          uint32_t off = (uint32_t)r * 128u + (uint32_t)ch * 16u;
+          off ^= ((off >> 7) & 7u) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[half]);         // 4 arrivals (this half's warps)
       }
-      l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[b]);              // 8 arrivals
-      if (dbg && threadIdx.x == 64 && j < 12) dbg[20 + j] = clock64();
+      if (dbg && threadIdx.x == 64 && J < 12) dbg[20 + J] = clock64();
     }
     // ---- partial results of this split
     mbar_wait(o_done, 0);
@@ -266,15 +280,16 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     if (dbg && threadIdx.x == 64) dbg[2] = clock64();
     const int q = q0 + r;
     if (half == 1) xmax[r] = l_sum;                        // (all pair barriers of the loop are behind both warps)
-    // partial O: TMEM -> swizzled fp32 tiles [8 chunks][128 rows][32 floats] in the drained K/V stages -> TMA store
+    // partial O: TMEM -> swizzled fp32 tiles [8 chunks][128 rows][32 floats] in the drained K/V rings -> TMA store
     // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction); each warp of a pair
     // drains half of the 256 columns
+    uint8_t* stage = sK;                                   // 128 KB behind Q: K ring + first two V slots
 #pragma unroll 1
     for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {
       uint32_t o[32];
       tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
       tmem_wait_ld();
-      uint8_t* tile = sKV + (size_t)(c >> 5) * (TQ * 128);
+      uint8_t* tile = stage + (size_t)(c >> 5) * (TQ * 128);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         uint32_t off = (uint32_t)r * 128u + (uint32_t)i * 16u;
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     asm volatile("bar.sync 1, 256;" ::: "memory");
     if (threadIdx.x == 64) {
 #pragma unroll 1
-      for (int c = 0; c < TDV; c += 32) tma_store_3d(&tmO, sKV + (size_t)(c >> 5) * (TQ * 128), c0 + c, q0, split);
+      for (int c = 0; c < TDV; c += 32) tma_store_3d(&tmO, stage + (size_t)(c >> 5) * (TQ * 128), c0 + c, q0, split);
       tma_store_commit_and_wait();
     }
     if (half == 0 && q < a.HW && blockIdx.y == 0) {
@@ -311,7 +326,8 @@ static int read_tc_splits(int M, int HW, int Do) {
   if (ns < 1) ns = 1;
   if (ns > nkb) ns = nkb;
   if (ns > 64) ns = 64;
-  const int bps = ceil_div(nkb, ns);
+  int bps = ceil_div(nkb, ns);
+  if (bps > 1 && (bps & 1)) ++bps;              // whole 128-key super-blocks per slice
   return ceil_div(nkb, bps);
 }
 
@@ -340,6 +356,7 @@ int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
   a.M = p->M; a.HW = p->HW; a.Do = p->Do;
   a.nsplit = read_tc_splits(p->M, p->HW, p->Do);
   a.blocks_per_split = ceil_div(ceil_div(p->M, TKB), a.nsplit);
+  if (a.blocks_per_split > 1 && (a.blocks_per_split & 1)) ++a.blocks_per_split;
   a.scale_log2 = (float)(1.4426950408889634 / sqrt((double)p->De));
   a.o_part = static_cast<float*>(p->workspace);
   a.ml_part = a.o_part + (int64_t)a.nsplit * p->HW * p->Do;
@@ -352,7 +369,7 @@ int memory_read_tc(const otvm_read_params* p, cudaStream_t s) {
   }
   {
     uint64_t dims[2] = {(uint64_t)TDE, (uint64_t)p->M}; uint64_t str[1] = {(uint64_t)TDE * 2};
-    uint32_t box[2] = {64, TKB};
+    uint32_t box[2] = {64, 2 * TKB};
     int rc = make_tmap_bf16(&tmK, p->keys, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B); if (rc) return rc;
   }
   {

@@ -18,5 +18,5 @@ for hw_side, T in [(32, 8), (32, 16)]:
     c = 5  # some CTA
     print("   s_full seen :", [int(x) for x in rel[c, 8:20]])
     print("   p written   :", [int(x) for x in rel[c, 20:32]])
-    print("   mma k_full  :", [int(x) for x in rel[c, 32:44]])
-    print("   mma p_full  :", [int(x) for x in rel[c, 44:56]])
+    print("   S issue     :", [int(x) for x in rel[c, 32:44]])
+    print("   PV issue    :", [int(x) for x in rel[c, 44:56]])
