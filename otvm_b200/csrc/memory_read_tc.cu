@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
           const float p0 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e) & 31]), scale, -m_used));
           const float p1 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e + 1) & 31]), scale, -m_used));
           __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          l4[e & 3] += __low2float(h) + __high2float(h);   // the sum uses the rounded weights the MMA will see
+          l4[e & 3] += p0 + p1;                            // (unrounded weights: the bf16 rounding of P is zero-mean, 2^-9)
           pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
