@@ -31,10 +31,10 @@ constexpr uint32_t kVBytes = TDV * TKB * 2;           // 32 KB: 256 channels x 6
 constexpr uint32_t kPBytes = TQ * TKB * 2;            // 16 KB
 constexpr uint32_t kOffK = kQBytes, kOffV = kOffK + TNK * kKBytes, kOffP = kOffV + TNV * kVBytes;
 constexpr uint32_t kOffAux = kOffP + 2 * kPBytes;     // 224 KB: barriers (256 B) + row-max exchange (2 KB)
-constexpr uint32_t kAlignSlack = 512;                 // the dynamic window is 1024-aligned in practice; checked at run time
-constexpr uint32_t kReadSmem = kOffAux + 256 + 4 * TQ * 4 + kAlignSlack;
+constexpr uint32_t kAlignSlack = 256;                 // the dynamic window is 1024-aligned in practice; checked at run time
+constexpr uint32_t kReadSmem = kOffAux + 256 + 8 * TQ * 2 + kAlignSlack;   // barriers + bf16 row-max exchange
 static_assert(kReadSmem <= 227 * 1024, "shared memory budget");
-constexpr int kReadThreads = 352;        // TMA warp, S-MMA warp, 8 softmax warps, PV-MMA warp
+constexpr int kReadThreads = 608;        // TMA warp, S-MMA warp, 16 softmax warps, PV-MMA warp
 constexpr float kLazyLog2 = 8.f;
 
 // 2^x on the SFU (ex2.approx.ftz): relative error ~2^-22, far below the bf16 rounding of P
@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   uint64_t* p_empty = p_full + 2;          // 2
   uint64_t* o_done = p_empty + 2;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
-  float* xmax = reinterpret_cast<float*>(smem + kOffAux + 256);        // [2 S buffers][2 halves][128 rows]
+  bf16* xmax = reinterpret_cast<bf16*>(smem + kOffAux + 256);          // [2 S buffers][4 subs][128 rows], 2 KB
+  float* xsum = reinterpret_cast<float*>(smem + kOffAux + 256);        // the same bytes after the loop: [3][128] row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
@@ -100,8 +101,8 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     for (int s = 0; s < TNK; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); }
     for (int s = 0; s < TNV; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 8);
-      mbar_init(&p_full[b], 4); mbar_init(&p_empty[b], 1);
+      mbar_init(&s_full[b], 1); mbar_init(&s_empty[b], 16);
+      mbar_init(&p_full[b], 8); mbar_init(&p_empty[b], 1);
     }
     mbar_init(o_done, 1);
     fence_barrier_init();
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     }
   } else if (warp == 1) {
     // ===== S issuer: S_J = Q K_J^T (M128 N128 K128) into TMEM S buffer J & 1 =====
-    // Two issuing threads (this one and the PV issuer, warp 10): a single thread walking wait -> issue -> commit for
+    // Two issuing threads (this one and the PV issuer, warp 18): a single thread walking wait -> issue -> commit for
     // both products was the pipeline's critical path (measured ~100 cycles per mbarrier operation).
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(128, 2 * TKB);
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         umma_commit(&k_empty[s]);                          // K slot free once S_J has been computed
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == 18) {
     // ===== PV issuer: O += P_j V_j (M128 N256 K64) =====
     if (lane == 0) {
       constexpr uint32_t idesc_o = make_idesc_bf16(128, TDV);
@@ -186,8 +187,12 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       umma_commit(o_done);
     }
   } else {
-    // ===== softmax / correction / epilogue: 8 warps; half 0 (warps 2-5) owns block 2J, half 1 (6-9) block 2J+1 =====
-    const int qd = warp & 3, half = (warp - 2) >> 2;
+    // ===== softmax / correction / epilogue: 16 warps = FOUR threads per query row =====
+    // warps w, w+4, w+8, w+12 (w = 2..5) share TMEM lane quarter w % 4.  sub = 0..3: half = sub >> 1 selects the
+    // 64-key block of the super-block (2J or 2J+1), quarter = sub & 1 the 32 keys of that block the thread owns.
+    // Four warps per scheduler hide each other's TMEM / barrier / fence latencies (the MUFU ex2 work, 1024 cycles per
+    // super-block and scheduler, is the floor); the four threads of a row agree on the row maximum once per 128 keys.
+    const int qd = warp & 3, sub = (warp - 2) >> 2, half = sub >> 1, quarter = sub & 1;
     const int r = qd * 32 + lane;
     const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float m_used = -CUDART_INF_F, l_sum = 0.f;
@@ -198,41 +203,46 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       mbar_wait(&s_full[sb], (J >> 1) & 1);
       tcgen05_after_sync();
       if (dbg && threadIdx.x == 64 && J < 12) dbg[8 + J] = clock64();
-      uint32_t raw[2][32];
-      tmem_ld32(tmem_s + lane_base + (uint32_t)(sb * 2 * TKB + half * TKB), raw[0]);
-      tmem_ld32(tmem_s + lane_base + (uint32_t)(sb * 2 * TKB + half * TKB + 32), raw[1]);
+      uint32_t raw[32];
+      tmem_ld32(tmem_s + lane_base + (uint32_t)(sb * 2 * TKB + sub * 32), raw);
       tmem_wait_ld();
+      if (dbg && threadIdx.x == 64 && J == 4) dbg[56] = clock64();
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);            // 8 arrivals: S buffer may be overwritten by super-block J+2
-      const int key0 = (kb0 + j) * TKB;
-      if (!has || key0 + TKB > a.M) {                      // absent block / ragged last block (warp-uniform branch)
+      if (lane == 0) mbar_arrive(&s_empty[sb]);            // 16 arrivals: S buffer may be overwritten by super-block J+2
+      const int key0 = (kb0 + j) * TKB + quarter * 32;
+      if (!has || key0 + 32 > a.M) {                       // absent block / ragged last block (warp-uniform branch)
 #pragma unroll
-        for (int i = 0; i < 64; ++i) if (!has || key0 + i >= a.M) raw[i >> 5][i & 31] = 0xff800000u;    // -inf
+        for (int i = 0; i < 32; ++i) if (!has || key0 + i >= a.M) raw[i] = 0xff800000u;    // -inf
       }
       float mx;
-      {   // 8 independent chains instead of one 64-deep dependent FMNMX chain
-        float m8[8];
+      {   // 4 independent chains instead of one 32-deep dependent FMNMX chain
+        float m4[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) m8[i] = __uint_as_float(raw[0][i]);
+        for (int i = 0; i < 4; ++i) m4[i] = __uint_as_float(raw[i]);
 #pragma unroll
-        for (int i = 8; i < 64; ++i) m8[i & 7] = fmaxf(m8[i & 7], __uint_as_float(raw[i >> 5][i & 31]));
-        mx = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), fmaxf(fmaxf(m8[4], m8[5]), fmaxf(m8[6], m8[7])));
+        for (int i = 4; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[i]));
+        mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
-      xmax[(sb * 2 + half) * TQ + r] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");          // the two warps of this lane quarter
-      mx = fmaxf(mx, xmax[(sb * 2 + (half ^ 1)) * TQ + r]) * scale;       // scale > 0: max commutes with the scaling
+      // the exchanged maxima are rounded UP to bf16 (the buffer must fit beside 224 KB of tiles): any common value
+      // >= the true maximum is a valid softmax reference, and all four threads read the same four numbers
+      bf16* xrow = xmax + (size_t)sb * 4 * TQ + r;         // [sb][sub][row]
+      xrow[sub * TQ] = __float2bfloat16_ru(mx);
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory");         // the four warps of this lane quarter
+      mx = fmaxf(fmaxf(__bfloat162float(xrow[0]), __bfloat162float(xrow[TQ])),
+                 fmaxf(__bfloat162float(xrow[2 * TQ]), __bfloat162float(xrow[3 * TQ]))) * scale;   // scale > 0
+      if (dbg && threadIdx.x == 64 && J == 4) dbg[57] = clock64();
       // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
       const bool grow = mx > m_used + kLazyLog2;
       if (J == 0) {
         m_used = mx;                                       // O not written yet: nothing to rescale
-      } else if (__any_sync(0xffffffffu, grow)) {          // both warps of a pair see the same rows -> same decision
+      } else if (__any_sync(0xffffffffu, grow)) {          // the four warps of a quarter see the same rows -> same decision
         const float m_new = grow ? mx : m_used;
         const float alpha = exp2f(m_used - m_new);
         mbar_wait(&p_empty[1], (J - 1) & 1);               // PV of block 2J-1 (and, in issue order, all earlier) complete
         tcgen05_after_sync();
 #pragma unroll 1
-        for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {     // each warp rescales half of the columns
+        for (int c = sub * (TDV / 4); c < (sub + 1) * (TDV / 4); c += 32) {       // each warp rescales a quarter of the columns
           uint32_t o[32];
           tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
           tmem_wait_ld();
@@ -242,35 +252,39 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         }
         tmem_wait_st();
         tcgen05_before_sync();
-        // P_2J is published by half 0 alone and P_2J+1 by half 1 alone: neither may release its PV product before the
-        // partner warp has finished rescaling its half of these rows' columns
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + qd) : "memory");
+        // P_j is published by the two warps of its block alone: none may release its PV product before all four
+        // warps of this lane quarter have finished rescaling these rows
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory");
         l_sum *= alpha;
         m_used = m_new;
       }
       if (has) {
         float l4[4] = {0.f, 0.f, 0.f, 0.f};                // independent partial sums
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e) & 31]), scale, -m_used));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[e >> 4][(2 * e + 1) & 31]), scale, -m_used));
-          __nv_bfloat162 h = __floats2bfloat162_rn(p0, p1);
-          l4[e & 3] += p0 + p1;                            // (unrounded weights: the bf16 rounding of P is zero-mean, 2^-9)
-          pk[e] = *reinterpret_cast<uint32_t*>(&h);
+        for (int e = 0; e < 16; ++e) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * e]), scale, -m_used));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * e + 1]), scale, -m_used));
+          // bf16 by truncation with integer ops: the F2FP conversion shares the 16-lane XU pipe with MUFU.EX2, which
+          // paces this loop; the row sum uses the SAME truncated weights the MMA sees, so the normalisation is exact
+          const uint32_t u0 = __float_as_uint(p0) & 0xffff0000u, u1 = __float_as_uint(p1) & 0xffff0000u;
+          l4[e & 3] += __uint_as_float(u0) + __uint_as_float(u1);
+          pk[e] = __byte_perm(u0, u1, 0x7632);             // low half = bf16(p0), high half = bf16(p1)
         }
         l_sum += (l4[0] + l4[1]) + (l4[2] + l4[3]);
+        if (dbg && threadIdx.x == 64 && J == 4) dbg[58] = clock64();
         if (J >= 1) mbar_wait(&p_empty[half], (J - 1) & 1);     // PV of block j-2 finished reading P[half]
+        if (dbg && threadIdx.x == 64 && J == 4) dbg[59] = clock64();
         uint8_t* prow = sP + (size_t)half * kPBytes;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {                   // the full 128-byte row: 8 chunks of 8 keys
-          uint32_t off = (uint32_t)r * 128u + (uint32_t)ch * 16u;
+        for (int ch = 0; ch < 4; ++ch) {                   // this thread's 64 bytes of the 128-byte row
+          uint32_t off = (uint32_t)r * 128u + (uint32_t)(quarter * 4 + ch) * 16u;
           off ^= ((off >> 7) & 7u) << 4;
           *reinterpret_cast<uint4*>(prow + off) = make_uint4(pk[4 * ch], pk[4 * ch + 1], pk[4 * ch + 2], pk[4 * ch + 3]);
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[half]);         // 4 arrivals (this half's warps)
+        if (lane == 0) mbar_arrive(&p_full[half]);         // 8 arrivals (this block's warps)
       }
       if (dbg && threadIdx.x == 64 && J < 12) dbg[20 + J] = clock64();
     }
@@ -279,13 +293,14 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
     tcgen05_after_sync();
     if (dbg && threadIdx.x == 64) dbg[2] = clock64();
     const int q = q0 + r;
-    if (half == 1) xmax[r] = l_sum;                        // (all pair barriers of the loop are behind both warps)
+    asm volatile("bar.sync 1, 512;" ::: "memory");         // every warp has read the last row maxima: reuse the buffer
+    if (sub != 0) xsum[(sub - 1) * TQ + r] = l_sum;
     // partial O: TMEM -> swizzled fp32 tiles [8 chunks][128 rows][32 floats] in the drained K/V rings -> TMA store
-    // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction); each warp of a pair
-    // drains half of the 256 columns
+    // (per-thread row stores would scatter 16-byte pieces over 32 rows per instruction); each of the four warps of
+    // a lane quarter drains 64 of the 256 columns
     uint8_t* stage = sK;                                   // 128 KB behind Q: K ring + first two V slots
 #pragma unroll 1
-    for (int c = half * (TDV / 2); c < (half + 1) * (TDV / 2); c += 32) {
+    for (int c = sub * (TDV / 4); c < (sub + 1) * (TDV / 4); c += 32) {
       uint32_t o[32];
       tmem_ld32(tmem_o + lane_base + (uint32_t)c, o);
       tmem_wait_ld();
@@ -298,15 +313,15 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
       }
     }
     fence_proxy_async_smem();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     if (threadIdx.x == 64) {
 #pragma unroll 1
       for (int c = 0; c < TDV; c += 32) tma_store_3d(&tmO, stage + (size_t)(c >> 5) * (TQ * 128), c0 + c, q0, split);
       tma_store_commit_and_wait();
     }
-    if (half == 0 && q < a.HW && blockIdx.y == 0) {
+    if (sub == 0 && q < a.HW && blockIdx.y == 0) {
       a.ml_part[((int64_t)split * a.HW + q) * 2 + 0] = m_used;
-      a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum + xmax[r];
+      a.ml_part[((int64_t)split * a.HW + q) * 2 + 1] = l_sum + xsum[r] + xsum[TQ + r] + xsum[2 * TQ + r];
     }
     if (dbg && threadIdx.x == 64) dbg[3] = clock64();
     tcgen05_before_sync();

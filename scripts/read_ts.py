@@ -20,3 +20,4 @@ for hw_side, T in [(32, 8), (32, 16)]:
     print("   p written   :", [int(x) for x in rel[c, 20:32]])
     print("   S issue     :", [int(x) for x in rel[c, 32:44]])
     print("   PV issue    :", [int(x) for x in rel[c, 44:56]])
+    print("   softmax J=4 : s_full", int(rel[c, 12]), "tmem_ld", int(rel[c, 56]), "row max agreed", int(rel[c, 57]), "exps done", int(rel[c, 58]), "p_empty passed", int(rel[c, 59]), "published", int(rel[c, 24]))
