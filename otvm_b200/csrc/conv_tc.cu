@@ -45,6 +45,9 @@ struct ConvTcArgs {
   double* gn_stats;
   const float* gn_gamma; const float* gn_beta; float gn_eps;   // GN == 2: normalise in this kernel (grid barrier)
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
+  // persistent patch-mode kernel (conv_tc_persist_kernel): tiles walked per CTA, smem carve-up
+  int ntiles;                  // tiles_x * tiles_y * N
+  uint32_t p_off, stage_off;   // byte offsets of the patch ring and of the two epilogue staging tiles (weights sit at 0)
 };
 
 constexpr int kConvThreads = 192;
@@ -68,6 +71,8 @@ __device__ __forceinline__ void gn_chunk(const float (&qv)[CH], int r, float* sr
 
 enum { EPI_RES = 1, EPI_RELU2 = 2, EPI_DIRECT = 4 };
 enum { GN_NONE = 0, GN_STATS = 1, GN_FUSED = 2 };   // GN_FUSED: statistics -> grid barrier -> normalise + affine in the epilogue
+
+__device__ __forceinline__ long long gtime_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
-  if (dbg && threadIdx.x == 0) dbg[0] = clock64();
+  if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[10] = gtime_ns(); }
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 
   // tile coordinates
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   // touches activations produced by earlier kernels
   pdl_trigger();
   pdl_wait();
-  if (dbg && threadIdx.x == 0) dbg[1] = clock64();
+  if (dbg && threadIdx.x == 0) { dbg[1] = clock64(); dbg[11] = gtime_ns(); }
 
   // NOTE on the single-thread loops below: one thread issuing a dependent scalar chain is the pipeline's critical
   // path (measured ~830 cycles per K iteration with runtime div/mod for the stage / tap / chunk indices, and ~430
@@ -479,7 +484,267 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     tcgen05_before_sync();
   }
   __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[7] = clock64();
+  if (dbg && threadIdx.x == 0) { dbg[7] = clock64(); dbg[12] = gtime_ns(); }
+  if (warp == 1) {
+    tcgen05_after_sync();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Persistent patch-mode kernel for the full-resolution 3x3 stride-1 layers (Cout = BN <= 64, Cin <= 128: the decoder
+// tail and the refinement module, thousands of 128-pixel tiles per layer).  The one-tile-per-CTA kernel above pays
+// its fixed costs (barrier init, TMEM allocation, descriptor fetch, first-load latency, drain) once per 16 KB of
+// output and re-reads the whole filter bank (up to 108 KB) from L2 for every tile.  Here ONE CTA per SM
+//   * loads the complete filter bank into shared memory once (before the PDL wait: weights are constants),
+//   * walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... : one TMA patch {KC, 8+2d, 16+2d} per K-chunk through a
+//     ring that runs ahead across tile boundaries,
+//   * runs TWO independent tile pipelines (even / odd tiles of the CTA): each has its own MMA issuer warp, its own
+//     pair of accumulators in tensor memory, its own 4 epilogue warps and its own bf16 staging tile.  Measured on B200
+//     (scripts/persist_ts.py): ONE thread cannot issue N <= 64 MMAs faster than ~55 cycles apiece (uniform-datapath
+//     descriptor arithmetic), which left the tensor pipe half idle; two issuers interleave on the pipe, and the
+//     epilogue of one tile overlaps the MMAs of the next two,
+//   * keeps the GroupNorm partial sums in registers across all its tiles and issues its 64 fp64 atomics once.
+// Warp roles (352 threads): 0 = patch producer, 1..2 = MMA issuers (warp 1 allocates TMEM), 3..6 / 7..10 = epilogue
+// of pipeline 0 / 1.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPersistThreads = 352;
+constexpr int kSredPitch2 = 257;             // 256 rows (two epilogue groups) + 1
+
+template <int BN, int GN, int KSTEPS>
+__global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                             const __grid_constant__ CUtensorMap tmB,
+                                                                             const __grid_constant__ CUtensorMap tmO,
+                                                                             const ConvTcArgs a) {
+  static_assert(GN == GN_NONE || (GN == GN_STATS && BN == 64), "statistics variant: 64 channels = 32 groups of 2");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + a.aux_off);
+  uint64_t* p_full = w_full + 1;                                      // [8] patch ring
+  uint64_t* p_empty = p_full + 8;                                     // [8]
+  uint64_t* acc_full = p_empty + 8;                                   // [4] accumulator 2g+b ready for epilogue group g
+  uint64_t* acc_empty = acc_full + 4;                                 // [4] accumulator 2g+b drained (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
+  float* sbias = reinterpret_cast<float*>(tmem_slot + 2);             // [BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr uint32_t TMEM_COLS = 4 * BN;                              // two accumulators per pipeline
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO);
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  for (int i = threadIdx.x; i < BN; i += kPersistThreads) sbias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp == 0) {
+    // the filter bank: 9 taps x nchunk boxes [BN x KC] behind one barrier.  Weights are never written inside a frame,
+    // so this is issued BEFORE the PDL wait and overlaps the previous kernel's tail.
+    if (elect_one()) {
+      mbar_arrive_expect_tx(w_full, (uint32_t)(9 * a.nchunk) * (uint32_t)(BN * a.KC * 2));
+      for (int chunk = 0; chunk < a.nchunk; ++chunk)
+        for (int tap = 0; tap < 9; ++tap)
+          tma_load_2d(smem + (size_t)(chunk * 9 + tap) * a.b_bytes, &tmB, w_full, tap * a.Cin + chunk * a.KC, 0);
+    }
+    __syncwarp();
+  }
+  pdl_trigger();
+  pdl_wait();
+
+  const int d = a.dil, pw = a.TW + 2 * a.dil;
+  // dev: per-tile clock64 stamps [grid][32 tiles][8] (NULL in production)
+  long long* dbg = a.dbg ? a.dbg + (size_t)blockIdx.x * 256 : nullptr;
+#define OTVM_PSTAMP(i, k) do { if (dbg && (i) < 32 && lane == 0) dbg[(i) * 8 + (k)] = clock64(); } while (0)
+  if (warp == 0) {
+    // ===== patch producer =====
+    int slot = 0; uint32_t ph = 0; int i = 0;
+    const uint32_t p_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes;
+    for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++i) {
+      const int bq = a.tiles_x_magic ? (int)__umulhi((uint32_t)t, a.tiles_x_magic) : t;
+      const int tx_i = t - bq * a.tiles_x;
+      const int n_img = a.tiles_y_magic ? (int)__umulhi((uint32_t)bq, a.tiles_y_magic) : bq;
+      const int ty_i = bq - n_img * a.tiles_y;
+      const int cx = tx_i * a.TW - a.pad, cy = ty_i * a.TH - a.pad;
+      for (int chunk = 0; chunk < a.nchunk; ++chunk) {
+        mbar_wait(&p_empty[slot], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&p_full[slot], p_tx);
+          tma_load_4d(smem + a.p_off + (size_t)slot * a.patch_bytes, &tmA, &p_full[slot], chunk * a.KC, cx, cy, n_img);
+        }
+        __syncwarp();
+        if (++slot == a.na) { slot = 0; ph ^= 1; }
+      }
+      OTVM_PSTAMP(i, 0);
+    }
+  } else if (warp <= 2) {
+    // ===== MMA issuers: warp 1 takes the CTA's even tiles (accumulator 0), warp 2 the odd ones (accumulator 1) =====
+    const int g = warp - 1;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    const uint64_t adesc0 = make_smem_desc(base + a.p_off, (uint32_t)pw * a.row_bytes, a.layout_type);
+    const uint64_t bdesc0 = make_smem_desc(base, a.sbo, a.layout_type);
+    const uint32_t b16 = a.b_bytes >> 4, patch16 = a.patch_bytes >> 4;
+    const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
+    mbar_wait(w_full, 0);
+    // patch-ring position of this pipeline's first tile; every tile consumes nchunk consecutive slots
+    int slot = 0; uint32_t ph = 0;
+    auto skip = [&](int n) { slot += n; while (slot >= a.na) { slot -= a.na; ph ^= 1; } };
+    if (g) skip(a.nchunk);
+    int j = 0;                                                   // tiles done by this pipeline
+    for (int t = blockIdx.x + g * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++j) {
+      const int ab = 2 * g + (j & 1);                              // the pipeline alternates between its two accumulators
+      mbar_wait(&acc_empty[ab], (((uint32_t)j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+      tcgen05_after_sync();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+      OTVM_PSTAMP(2 * j + g, 1);
+      for (int chunk = 0; chunk < a.nchunk; ++chunk) {
+        mbar_wait(&p_full[slot], ph);
+        tcgen05_after_sync();
+        if (chunk == a.nchunk - 1) OTVM_PSTAMP(2 * j + g, 2);
+        if (elect_one()) {
+          const uint64_t ad0 = adesc0 + (uint64_t)((uint32_t)slot * patch16);
+          const uint64_t bd0 = bdesc0 + (uint64_t)((uint32_t)(chunk * 9) * b16);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+              const uint64_t ad = ad0 + (uint64_t)((uint32_t)ky * ky16 + (uint32_t)kx * kx16);
+              const uint64_t bd = bd0 + (uint64_t)((uint32_t)(ky * 3 + kx) * b16);
+#pragma unroll
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (chunk | ky | kx | k) != 0);
+            }
+          }
+          umma_commit(&p_empty[slot]);                         // all 9 taps have read this patch
+          if (chunk == a.nchunk - 1) umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+        if (++slot == a.na) { slot = 0; ph ^= 1; }
+      }
+      OTVM_PSTAMP(2 * j + g, 3);
+      skip(a.nchunk);                                            // the other pipeline's tile
+    }
+  } else {
+    // ===== epilogue: group g = warps 3+4g .. 6+4g; a warp owns TMEM lanes 32*(warp%4) .. +31 =====
+    const int g = (warp - 3) >> 2;
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int ty = r >> a.tw_shift, tx = r - (ty << a.tw_shift);
+    const bool leader = (warp - 3 - 4 * g) == 0 && lane == 0;   // issues this group's TMA stores
+    constexpr int CH = BN >= 32 ? 32 : 16;
+    constexpr uint32_t ROWB = BN * 2, MASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
+    constexpr uint32_t STAGE_BYTES = 128u * ROWB;
+    const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
+    uint8_t* stg = smem + a.stage_off + (size_t)g * STAGE_BYTES;
+    float s1[GN == GN_STATS ? 32 : 1], s2[GN == GN_STATS ? 32 : 1];
+    if constexpr (GN == GN_STATS) {
+#pragma unroll
+      for (int u = 0; u < 32; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
+    }
+    int j = 0;
+    for (int t = blockIdx.x + g * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++j) {
+      const int bq = a.tiles_x_magic ? (int)__umulhi((uint32_t)t, a.tiles_x_magic) : t;
+      const int tx_i = t - bq * a.tiles_x;
+      const int n_img = a.tiles_y_magic ? (int)__umulhi((uint32_t)bq, a.tiles_y_magic) : bq;
+      const int ty_i = bq - n_img * a.tiles_y;
+      const int x0 = tx_i * a.TW, y0 = ty_i * a.TH;
+      const bool valid = (y0 + ty) < a.Ho && (x0 + tx) < a.Wo;
+      const int ab = 2 * g + (j & 1);
+      mbar_wait(&acc_full[ab], ((uint32_t)j >> 1) & 1u);
+      tcgen05_after_sync();
+      if (q == 3) OTVM_PSTAMP(2 * j + g, 4);
+      // the group's staging tile was handed to the TMA store of its previous tile: wait until that store has read it
+      if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+#pragma unroll
+      for (int c = 0; c < BN; c += CH) {
+        uint32_t raw[CH];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c);
+        if constexpr (CH == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
+        tmem_wait_ld();
+        float v[CH];
+#pragma unroll
+        for (int e = 0; e < CH; e += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(sbias + c + e);
+          v[e] = __uint_as_float(raw[e]) + b4.x; v[e + 1] = __uint_as_float(raw[e + 1]) + b4.y;
+          v[e + 2] = __uint_as_float(raw[e + 2]) + b4.z; v[e + 3] = __uint_as_float(raw[e + 3]) + b4.w;
+        }
+        if constexpr (GN == GN_STATS) {
+          // statistics of the values GroupNorm will read back (rounded to bf16); rows outside the image count 0
+#pragma unroll
+          for (int e = 0; e < CH; e += 2) {
+            const float q0 = valid ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
+            const float q1 = valid ? __bfloat162float(__float2bfloat16_rn(v[e + 1])) : 0.f;
+            s1[(c + e) >> 1] += q0 + q1;
+            s2[(c + e) >> 1] += q0 * q0 + q1 * q1;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < CH; ++e) v[e] = fmaxf(v[e], 0.f) + slope * fminf(v[e], 0.f);
+#pragma unroll
+        for (int e8 = 0; e8 < CH / 8; ++e8) {
+          const int cc = c + 8 * e8;
+          uint32_t off = (uint32_t)r * ROWB + (uint32_t)cc * 2u;
+          off ^= ((off >> 7) & MASK) << 4;
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * e8 + 2 * e], v[8 * e8 + 2 * e + 1]);
+            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          *reinterpret_cast<uint4*>(stg + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      // this warp's share of the accumulator is staged: hand the TMEM buffer back to the pipeline's MMA warp
+      tcgen05_before_sync();
+      __syncwarp();
+      if (q == 3) OTVM_PSTAMP(2 * j + g, 5);
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
+      asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
+      if (leader) {
+        tma_store_4d(&tmO, stg, 0, x0, y0, n_img);            // clips ragged tiles
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      if (q == 3) OTVM_PSTAMP(2 * j + g, 6);
+    }
+    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if constexpr (GN == GN_STATS) {
+      // Both groups have seen their last accumulator, so every MMA of this CTA has completed and (after the wait above)
+      // every store has read its staging tile: the patch ring + staging region is dead.  Park the per-row partials
+      // there, add up the 256 rows per (group, moment) in fp64 and issue this CTA's 64 atomics.
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      float* sred = reinterpret_cast<float*>(smem + a.p_off);
+      const int row = g * 128 + r;
+#pragma unroll
+      for (int u = 0; u < 32; ++u) { sred[u * kSredPitch2 + row] = s1[u]; sred[(32 + u) * kSredPitch2 + row] = s2[u]; }
+      asm volatile("bar.sync 5, 256;" ::: "memory");
+      const int e = threadIdx.x - 96;
+      if (e < 64) {
+        // (fp64 adds are ~64x slower than fp32 on this part: 8 independent fp32 chains, fixed order, combined in fp64)
+        const float* rowp = sred + e * kSredPitch2;          // e = which * 32 + group
+        float p8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (int k = 0; k < 256; k += 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) p8[u] += rowp[k + u];
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += (double)p8[u];
+        atomicAdd(&a.gn_stats[(e & 31) * 2 + (e >> 5)], acc);
+      }
+    }
+    tcgen05_before_sync();
+  }
+#undef OTVM_PSTAMP
+  __syncthreads();
   if (warp == 1) {
     tcgen05_after_sync();
     tmem_dealloc<TMEM_COLS>(tmem_base);
@@ -567,6 +832,13 @@ static int conv_halo_mode() {
   return g_conv_halo;
 }
 
+static long long g_conv_persist_launches = 0;
+static int g_conv_persist = -2;           // -2 unset, -1 auto (default), 0 off, 1 whenever the shape allows
+static int conv_persist_mode() {
+  if (g_conv_persist == -2) { const char* e = getenv("OTVM_CONV_PERSIST"); g_conv_persist = e ? atoi(e) : -1; }
+  return g_conv_persist;
+}
+
 static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16; }
 
 static bool aligned_view(const void* ptr, int64_t ld) {
@@ -649,6 +921,62 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   launch_k(conv_tc_kernel<BN, GN, EPI, HALO>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
+}
+
+template <int BN, int GN, int KSTEPS>
+static int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvTcArgs& a,
+                               int grid, size_t smem, cudaStream_t s) {
+  static bool attr = false;
+  if (!attr) {
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_persist_kernel<BN, GN, KSTEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  launch_k(conv_tc_persist_kernel<BN, GN, KSTEPS>, grid, kPersistThreads, smem, s, tmA, tmB, tmO, a);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+template <int BN, int GN>
+static int launch_conv_persist_k(int ksteps, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                 const ConvTcArgs& a, int grid, size_t smem, cudaStream_t s) {
+  return ksteps == 4 ? launch_conv_persist<BN, GN, 4>(tmA, tmB, tmO, a, grid, smem, s)
+                     : launch_conv_persist<BN, GN, 2>(tmA, tmB, tmO, a, grid, smem, s);
+}
+
+// Persistent patch-mode variant (conv_tc_persist_kernel) when the layer qualifies; returns 1 when it launched, 0 when the
+// caller should take the one-tile-per-CTA kernel, < 0 on error.
+static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int bn, int epi, int gn,
+                            const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t s) {
+  const int mode = conv_persist_mode();
+  if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
+  if (gn == GN_STATS && p->Cout != 64) return 0;
+  if (a0.KC != 64 && a0.KC != 32) return 0;
+  ConvTcArgs a = a0;
+  a.ntiles = a.tiles_x * a.tiles_y * p->N;
+  // auto: only where a CTA gets several tiles (measured: 11.2 vs 16.1 us at 3.5 tiles per SM, 64->64 at 256^2);
+  // smaller grids are latency-bound by their single wave and keep the deeper per-tile rings
+  if (mode < 0 && a.ntiles < 2 * sm_count()) return 0;
+  const uint32_t w_bytes = (uint32_t)(9 * a.nchunk) * a.b_bytes;
+  const uint32_t stage_bytes = 2u * 128u * (uint32_t)bn * 2u;
+  const uint32_t budget = 200u * 1024u;
+  if (w_bytes + stage_bytes + 2 * a.patch_bytes > budget) return 0;
+  int na = (int)((budget - w_bytes - stage_bytes) / a.patch_bytes);
+  if (na > 8) na = 8;
+  // the final GroupNorm reduction parks [64][257] floats in the (then dead) patch ring + staging region
+  if (gn == GN_STATS && (uint32_t)na * a.patch_bytes + stage_bytes < 64u * kSredPitch2 * sizeof(float)) return 0;
+  a.na = na;
+  a.p_off = w_bytes;                                   // b_bytes and patch_bytes are multiples of 1024
+  a.stage_off = a.p_off + (uint32_t)na * a.patch_bytes;
+  a.aux_off = a.stage_off + stage_bytes;
+  const size_t smem = (size_t)a.aux_off + 1024 + 32 * 8 + 16 + 64 * sizeof(float) + 64;
+  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  int rc;
+  const int ks = a.KC / 16;
+  if (bn == 64) rc = gn == GN_STATS ? launch_conv_persist_k<64, GN_STATS>(ks, tmA, tmB, tmO, a, grid, smem, s)
+                                    : launch_conv_persist_k<64, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
+  else if (bn == 32) rc = launch_conv_persist_k<32, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
+  else rc = launch_conv_persist_k<16, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
+  if (rc == OTVM_OK) ++g_conv_persist_launches;
+  return rc == OTVM_OK ? 1 : rc;
 }
 
 template <int BN>
@@ -839,6 +1167,10 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   } else if (dry_run) {
     return OTVM_ERR_UNSUPPORTED;
   }
+  if (!fuse_gn && tma_store) {
+    const int pr = try_conv_persist(p, a, bn, epi, gn, tmA, tmB, tmO, s);
+    if (pr != 0) return pr > 0 ? OTVM_OK : pr;
+  }
   switch (bn) {
     case 128: return dispatch_conv_tc<128>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
     case 64: return dispatch_conv_tc<64>(gn, epi, tmA, tmB, tmO, tmR, a, grid, smem, s, dry_run);
@@ -884,6 +1216,9 @@ extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_times
   otvm::g_conv_dbg = buf;
 }
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_budget_kb(int kb) { otvm::g_conv_budget_kb = kb; }
+// dev hook: persistent patch-mode kernel (-1 auto, 0 off, 1 whenever the shape allows; env OTVM_CONV_PERSIST)
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_persist(int mode) { otvm::g_conv_persist = mode; }
+extern "C" __attribute__((visibility("default"))) long long otvm_debug_conv_persist_launches() { return otvm::g_conv_persist_launches; }
 // dev hook: 3x3 halo-patch mode on/off (default on; env OTVM_CONV_HALO=0)
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_halo(int enabled) {
   otvm::g_conv_halo = enabled;              // -1 auto, 0 off, 1 forced on

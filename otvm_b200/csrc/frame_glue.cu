@@ -88,7 +88,8 @@ __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, cons
 //   pass 1 (rows)   : g2[y][x] = squared distance to the nearest seed in row y -- one warp per row, the nearest seed
 //                     to the left / right comes from a warp max / min scan carried across 32-pixel chunks
 //   pass 2 (columns): d2[y][x] = min_y' (y-y')^2 + g2[y'][x] -- a 32-column strip of g2 sits in shared memory and
-//                     every pixel takes the exhaustive minimum over its column (integer, branch-free)
+//                     every pixel searches its column outward from its own row until no farther row can win
+//                     (integer, exact; the exit test is warp-uniform)
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) edt_rowscan_kernel(const uint8_t* __restrict__ seed, int H, int W, int nmask,
                                                           int* __restrict__ g2) {
@@ -132,26 +133,37 @@ __global__ void __launch_bounds__(256) edt_cols_kernel(const int* __restrict__ g
   const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5, nwy = blockDim.x >> 5;
   const int x = x0 + lane;
   const int* g = g2 + (int64_t)m * H * W;
-  for (int y = wy; y < H; y += nwy) strip[y * 32 + lane] = x < W ? g[(int64_t)y * W + x] : EDT_INF;
-  __syncthreads();
-  if (x >= W) return;
+  // columns beyond the image hold 0 so that they never keep the warp-uniform search below alive
+  int any = 0;
+  for (int y = wy; y < H; y += nwy) {
+    const int v = x < W ? g[(int64_t)y * W + x] : 0;
+    strip[y * 32 + lane] = v;
+    any |= (x < W && v < EDT_INF);
+  }
+  const int has_seed = __syncthreads_or(any);
   // blockIdx.z splits the rows so that the grid covers the GPU (the whole strip is still needed for the search)
   const int rows_per = (H + gridDim.z - 1) / gridDim.z;
   const int y_lo = blockIdx.z * rows_per, y_hi = min(H, y_lo + rows_per);
   for (int y = y_lo + wy; y < y_hi; y += nwy) {
-    // branch-free exhaustive minimum over the column (masks with a handful of seeds make every early-exit search
-    // degenerate into a divergent full scan, which measured 6x slower than this)
-    int best = EDT_INF;
-    int yp = 0;
-    for (; yp + 8 <= H; yp += 8) {
+    // Outward search from the pixel's own row, 8 row pairs (y-d, y+d) per step, branch-free inside a step.  A row at
+    // distance d can only contribute values >= d*d, so the warp stops once d*d >= the largest running minimum of its
+    // 32 columns (warp-uniform exit: no divergence; a mask with few seeds degenerates into the full column scan at
+    // the cost of the old exhaustive loop).  Row indices are clamped instead of predicated: a clamped row r' is
+    // closer than d, so strip[r'] + d*d over-estimates a candidate that is (or was) also taken at its true distance.
+    int best = strip[y * 32 + lane];
+    if (has_seed) {                                    // an empty mask has no finite distance anywhere
+      const int rmax = max(y, H - 1 - y);
+      for (int r = 1; r <= rmax; r += 8) {
+        if (r * r >= __reduce_max_sync(0xffffffffu, best)) break;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int dy = y - (yp + u);
-        best = min(best, strip[(yp + u) * 32 + lane] + dy * dy);
+        for (int u = 0; u < 8; ++u) {
+          const int d = r + u;
+          const int up = strip[max(y - d, 0) * 32 + lane], dn = strip[min(y + d, H - 1) * 32 + lane];
+          best = min(best, min(up, dn) + d * d);
+        }
       }
     }
-    for (; yp < H; ++yp) { const int dy = y - yp; best = min(best, strip[yp * 32 + lane] + dy * dy); }
-    d2[((int64_t)m * H + y) * W + x] = best >= EDT_INF ? EDT_INF : best;
+    if (x < W) d2[((int64_t)m * H + y) * W + x] = best >= EDT_INF ? EDT_INF : best;
   }
 }
 

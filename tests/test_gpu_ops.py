@@ -192,7 +192,8 @@ def test_edt_bit_exact():
     import otvm_oracle as O
     ops = _ops()
     r = np.random.RandomState(0)
-    for (H, W), p in (((37, 53), 0.02), ((64, 64), 0.3), ((5, 90), 0.5), ((128, 96), 0.0005), ((33, 31), 0.0)):
+    for (H, W), p in (((37, 53), 0.02), ((64, 64), 0.3), ((5, 90), 0.5), ((128, 96), 0.0005), ((33, 31), 0.0),
+                      ((512, 512), 0.00002), ((300, 200), 0.2), ((257, 130), 0.001)):
         seed = (r.uniform(size=(H, W)) < p)
         if p > 0:
             seed[r.randint(H), r.randint(W)] = True
@@ -340,6 +341,68 @@ def test_conv2d_tcgen05(case, conv_halo):
         out4 = torch.zeros(1, Ho, Wo, Cout, dtype=dtype, device=DEV); outr4 = torch.zeros_like(out4)
         ops.conv2d(xd, wd, b.to(DEV), out4, pad=p, dil=d, res=nhwc(res, dtype), act=ops.ACT_RELU, out_relu=outr4, workspace=ws)
         assert rel_err(nchw(out4), want2) < 1e-2 and rel_err(nchw(outr4), want2) < 1e-2
+
+
+PERSIST_CASES = [
+    # Cin, Cout, k, pad, dil, H, W, gn   (3x3 stride-1, Cout in {16, 32, 64}: the persistent patch-mode kernel)
+    (64, 64, 3, 1, 1, 96, 128, True),        # one tile per CTA
+    (64, 64, 3, 1, 1, 296, 304, True),       # ~5 tiles per CTA, ragged rows
+    (96, 64, 3, 1, 1, 200, 168, True),       # three K-chunks per tile
+    (96, 32, 3, 1, 1, 250, 180, False),      # ragged columns
+    (64, 32, 3, 1, 1, 160, 160, False),
+    (32, 16, 3, 1, 1, 320, 320, False),
+    (64, 64, 3, 2, 2, 128, 128, False),      # dilation 2
+    (128, 32, 3, 1, 1, 64, 72, False),       # two 64-channel chunks
+    (64, 64, 3, 1, 1, 512, 512, True),       # the refinement-module layer itself (2048 tiles, auto mode)
+]
+
+
+@pytest.mark.parametrize("case", PERSIST_CASES)
+def test_conv2d_persistent(case):
+    """persistent patch-mode tcgen05 kernel (resident filter bank, tile loop, double-buffered TMEM accumulators and
+    staging tiles) == fp32 math on the bf16-rounded operands, incl. the GroupNorm statistics of the stored values"""
+    import ctypes
+    from otvm_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    lib.otvm_debug_set_conv_persist.argtypes = [ctypes.c_int]
+    lib.otvm_debug_conv_persist_launches.restype = ctypes.c_longlong
+    dtype = torch.bfloat16
+    Cin, Cout, k, p, d, H, W, gn = case
+    g = torch.Generator().manual_seed(sum(case[:7]))
+    x = torch.randn(1, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(Cout, generator=g)
+    want = F.conv2d(rnd(dtype, x), rnd(dtype, w), b, 1, p, d)
+    if not gn:
+        want = F.leaky_relu(want, 0.01)
+    xd = nhwc(x, dtype, ld=Cin + 8)
+    wd = w.permute(0, 2, 3, 1).contiguous().to(DEV, dtype)
+    auto = H * W >= 512 * 512
+    lib.otvm_debug_set_conv_persist(-1 if auto else 1)
+    try:
+        for trial in range(2):
+            out = torch.zeros(1, H, W, Cout + 8, dtype=dtype, device=DEV)[..., :Cout]
+            stats = torch.zeros(64, dtype=torch.float64, device=DEV) if gn else None
+            n0 = lib.otvm_debug_conv_persist_launches()
+            ops.conv2d(xd, wd, b.to(DEV), out, pad=p, dil=d, gn_stats=stats, act=ops.ACT_NONE if gn else ops.ACT_LEAKY)
+            torch.cuda.synchronize()
+            assert lib.otvm_debug_conv_persist_launches() == n0 + 1, "persistent kernel not selected"
+            assert rel_err(nchw(out), want) < 1e-2
+            if gn:
+                q = rnd(dtype, want).double()[0].reshape(32, -1)
+                assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 2e-3
+                assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 2e-3
+    finally:
+        lib.otvm_debug_set_conv_persist(-1)
+    # same layer through the one-tile-per-CTA kernel: both kernels round identically (fp32 accumulate, one bf16 rounding)
+    lib.otvm_debug_set_conv_persist(0)
+    try:
+        out0 = torch.zeros(1, H, W, Cout, dtype=dtype, device=DEV)
+        ops.conv2d(xd, wd, b.to(DEV), out0, pad=p, dil=d, act=ops.ACT_NONE if gn else ops.ACT_LEAKY)
+    finally:
+        lib.otvm_debug_set_conv_persist(-1)
+    assert rel_err(nchw(out0), nchw(out)) < 2e-3
 
 
 FUSED_GN_CASES = [
