@@ -16,6 +16,7 @@
 // another's main loop.
 #include <stdio.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "tc_common.cuh"
 
 namespace otvm {
@@ -210,66 +211,83 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
     }
   } else {
-  if (warp == 0 || warp == 2) {
-      // ===== TMA producers: warp 0 loads the activation boxes, warp 2 the weight boxes (it joins the epilogue
-      // afterwards).  Each ring slot ("group") holds KSUB K-chunks behind ONE full/empty barrier pair, so the
-      // ~400-cycle wait/arrive/issue latency of a single thread is paid once per KSUB chunks.  The A-side thread posts
-      // the expected byte count of the whole group; a B box landing first only makes the transaction count
-      // transiently negative, the phase cannot complete before the A-side arrival. =====
-      const bool load_a = warp == 0;
-      int s = 0; uint32_t ph = 0;
-      int tap = 0, chunk = 0, ky = 0, kx = 0;
-      if (it0 != 0) { tap = it0 / a.nchunk; chunk = it0 - tap * a.nchunk; ky = tap / a.KW; kx = tap - ky * a.KW; }   // split-K slices only
-      const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
-      const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
-      // The loop body is kept minimal and warp-uniform (elected lane issues): the serial instruction stream of this
-      // warp is the pipeline's critical path.  Measured per-iteration periods of variants of this loop: runtime
-      // div/mod indices 830 cycles, coordinate table in smem 700, nested K-chunk groups 870, this form 425.
-      for (int it = 0; it < num_k; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = smem + (size_t)s * stage_bytes;
-          if (load_a) {
-            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_4d(sa, &tmA, &full_bar[s], chunk * a.KC, cx + kx * a.dil, cy + ky * a.dil, n_img);
-            if (dbg && it == 0) dbg[2] = clock64();
-            if (dbg && it < 16) dbg[32 + it] = clock64();
-          } else {
-            tma_load_2d(sa + a.a_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
-          }
-        }
-        __syncwarp();
-        if (++s == a.nstage) { s = 0; ph ^= 1; }
-        if (++chunk == a.nchunk) { chunk = 0; ++tap; if (++kx == a.KW) { kx = 0; ++ky; } }
+  // ===== one-box-per-tap mode.  Each of the three loops below is ONE serial instruction stream (an elected lane) that
+  // paces the whole pipeline, so they are written to the instruction: raw 32-bit shared-memory addresses carried
+  // incrementally, 32-bit descriptor low words, K steps unrolled at compile time, no debug stamps inside.  Measured
+  // before (scripts/conv_ts3.py): the MMA warp passed one stage per 495 cycles and the producers issued one per 425,
+  // against 256 cycles of tensor work per 128x128x64 stage. =====
+  if (warp == 0) {
+    // ----- activation producer: one 4-D box {KC, TW*s, TH*s, 1} per (tap, chunk); posts the stage's byte count -----
+    int chunk = 0, kx = 0, ky = 0;
+    if (it0 != 0) { const int tap = it0 / a.nchunk; chunk = it0 - tap * a.nchunk; ky = tap / a.KW; kx = tap - ky * a.KW; }
+    const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
+    int c0 = chunk * a.KC, xx = cx + kx * a.dil, yy = cy + ky * a.dil;
+    const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    uint32_t fa = full0, ea = empty0, sa = base, ph = 1;
+    int s = 0;
+    for (int it = 0; it < num_k; ++it) {
+      mbar_wait_a(ea, ph);
+      if (elect_one()) {
+        mbar_arrive_expect_tx_a(fa, tx_bytes);
+        tma_load_4d_a(sa, &tmA, fa, c0, xx, yy, n_img);
+        if (dbg && it == 0) dbg[2] = clock64();
       }
-    } else if (warp == 1) {
-      // ===== MMA issuer (one elected thread); descriptors are advanced by adding byte offsets >> 4 to the low word =====
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
-      const int ksteps = a.KC / 16;
-      const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
-      const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
-      const uint32_t stage16 = stage_bytes >> 4;
-      int s = 0; uint32_t ph = 0, soff = 0;
+      __syncwarp();
+      fa += 8; ea += 8; sa += stage_bytes;
+      if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; sa = base; }
+      c0 += a.KC;
+      if (++chunk == a.nchunk) { chunk = 0; c0 = 0; xx += a.dil; if (++kx == a.KW) { kx = 0; xx = cx; yy += a.dil; } }
+    }
+  } else if (warp == 2) {
+    // ----- weight producer (joins the epilogue afterwards): box [BN x KC] at K offset (it0 + it) * KC (the packed K
+    // axis is tap-major, chunk-minor, so consecutive iterations are consecutive K columns).  A weight box landing
+    // before the activation thread's expect_tx only makes the transaction count transiently negative. -----
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    uint32_t fa = full0, ea = empty0, sb = base + a.a_bytes, ph = 1;
+    int s = 0, k0 = it0 * a.KC;
+    for (int it = 0; it < num_k; ++it) {
+      mbar_wait_a(ea, ph);
+      if (elect_one()) tma_load_2d_a(sb, &tmB, fa, k0, n0);
+      __syncwarp();
+      fa += 8; ea += 8; sb += stage_bytes; k0 += a.KC;
+      if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; sb = base + a.a_bytes; }
+    }
+  } else if (warp == 1) {
+    // ----- MMA issuer -----
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+    const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
+    const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
+    const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0, hi = (uint32_t)(adesc0 >> 32);   // same SBO / layout
+    const uint32_t stage16 = stage_bytes >> 4;
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), accum_a = smem_u32(accum_bar);
+    auto mma_loop = [&](auto ks_tag) {
+      constexpr int KS = decltype(ks_tag)::value;
+      uint32_t fa = full0, ea = empty0, a_lo = a_lo0, b_lo = b_lo0, ph = 0;
+      int s = 0;
       for (int it = 0; it < num_k; ++it) {
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait_a(fa, ph);
         tcgen05_after_sync();
         if (elect_one()) {
           if (dbg && it == 0) dbg[3] = clock64();
-          if (dbg && it < 16) dbg[16 + it] = clock64();
-          const uint64_t ad = adesc0 + soff, bd = bdesc0 + soff;
-          umma_bf16(tmem_base, ad, bd, idesc, it != 0);
-          for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
-          umma_commit(&empty_bar[s]);                          // frees the stage when these MMAs have read it
+          umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, it != 0);
+#pragma unroll
+          for (int k = 1; k < KS; ++k) umma_bf16_lh(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, 1u);
+          umma_commit_a(ea);                                   // frees the stage when these MMAs have read it
           if (it == num_k - 1) {
-            umma_commit(accum_bar);                            // accumulator complete
+            umma_commit_a(accum_a);                            // accumulator complete
             if (dbg) dbg[4] = clock64();
           }
         }
         __syncwarp();
-        soff += stage16;
-        if (++s == a.nstage) { s = 0; ph ^= 1; soff = 0; }
+        fa += 8; ea += 8; a_lo += stage16; b_lo += stage16;
+        if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; a_lo = a_lo0; b_lo = b_lo0; }
       }
-    }
+    };
+    if (a.KC == 64) mma_loop(std::integral_constant<int, 4>{});
+    else if (a.KC == 32) mma_loop(std::integral_constant<int, 2>{});
+    else mma_loop(std::integral_constant<int, 1>{});
+  }
 }
   if (warp >= 2) {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
