@@ -224,33 +224,50 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     int c0 = chunk * a.KC, xx = cx + kx * a.dil, yy = cy + ky * a.dil;
     const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t gbytes = (uint32_t)a.ksub * stage_bytes;            // one ring slot = ksub consecutive {A,B} stages
     uint32_t fa = full0, ea = empty0, sa = base, ph = 1;
     int s = 0;
-    for (int it = 0; it < num_k; ++it) {
+    auto advance = [&]() {
+      c0 += a.KC;
+      if (++chunk == a.nchunk) { chunk = 0; c0 = 0; xx += a.dil; if (++kx == a.KW) { kx = 0; xx = cx; yy += a.dil; } }
+    };
+    for (int it = 0; it < num_k;) {
+      const bool two = a.ksub == 2 && it + 1 < num_k;
       mbar_wait_a(ea, ph);
+      const int c0a = c0, xa = xx, ya = yy;
+      advance();
+      const int c0b = c0, xb = xx, yb = yy;
+      if (two) advance();
       if (elect_one()) {
-        mbar_arrive_expect_tx_a(fa, tx_bytes);
-        tma_load_4d_a(sa, &tmA, fa, c0, xx, yy, n_img);
+        mbar_arrive_expect_tx_a(fa, two ? 2 * tx_bytes : tx_bytes);
+        tma_load_4d_a(sa, &tmA, fa, c0a, xa, ya, n_img);
+        if (two) tma_load_4d_a(sa + stage_bytes, &tmA, fa, c0b, xb, yb, n_img);
         if (dbg && it == 0) dbg[2] = clock64();
       }
       __syncwarp();
-      fa += 8; ea += 8; sa += stage_bytes;
+      it += two ? 2 : 1;
+      fa += 8; ea += 8; sa += gbytes;
       if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; sa = base; }
-      c0 += a.KC;
-      if (++chunk == a.nchunk) { chunk = 0; c0 = 0; xx += a.dil; if (++kx == a.KW) { kx = 0; xx = cx; yy += a.dil; } }
     }
   } else if (warp == 2) {
     // ----- weight producer (joins the epilogue afterwards): box [BN x KC] at K offset (it0 + it) * KC (the packed K
     // axis is tap-major, chunk-minor, so consecutive iterations are consecutive K columns).  A weight box landing
     // before the activation thread's expect_tx only makes the transaction count transiently negative. -----
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    const uint32_t gbytes = (uint32_t)a.ksub * stage_bytes;
     uint32_t fa = full0, ea = empty0, sb = base + a.a_bytes, ph = 1;
     int s = 0, k0 = it0 * a.KC;
-    for (int it = 0; it < num_k; ++it) {
+    for (int it = 0; it < num_k;) {
+      const bool two = a.ksub == 2 && it + 1 < num_k;
       mbar_wait_a(ea, ph);
-      if (elect_one()) tma_load_2d_a(sb, &tmB, fa, k0, n0);
+      if (elect_one()) {
+        tma_load_2d_a(sb, &tmB, fa, k0, n0);
+        if (two) tma_load_2d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, n0);
+      }
       __syncwarp();
-      fa += 8; ea += 8; sb += stage_bytes; k0 += a.KC;
+      it += two ? 2 : 1;
+      k0 += two ? 2 * a.KC : a.KC;
+      fa += 8; ea += 8; sb += gbytes;
       if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; sb = base + a.a_bytes; }
     }
   } else if (warp == 1) {
@@ -263,9 +280,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), accum_a = smem_u32(accum_bar);
     auto mma_loop = [&](auto ks_tag) {
       constexpr int KS = decltype(ks_tag)::value;
+      const uint32_t g16 = (uint32_t)a.ksub * stage16;
       uint32_t fa = full0, ea = empty0, a_lo = a_lo0, b_lo = b_lo0, ph = 0;
       int s = 0;
-      for (int it = 0; it < num_k; ++it) {
+      for (int it = 0; it < num_k;) {
+        const bool two = a.ksub == 2 && it + 1 < num_k;
+        const bool last = it + (two ? 2 : 1) >= num_k;
         mbar_wait_a(fa, ph);
         tcgen05_after_sync();
         if (elect_one()) {
@@ -273,14 +293,20 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, it != 0);
 #pragma unroll
           for (int k = 1; k < KS; ++k) umma_bf16_lh(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, 1u);
-          umma_commit_a(ea);                                   // frees the stage when these MMAs have read it
-          if (it == num_k - 1) {
+          if (two) {
+#pragma unroll
+            for (int k = 0; k < KS; ++k)
+              umma_bf16_lh(tmem_base, a_lo + stage16 + 2 * k, hi, b_lo + stage16 + 2 * k, hi, idesc, 1u);
+          }
+          umma_commit_a(ea);                                   // frees the slot when these MMAs have read it
+          if (last) {
             umma_commit_a(accum_a);                            // accumulator complete
             if (dbg) dbg[4] = clock64();
           }
         }
         __syncwarp();
-        fa += 8; ea += 8; a_lo += stage16; b_lo += stage16;
+        it += two ? 2 : 1;
+        fa += 8; ea += 8; a_lo += g16; b_lo += g16;
         if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; a_lo = a_lo0; b_lo = b_lo0; }
       }
     };
@@ -850,6 +876,11 @@ static int conv_halo_mode() {
   return g_conv_halo;
 }
 
+static int g_conv_ksub = -2;              // K-chunks per barrier pair on one-wave grids: 2 (default) or 1
+static int conv_ksub_mode() {
+  if (g_conv_ksub == -2) { const char* e = getenv("OTVM_CONV_KSUB"); g_conv_ksub = e ? atoi(e) : 2; }
+  return g_conv_ksub;
+}
 static long long g_conv_persist_launches = 0;
 static int g_conv_persist = -2;           // -2 unset, -1 auto (default), 0 off, 1 whenever the shape allows
 static int conv_persist_mode() {
@@ -1063,14 +1094,21 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
                   : bn <= 64 ? 48u * 1024u : 96u * 1024u;
   if (a.halo && a.b_off + 3 * a.b_bytes > budget) budget = 190u * 1024u;
   const int num_k = a.KH * a.KW * a.nchunk;
-  int ksub = 1;                            // (K-chunk groups per barrier were measured slower; kept at 1)
-  a.ksub = ksub;
-  int nstage = (int)((budget - a.b_off) / (stage * ksub));
-  if (nstage > 8) nstage = 8;
-  const int ngroups_total = ceil_div(num_k, ksub);
-  if (nstage > ngroups_total) nstage = ngroups_total < 2 ? 2 : ngroups_total;
-  if (nstage < 2) nstage = 2;
-  a.nstage = nstage;
+  // K-chunk groups: a one-wave grid is paced by the per-stage round trip of its single-thread loops (wait, elect,
+  // issue, commit: ~420 cycles per 128x128x64 stage against 256 cycles of tensor work, scripts/conv_ts3.py), so there
+  // one barrier pair covers TWO consecutive K-chunks (8 MMAs / 2+2 TMA boxes per round trip).  Multi-wave grids keep
+  // single chunks: with two CTAs per SM the tensor pipe is already shared at ~2 x 256 cycles per stage pair.
+  auto ring = [&](int ksub_, int iters) {
+    uint32_t bud = budget;
+    if (ksub_ == 2 && bud < 200u * 1024u) bud = 200u * 1024u;
+    int n = (int)((bud - a.b_off) / (stage * ksub_));
+    if (n > 8) n = 8;
+    const int groups = ceil_div(iters, ksub_);
+    if (n > groups) n = groups;
+    if (n < 2) n = 2;
+    return n;
+  };
+  int ksub = (!a.halo && ctas <= sm_count() && num_k >= 8 && conv_ksub_mode() >= 2) ? 2 : 1;
   // split-K: a grid that fills less than half of the SMs walks K serially at TMA/L2 latency; slice K across
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
   int nsplit = 1;
@@ -1090,7 +1128,10 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   }
   nsplit = ceil_div(num_k, a.k_per_split);
   a.split_stride = Mtot * p->Cout;
-  { const int gps = ceil_div(a.k_per_split, a.ksub); if (a.nstage > gps) a.nstage = gps < 2 ? 2 : gps; }
+  if (a.k_per_split < 4) ksub = 1;
+  a.ksub = ksub;
+  a.nstage = ring(ksub, a.k_per_split);
+  const int nstage = a.nstage;
   a.bias = p->bias; a.out = p->out; a.out_ps = p->out_ps; a.out_cs = p->out_cs;
   a.res = static_cast<const bf16*>(p->res); a.res_ld = p->res_ld;
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
@@ -1234,6 +1275,8 @@ extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_times
   otvm::g_conv_dbg = buf;
 }
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_budget_kb(int kb) { otvm::g_conv_budget_kb = kb; }
+// dev hook: K-chunks per barrier pair on one-wave grids (1 or 2; env OTVM_CONV_KSUB)
+extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_ksub(int n) { otvm::g_conv_ksub = n; }
 // dev hook: persistent patch-mode kernel (-1 auto, 0 off, 1 whenever the shape allows; env OTVM_CONV_PERSIST)
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_persist(int mode) { otvm::g_conv_persist = mode; }
 extern "C" __attribute__((visibility("default"))) long long otvm_debug_conv_persist_launches() { return otvm::g_conv_persist_launches; }
