@@ -45,8 +45,10 @@ struct ConvTcArgs {
   int act, out_f32;
   double* gn_stats;
   const float* gn_gamma; const float* gn_beta; float gn_eps;   // GN == 2: normalise in this kernel (grid barrier)
+  double gn_inv_cnt;           // 1 / elements per GroupNorm group
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
   // persistent patch-mode kernel (conv_tc_persist_kernel): tiles walked per CTA, smem carve-up
+  int vec_store;               // one-wave grids: 16-byte global stores straight from registers (no staging tile / TMA store)
   int ntiles;                  // tiles_x * tiles_y * N
   uint32_t p_off, stage_off;   // byte offsets of the patch ring and of the two epilogue staging tiles (weights sit at 0)
 };
@@ -391,10 +393,10 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (e < BN && n0 + e < a.Cout) {
         const int ch = n0 + e, g = ch / cg;
-        const double cnt = (double)a.Ho * a.Wo * cg;
-        const double mean = __ldcg(&a.gn_stats[g * 2]) / cnt;
-        const double var = __ldcg(&a.gn_stats[g * 2 + 1]) / cnt - mean * mean;
-        const float rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)a.gn_eps));
+        // (fp64 only for the cancelling subtraction; fp64 division / square root run at 1/64 rate on this part)
+        const double mean = __ldcg(&a.gn_stats[g * 2]) * a.gn_inv_cnt;
+        const double var = fma(-mean, mean, __ldcg(&a.gn_stats[g * 2 + 1]) * a.gn_inv_cnt);
+        const float rstd = 1.0f / sqrtf(fmaxf((float)var, 0.f) + a.gn_eps);
         const float sc = rstd * a.gn_gamma[ch];
         sstat[e] = sc;
         sstat[128 + e] = a.gn_beta[ch] - (float)mean * sc;
@@ -455,6 +457,39 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
       if constexpr (!kDirect) {
+        if (a.vec_store) {
+          // experiment (OTVM_CONV_VEC_STORE=1, off by default): 16-byte stores straight from registers instead of the
+          // staging tile + proxy fence + barrier + TMA store + read-wait tail.  It shortens the CTA's epilogue by ~600
+          // cycles (scripts/conv_ts3.py) but the frame got SLOWER (416.6 vs 421.6 frames/s, two runs each): the
+          // quarter-sector stores of 32 lanes x 16 bytes cost the consumers more than the tail saved.
+          if (valid) {
+            bf16* op = static_cast<bf16*>(a.out) + pix * a.out_ps + cbase;
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              if (cbase + 8 * j < a.Cout) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+            if constexpr (kRelu2) {
+              bf16* rp2 = a.out_relu + pix * a.out_relu_ld + cbase;
+#pragma unroll
+              for (int j = 0; j < CH / 8; ++j) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(v[8 * j + 2 * e], 0.f), fmaxf(v[8 * j + 2 * e + 1], 0.f));
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                if (cbase + 8 * j < a.Cout) *reinterpret_cast<uint4*>(rp2 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          continue;
+        }
         // swizzled staging tile(s): [BN/64][128 rows][min(BN,64) ch]; 16-byte chunk j of row r lands at the address the
         // TMA swizzle expects, so 8 consecutive rows cover all 32 banks (conflict-free 16 B stores).  Rows outside
         // the image are staged too and clipped by the tensor store.
@@ -494,7 +529,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
     }
     if (dbg && threadIdx.x == 64) dbg[9] = clock64();
-    if constexpr (!kDirect) {
+    if (!kDirect && !a.vec_store) {
       fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (threadIdx.x == 64) {
@@ -876,6 +911,11 @@ static int conv_halo_mode() {
   return g_conv_halo;
 }
 
+static int g_conv_vec_store = -2;         // one-wave grids store straight from registers (default 0: measured 416.6 vs 421.6 frames/s)
+static int conv_vec_store_mode() {
+  if (g_conv_vec_store == -2) { const char* e = getenv("OTVM_CONV_VEC_STORE"); g_conv_vec_store = e ? atoi(e) : 0; }
+  return g_conv_vec_store;
+}
 static int g_conv_ksub = -2;              // K-chunks per barrier pair on one-wave grids: 2 (default) or 1
 static int conv_ksub_mode() {
   if (g_conv_ksub == -2) { const char* e = getenv("OTVM_CONV_KSUB"); g_conv_ksub = e ? atoi(e) : 2; }
@@ -888,7 +928,29 @@ static int conv_persist_mode() {
   return g_conv_persist;
 }
 
-static int pick_bn(int Cout) { return Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16; }
+static int g_conv_small_bn = -2;          // narrower tiles on SM-starved grids (default 1; env OTVM_CONV_SMALL_BN)
+static int conv_small_bn_mode() {
+  if (g_conv_small_bn == -2) { const char* e = getenv("OTVM_CONV_SMALL_BN"); g_conv_small_bn = e ? atoi(e) : 1; }
+  return g_conv_small_bn;
+}
+
+// Tile width (output channels per CTA).  128 wherever the grid can fill the SMs; a grid that would leave more than half
+// of them idle takes 64-channel tiles instead: twice the CTAs, and each CTA's K loop is paced by its single MMA-issuing
+// thread at ~77 cycles per N=128 instruction against ~50 per N=64 one (scripts/conv_ts3.py), with half the epilogue.
+static int pick_bn(const otvm_conv_params* p) {
+  const int Cout = p->Cout;
+  int bn = Cout >= 128 ? 128 : Cout > 32 ? 64 : Cout > 16 ? 32 : 16;
+  if (bn == 128 && conv_small_bn_mode() > 0) {
+    const int Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
+    const int Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
+    int tw = 8; while (tw * 2 <= Wo && tw < 128) tw *= 2;
+    const int64_t tiles = (int64_t)ceil_div(Wo, tw) * ceil_div(Ho, 128 / tw) * p->N;
+    const int kc = p->Cin % 64 == 0 ? 64 : p->Cin % 32 == 0 ? 32 : 16;
+    const int num_k = p->KH * p->KW * (p->Cin / kc);            // long-K layers keep 128 and slice K instead (split-K)
+    if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k < 48) bn = 64;
+  }
+  return bn;
+}
 
 static bool aligned_view(const void* ptr, int64_t ld) {
   return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (ld * 2) % 16 == 0;
@@ -924,7 +986,7 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   if (Wo < 8 || Ho < 1 || (int64_t)Ho * Wo < 64) return false;
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
   if (p->gn_stats && (p->N != 1 || p->Cout % 32 != 0)) return false;
-  const int bn = pick_bn(p->Cout);
+  const int bn = pick_bn(p);
   if (conv_tc_epi(p, bn) < 0) return false;
   if (p->gn_stats) {            // a GroupNorm group must not straddle tiles / 16-column chunks irregularly
     const int cg = p->Cout / 32;
@@ -1047,6 +1109,7 @@ static int dispatch_conv_tc(int gn, int epi, const CUtensorMap& tmA, const CUten
 
 int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   ConvTcArgs a;
+  a.vec_store = 0; a.ntiles = 0; a.p_off = 0; a.stage_off = 0;
   a.N = p->N; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
   a.pad = p->pad; a.dil = p->dil; a.stride = p->stride;
   a.Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
@@ -1075,7 +1138,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.tw_shift = 0; while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
   a.tiles_x_magic = magic(a.tiles_x); a.tiles_y_magic = magic(a.tiles_y);     // exact for n * d < 2^32 (n < 2^16 tiles)
-  const int bn = pick_bn(p->Cout);
+  const int bn = pick_bn(p);
   a.a_bytes = a.halo ? 0u : 128u * a.KC * 2;
   a.b_bytes = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
   a.b_off = (uint32_t)a.na * a.patch_bytes;
@@ -1137,6 +1200,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
   a.gn_gamma = p->gn_gamma; a.gn_beta = p->gn_beta; a.gn_eps = p->gn_eps;
+  a.gn_inv_cnt = 1.0 / ((double)a.Ho * a.Wo * (double)(p->Cout >= 32 ? p->Cout / 32 : 1));
   a.dbg = g_conv_dbg;
   const bool fuse_gn = p->gn_gamma != nullptr;
   if (fuse_gn) {
@@ -1219,6 +1283,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.aux_off = (uint32_t)pipe;
   const int gn = fuse_gn ? GN_FUSED : p->gn_stats != nullptr ? GN_STATS : GN_NONE;
   const int epi = conv_tc_epi(p, bn);
+  a.vec_store = tma_store && ctas <= sm_count() && conv_vec_store_mode() != 0;
   if (fuse_gn) {
     const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
     const int64_t resident = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
                                                        const T* __restrict__ res, int64_t res_ld, int act,
-                                                       T* __restrict__ out, int64_t out_ld) {
+                                                       T* __restrict__ out, int64_t out_ld, double inv_cnt) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int n = blockIdx.y;
   const int tpp = C >> 3;                         // threads per pixel (divides 256)
@@ -85,12 +85,13 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   const int ppb = 256 / tpp;                      // pixels per block pass
   const int cg = C >> 5;
   __shared__ float g_mean[32], g_rstd[32];
-  if (threadIdx.x < 32) {                         // fp64 only for the 32 group moments (E[x^2] - E[x]^2 cancels)
-    const double cnt = (double)HW * cg;
-    const double mean = stats[(n * 32 + threadIdx.x) * 2] / cnt;
-    const double var = stats[(n * 32 + threadIdx.x) * 2 + 1] / cnt - mean * mean;
+  if (threadIdx.x < 32) {
+    // fp64 only where E[x^2] - E[x]^2 cancels (two multiplies and one fma: fp64 division / square root run at 1/64
+    // rate here and sat in every block's prologue); the reciprocal square root of the fp32 variance is exact enough
+    const double mean = stats[(n * 32 + threadIdx.x) * 2] * inv_cnt;
+    const double var = fma(-mean, mean, stats[(n * 32 + threadIdx.x) * 2 + 1] * inv_cnt);
     g_mean[threadIdx.x] = (float)mean;
-    g_rstd[threadIdx.x] = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps));
+    g_rstd[threadIdx.x] = 1.0f / sqrtf(fmaxf((float)var, 0.f) + eps);
   }
   __syncthreads();
   float sc[8], sh[8];
@@ -148,6 +149,7 @@ static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const dou
                       const float* beta, float eps, const void* res, int64_t res_ld, int act, void* out,
                       int64_t out_ld, cudaStream_t s) {
   const int tpp = C / 8, ppb = 256 / tpp;
+  const double inv_cnt = 1.0 / ((double)HW * (double)(C / 32));      // elements per (sample, group)
   int64_t blocks = ((int64_t)HW + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4);
   const int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
@@ -155,10 +157,10 @@ static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const dou
   dim3 grid((unsigned)blocks, N);
   if (res)
     launch_k(gn_apply_kernel<T, true>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
-                                                  static_cast<const T*>(res), res_ld, act, static_cast<T*>(out), out_ld);
+                                                  static_cast<const T*>(res), res_ld, act, static_cast<T*>(out), out_ld, inv_cnt);
   else
     launch_k(gn_apply_kernel<T, false>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
-                                                   nullptr, 0, act, static_cast<T*>(out), out_ld);
+                                                   nullptr, 0, act, static_cast<T*>(out), out_ld, inv_cnt);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
