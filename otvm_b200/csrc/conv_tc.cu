@@ -138,9 +138,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   // PDL: everything above (barriers, TMEM, tensor-map prefetch, bias = constant weights) overlapped the previous
   // kernel's tail; this CTA now owns all its resources, so dependents may be scheduled, and from here on it
   // touches activations produced by earlier kernels
+  // The weight-producer warp does NOT wait here: filters are never written inside a frame, so it issues the weight boxes
+  // of the whole first ring pass (every slot is free at kernel start) while the previous kernel is still running, and
+  // only then joins the wait.  Weights stream from HBM (150 MB per frame do not stay in L2), so they were the slowest
+  // part of a CTA's first stage.
+  constexpr int kWeightWarp = HALO ? 0 : 2;
   pdl_trigger();
-  pdl_wait();
-  if (dbg && threadIdx.x == 0) { dbg[1] = clock64(); dbg[11] = gtime_ns(); }
+  if (warp != kWeightWarp) pdl_wait();
+  if (dbg && threadIdx.x == 32) { dbg[1] = clock64(); dbg[11] = gtime_ns(); }
 
   // NOTE on the single-thread loops below: one thread issuing a dependent scalar chain is the pipeline's critical
   // path (measured ~830 cycles per K iteration with runtime div/mod for the stage / tap / chunk indices, and ~430
@@ -170,8 +175,12 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       int s = 0; uint32_t ph = 0;
       int tap = 0, chunk = it0 / 9;
       const uint32_t b_tx = (uint32_t)(BN * a.KC * 2);
+      bool waited = false;
       for (int it = 0; it < num_k; ++it) {
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (it >= a.nstage) {                                  // first ring pass: slots are free, no PDL wait yet
+          if (!waited) { pdl_wait(); waited = true; }
+          mbar_wait(&empty_bar[s], ph ^ 1);
+        }
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], b_tx);
           tma_load_2d(smem + a.b_off + (size_t)s * a.b_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         if (++s == a.nstage) { s = 0; ph ^= 1; }
         if (++tap == 9) { tap = 0; ++chunk; }
       }
+      if (!waited) pdl_wait();
     } else if (warp == 1) {
       // ===== MMA issuer: A descriptor = patch slot + (ky*d*pw + kx*d) pixel rows; 8-row groups are tile rows (TW = 8),
       // SBO = pw pixel rows.  Row-shifted SWIZZLE_* operands are valid because the hardware swizzles on absolute
@@ -259,9 +269,13 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const uint32_t gbytes = (uint32_t)a.ksub * stage_bytes;
     uint32_t fa = full0, ea = empty0, sb = base + a.a_bytes, ph = 1;
     int s = 0, k0 = it0 * a.KC;
-    for (int it = 0; it < num_k;) {
+    bool waited = false;
+    for (int it = 0, gi = 0; it < num_k; ++gi) {
       const bool two = a.ksub == 2 && it + 1 < num_k;
-      mbar_wait_a(ea, ph);
+      if (gi >= a.nstage) {                                    // first ring pass: slots are free, no PDL wait yet
+        if (!waited) { pdl_wait(); waited = true; }
+        mbar_wait_a(ea, ph);
+      }
       if (elect_one()) {
         tma_load_2d_a(sb, &tmB, fa, k0, n0);
         if (two) tma_load_2d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, n0);
@@ -272,6 +286,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       fa += 8; ea += 8; sb += gbytes;
       if (++s == a.nstage) { s = 0; ph ^= 1; fa = full0; ea = empty0; sb = base + a.a_bytes; }
     }
+    if (!waited) pdl_wait();
   } else if (warp == 1) {
     // ----- MMA issuer -----
     constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
@@ -948,6 +963,7 @@ static int pick_bn(const otvm_conv_params* p) {
     const int kc = p->Cin % 64 == 0 ? 64 : p->Cin % 32 == 0 ? 32 : 16;
     const int num_k = p->KH * p->KW * (p->Cin / kc);            // long-K layers keep 128 and slice K instead (split-K)
     if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k < 48) bn = 64;
+    // (32-channel tiles on the even smaller grids measured slower: 429.6 vs 433.2 frames/s)
   }
   return bn;
 }
