@@ -167,7 +167,8 @@ def run_b200(args):
                               "n_gpus": world, "steps": args.steps, "ms_per_step": round(ms_dev / args.steps, 4),
                               "e2e": {"value": round(world * args.steps / (ms_e2e * 1e-3), 3), "unit": "frames/s"},
                               "gpu_launches": int(launches), "clocks": clk,
-                              "config": {"overlap": os.environ.get("OTVM_OVERLAP", "1"), "pdl": os.environ.get("OTVM_PDL", "1")}}),
+                              "config": {"frame": [H, W], "memory_frames": T_MEM, "overlap": os.environ.get("OTVM_OVERLAP", "1"),
+                                         "pdl": os.environ.get("OTVM_PDL", "1")}}),
                   flush=True)
         if dist is not None:
             dist.destroy_process_group()
@@ -226,8 +227,8 @@ def run_b200(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_dev / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.precision,
             "data": "synthetic",
-            "config": {"workload": "512x512 synthetic clip, T=8 memory frames, full eval.py trimap->alpha per-frame loop "
-                                   "(BASELINE configs[1]); one independent clip per GPU, no collective",
+            "config": {"workload": f"{H}x{W} synthetic clip, T={T_MEM} memory frames, full eval.py trimap->alpha per-frame loop "
+                                   f"(BASELINE configs[{1 if H == 512 else 2}]); one independent clip per GPU, no collective",
                        "frame": [H, W], "memory_frames": T_MEM, "weights": "random-init (fixtures 'tempered', seed 111)",
                        "l2": "per-frame working set (activations + 150 MB of bf16 weights) exceeds the 126 MB L2; "
                              "8 distinct frames are cycled, no explicit flush"},
@@ -269,7 +270,7 @@ def run_reference_sample(steps, warmup):
             om(*f, **kw)
         dt = time.perf_counter() - t0
     return {"value": round(steps / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
-            "sample": f"{steps} steady-state 512x512 frames at T=8 (after {warmup} warm-up), oracle port of the "
+            "sample": f"{steps} steady-state {H}x{W} frames at T={T_MEM} (after {warmup} warm-up), oracle port of the "
                       f"reference on {cores} host threads, torch {torch.__version__} CPU fp32",
             "ms_per_step": round(dt / steps * 1e3, 1)}
 
@@ -284,7 +285,8 @@ def run_reference(args):
             "n_gpus": int(os.environ.get("WORLD_SIZE", 1)), "steps": steps, "warmup": warmup,
             "ms_per_step": cpu["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "512x512 synthetic clip, T=8 memory frames, full per-frame loop on host CPU cores"},
+            "config": {"workload": f"{H}x{W} synthetic clip, T={T_MEM} memory frames, full eval.py trimap->alpha per-frame "
+                                   "loop on the host CPU cores (oracle port of the reference)"},
             "cpu_baseline": cpu,
             "e2e": {"value": cpu["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -299,7 +301,13 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="dev: skip the instrumented per-family pass")
+    ap.add_argument("--size", type=int, default=512, help="frame height = width (BASELINE configs[2]: 1024)")
+    ap.add_argument("--memory", type=int, default=8, help="memory-bank frames T (BASELINE configs[2]: 16)")
     args = ap.parse_args()
+    global H, W, T_MEM, METRIC
+    H = W = args.size
+    T_MEM = args.memory
+    METRIC = f"frames/sec at {H}x{W}, T={T_MEM} memory"
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

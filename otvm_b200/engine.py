@@ -40,7 +40,8 @@ def _ws(w: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """state_dict -> kernel-ready tensors on ``device`` in ``dtype``."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device):
+    def __init__(self, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device, fba: bool = True):
+        """``fba=False`` packs the trimap-propagation network only (a stand-alone ``FullModel_eval``)."""
         self.dtype, self.device = dtype, device
         self.conv: Dict[str, tuple] = {}
         self.norm: Dict[str, tuple] = {}
@@ -86,10 +87,16 @@ class PackedWeights:
         plain = [d + ".convFM", d + ".ResMM.conv1", d + ".ResMM.conv2", d + ".pred"]
         for rf in ("RF3", "RF2"):
             plain += [f"{d}.{rf}.convFS"] + [f"{d}.{rf}.{rb}.conv{c}" for rb in ("ResFS", "ResMM") for c in "12"]
-        plain += ["NET.decoder.conv_up4.2", "NET.decoder.conv_up4.4", "NET.refine.pred.0", "NET.refine.pred.2",
-                  "NET.refine.pred.4"]
+        if fba:
+            plain += ["NET.decoder.conv_up4.2", "NET.decoder.conv_up4.4", "NET.refine.pred.0", "NET.refine.pred.2",
+                      "NET.refine.pred.4"]
         for name in plain:
             put(name, f(name + ".weight"), f(name + ".bias"))
+        ms = lambda m, s: [float(v) for v in f(m).flatten()] + [float(v) for v in f(s).flatten()]
+        self.ms_q = ms("trimap.model.Encoder_Q.mean", "trimap.model.Encoder_Q.std")
+        self.ms_m = ms("trimap.model.Encoder_M.mean", "trimap.model.Encoder_M.std")
+        if not fba:
+            return
         put("NET.decoder.conv_up4.0", f("NET.decoder.conv_up4.0.weight"), f("NET.decoder.conv_up4.0.bias"), cin_pad=96)
 
         # ---- FBA: weight-standardised convs + GroupNorm affine -----------------------------------------
@@ -118,18 +125,15 @@ class PackedWeights:
             for c in ("1", "2"):
                 ws_put(f"NET.refine.{l}.conv{c}"); gn_put(f"NET.refine.{l}.bn{c}")
 
-        ms = lambda m, s: [float(v) for v in f(m).flatten()] + [float(v) for v in f(s).flatten()]
         self.ms_alpha = ms("IMG_MEAN", "IMG_STD")
-        self.ms_q = ms("trimap.model.Encoder_Q.mean", "trimap.model.Encoder_Q.std")
-        self.ms_m = ms("trimap.model.Encoder_M.mean", "trimap.model.Encoder_M.std")
 
 
 class FramePlan:
     """Device buffers for one padded frame size (allocated once, reused every frame)."""
 
-    def __init__(self, H, W, dtype, device):
+    def __init__(self, H, W, dtype, device, multiple=32):
         self.H, self.W = H, W
-        self.Hp, self.Wp = H + (32 - H % 32) % 32, W + (32 - W % 32) % 32
+        self.Hp, self.Wp = H + (multiple - H % multiple) % multiple, W + (multiple - W % multiple) % multiple
         self.pad_top, self.pad_left = (self.Hp - H) // 2, (self.Wp - W) // 2     # models/alpha/common.py:17-19
         self.dtype, self.device = dtype, device
         self.bufs: Dict[str, torch.Tensor] = {}
@@ -239,9 +243,9 @@ class _Fork:
 
 
 class Engine:
-    def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16):
+    def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16, fba=True):
         self.dtype, self.device = dtype, torch.device(device)
-        self.w = PackedWeights(state_dict, dtype, self.device)
+        self.w = PackedWeights(state_dict, dtype, self.device, fba=fba)
         self.bank_capacity = bank_capacity
         self.plans: Dict[tuple, FramePlan] = {}
         self.banks: Dict[tuple, MemoryBank] = {}
@@ -378,8 +382,8 @@ class Engine:
             self._conv(pl, "trimap.model.KV_Q_r4.Value", r4, out=m4in[..., DO:], pad=1)
         qk = self._conv(pl, "trimap.model.KV_Q_r4.Key", r4, "q_key", pad=1)
         M = bank.T * bank.hw
-        ws_bytes = ops.memory_read_workspace(self.bank_capacity * bank.hw, h * w, DE, DO, self.dtype)
-        ws = pl.buf("read_ws", (ws_bytes // 4,), torch.float32)
+        ws_bytes = ops.memory_read_workspace(bank.cap * bank.hw, h * w, DE, DO, self.dtype)
+        ws = pl.buf(f"read_ws.{bank.cap}", (ws_bytes // 4,), torch.float32)
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)      # deferred memorize of the previous frame has landed
         ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws)
@@ -433,6 +437,57 @@ class Engine:
         if pl.pending is not None:
             self.memorize(pl, self.bank(pl), pl.pending)
             pl.pending = None
+
+    # ---- stand-alone STM entry points (FullModel_eval.forward(memorize=) / (segment=)) -----------------
+    def _stm_plan(self, H, W) -> FramePlan:
+        """buffers for STM.memorize / STM.segment called on their own: pad to 16 (STM.py:204,241), not 32"""
+        k = ("stm", H, W)
+        if k not in self.plans:
+            self.plans[k] = FramePlan(H, W, self.dtype, self.device, multiple=16)
+        return self.plans[k]
+
+    def stm_memorize(self, frame, masks):
+        """STM.memorize (STM.py:201-228): frame [1,3,H,W] RGB in [0,1], masks [1,20,H,W] = trimap 3 | alpha 1 | hidden 16
+        (models/trimap/model.py:231).  Returns key [1,1,128,1,h,w], value [1,1,512,1,h,w] fp32."""
+        H, W = frame.shape[-2:]
+        pl = self._stm_plan(H, W)
+        mean = torch.tensor(self.w.ms_m[:3], device=self.device).view(1, 3, 1, 1)
+        std = torch.tensor(self.w.ms_m[3:], device=self.device).view(1, 3, 1, 1)
+        lw, lh = (pl.Wp - W) // 2, (pl.Hp - H) // 2
+        pad = (lw, pl.Wp - W - lw, lh, pl.Hp - H - lh)
+        f = (torch.nn.functional.pad(frame.float(), pad) - mean) / std           # padding happens BEFORE Encoder_M normalises
+        m = torch.nn.functional.pad(masks.float(), pad)
+        x = torch.cat([f, m[:, 1:]], dim=1).contiguous()                         # rgb 3 | unknown | fg | alpha | hidden 16
+        mem_in = pl.buf("mem_in", (1, pl.Hp, pl.Wp, self.w.cin_mem), zero=True)
+        ops.nchw_to_nhwc(x, mem_in[..., :22])
+        bank = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), 1, self.dtype, self.device)
+        self.memorize(pl, bank, 0)
+        h, w = pl.Hp // 16, pl.Wp // 16
+        key = bank.keys.float().view(h, w, DE).permute(2, 0, 1).reshape(1, 1, DE, 1, h, w).contiguous()
+        val = bank.vals.float().view(1, 1, DO, 1, h, w).contiguous()
+        return key, val
+
+    def stm_segment(self, frame, keys, values):
+        """STM.segment (STM.py:239-257): frame [1,3,H,W] RGB in [0,1], keys [1,1,128,T,h,w], values [1,1,512,T,h,w].
+        Returns the trimap logits [1,3,H,W] fp32 (padding cropped)."""
+        H, W = frame.shape[-2:]
+        pl = self._stm_plan(H, W)
+        mean = torch.tensor(self.w.ms_q[:3], device=self.device).view(1, 3, 1, 1)
+        std = torch.tensor(self.w.ms_q[3:], device=self.device).view(1, 3, 1, 1)
+        lw, lh = (pl.Wp - W) // 2, (pl.Hp - H) // 2
+        f = (torch.nn.functional.pad(frame.float(), (lw, pl.Wp - W - lw, lh, pl.Hp - H - lh)) - mean) / std
+        imgn = pl.buf("imgn", (1, pl.Hp, pl.Wp, self.w.cin_img), zero=True)
+        ops.nchw_to_nhwc(f.contiguous(), imgn[..., :3])
+        T = keys.shape[3]
+        hw = (pl.Hp // 16) * (pl.Wp // 16)
+        assert keys.shape[-2:] == (pl.Hp // 16, pl.Wp // 16), "memory and query frame sizes differ"
+        bank = MemoryBank(hw, T, self.dtype, self.device)
+        bank.keys.copy_(keys[0, 0].permute(1, 2, 3, 0).reshape(T * hw, DE))
+        bank.vals.copy_(values[0, 0].reshape(DO, T * hw))
+        bank.order = list(range(T))
+        logits = self.segment(pl, bank)
+        out = logits[0, lh:lh + H, lw:lw + W, :3].permute(2, 0, 1).unsqueeze(0).contiguous()
+        return out
 
     # ---- FBA ---------------------------------------------------------------------------------------
     def matting(self, pl: FramePlan):

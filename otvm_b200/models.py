@@ -67,9 +67,52 @@ class FullModel_eval(nn.Module):
         self.memory_update = False
         _grow(self, "trimap.")
 
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError("FullModel_eval is driven by EvalModel.forward (segment / memorize run "
-                                  "inside the engine); see otvm_b200.engine.Engine.segment / .memorize")
+    # -- the wrapper runs on its own too (reference models/trimap/model.py:247-264) ---------------------------
+    def load_state_dict(self, *a, **k):
+        r = super().load_state_dict(*a, **k)
+        self._engine = None
+        return r
+
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def set_precision(self, precision: str):
+        assert precision in PRECISIONS
+        self.precision, self._engine = precision, None
+        return self
+
+    @property
+    def engine(self) -> Engine:
+        if getattr(self, "_engine", None) is None:
+            dev = self.IMG_MEAN.device
+            if dev.type != "cuda":
+                raise RuntimeError("otvm_b200 runs on a CUDA device only (no CPU fallback): call model.cuda()")
+            sd = {"trimap." + k: v for k, v in self.state_dict().items()}
+            precision = getattr(self, "precision", None) or os.environ.get("OTVM_PRECISION", "bf16")
+            self._engine = Engine(sd, PRECISIONS[precision], dev, fba=False)
+        return self._engine
+
+    @torch.no_grad()
+    def forward(self, a, fg, bg, tri=None, first_frame=False, og_shape=None, memorize=False, segment=False,
+                memories=None, hid=None, save_memory=False, max_memory_num=2, memory_update=False, memorize_gt=False):
+        """``memorize=True``: ``bg`` = frame (RGB in [0,1]) [1,3,H,W], ``tri`` [1,3,H,W], ``a`` = alpha [1,1,H,W],
+        ``hid`` [1,16,H,W] -> ``{'key': [1,1,128,1,h,w], 'val': [1,1,512,1,h,w]}`` (``_forward_memorize`` :227-239).
+        ``segment=True``: ``fg`` = query frame [1,3,H,W], ``memories`` = dict of key/val banks [1,1,C,T,h,w] -> trimap
+        logits [1,3,H,W] (``_forward_segment`` :241-245).  The stage-1 propagation loop (neither flag) is not part of the
+        stage-4 inference path."""
+        if memorize:
+            if bg.shape[0] != 1:
+                raise NotImplementedError("the reference memorises one frame at a time (b=1)")
+            masks = torch.cat([tri, a, hid], dim=1) if self.hdim > 0 else tri
+            key, val = self.engine.stm_memorize(bg, masks)
+            return {"key": key, "val": val}
+        if segment:
+            if fg.shape[0] != 1:
+                raise NotImplementedError("the reference segments one frame at a time (b=1)")
+            return self.engine.stm_segment(fg, memories["key"], memories["val"])
+        raise NotImplementedError("FullModel_eval without memorize= / segment= is the stage-1 propagation loop "
+                                  "(models/trimap/model.py:174-225); otvm_b200 covers the stage-4 inference path")
 
 
 class EvalModel(nn.Module):

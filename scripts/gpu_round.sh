@@ -24,6 +24,9 @@ for s in $STEPS; do
     bench)
       timeout 900 python bench.py --steps 32 --warmup 4 > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?"
       tail -3 $OUT/bench.err; cat $OUT/bench.json | head -c 3500; echo ;;
+    cfg3)  # BASELINE configs[2]: 1024x1024 clip, T=16 growing memory bank
+      timeout 600 python bench.py --size 1024 --memory 16 --steps 16 --warmup 3 --no-cpu-baseline --no-profile \
+        > $OUT/bench_cfg3.json 2> $OUT/bench_cfg3.err; echo "cfg3 rc=$?"; tail -2 $OUT/bench_cfg3.err; cat $OUT/bench_cfg3.json ;;
     ab)   # scheduling A/B: side-stream memorize and PDL on/off (device-resident value only)
       for v in "0 0" "1 0" "0 1"; do set -- $v
         OTVM_OVERLAP=$1 OTVM_PDL=$2 timeout 600 python bench.py --steps 32 --warmup 4 --no-cpu-baseline --no-profile \
@@ -45,7 +48,7 @@ for s in $STEPS; do
         -k regex:memory_read_tc -c 1 -f -o $OUT/read_full python scripts/one_frame.py bf16 1 > $OUT/ncu_read.log 2>&1; echo "ncu read rc=$?"
       export_rep $OUT/read_full source
       OTVM_PDL=0 timeout 600 ncu --set full --clock-control none --import-source on \
-        -k regex:conv_tc_kernel -c 12 -f -o $OUT/conv_full python scripts/conv_one.py > $OUT/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
+        -k regex:conv_tc -c 12 -f -o $OUT/conv_full python scripts/conv_one.py > $OUT/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
       export_rep $OUT/conv_full source
       OTVM_PDL=0 timeout 600 ncu --set full --clock-control none \
         -k regex:gn_apply -c 4 -f -o $OUT/gn_full python scripts/conv_one.py gn > $OUT/ncu_gn.log 2>&1; echo "ncu gn rc=$?"

@@ -109,3 +109,41 @@ def test_bf16_frames_teacher_forced():
         for k in ("dec_fused", "refine_fused", "alpha"):
             assert e[k][1] < 2.5e-2, (i, k, e[k])
         assert e["scaled_img"][0] < 1e-6 and e["tri_gt"][0] == 0
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+def test_trimap_wrapper_standalone(precision, tol):
+    """FullModel_eval.forward(memorize=True) / (segment=True) called directly with the reference's argument meaning
+    (models/trimap/model.py:247-264), on a size that needs the pad-16 of STM.memorize / STM.segment (STM.py:204,241),
+    against the oracle's restatement of the same two functions"""
+    import types
+    import otvm_b200
+    import otvm_oracle as O
+    from otvm_b200.fixtures import make_state_dict
+    sd = make_state_dict("tempered")
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4))
+    mt = otvm_b200.get_model_trimap(cfg, "Test", 12)
+    mt.load_state_dict({k[len("trimap."):]: v for k, v in sd.items() if k.startswith("trimap.")})
+    mt = mt.cuda().eval().set_precision(precision)
+    H, W = 88, 120                                   # pads to 96 x 128
+    g = torch.Generator().manual_seed(5)
+    frames = [torch.rand(1, 3, H, W, generator=g) for _ in range(3)]
+    tri = torch.nn.functional.one_hot(torch.randint(0, 3, (1, H, W), generator=g), 3).permute(0, 3, 1, 2).float()
+    alpha = torch.rand(1, 1, H, W, generator=g)
+    hid = torch.randn(1, 16, H, W, generator=g) * 0.5
+    keys, vals, okeys, ovals = [], [], [], []
+    for f in frames[:2]:
+        mem = mt(alpha.cuda(), None, f.cuda(), tri=tri.cuda(), memorize=True, hid=hid.cuda())
+        k4, v4 = O.stm_memorize(sd, f, torch.cat([tri, alpha, hid], dim=1))
+        assert mem["key"].shape == (1, 1, 128, 1, 6, 8) and mem["val"].shape == (1, 1, 512, 1, 6, 8)
+        assert rel_err(mem["key"][0].cpu(), k4) < tol and rel_err(mem["val"][0].cpu(), v4) < tol
+        keys.append(mem["key"]); vals.append(mem["val"]); okeys.append(k4); ovals.append(v4)
+    # segment the third frame against the ORACLE's two-frame bank (teacher forcing), then against its own
+    bank = {"key": torch.cat(okeys, dim=2).unsqueeze(0).cuda(), "val": torch.cat(ovals, dim=2).unsqueeze(0).cuda()}
+    logit = mt(None, frames[2].cuda(), None, segment=True, memories=bank)
+    want, _ = O.stm_segment(sd, frames[2], torch.cat(okeys, dim=2), torch.cat(ovals, dim=2))
+    assert logit.shape == (1, 3, H, W)
+    assert rel_err(logit.cpu(), want) < tol
+    own = {"key": torch.cat(keys, dim=3), "val": torch.cat(vals, dim=3)}
+    logit2 = mt(None, frames[2].cuda(), None, segment=True, memories=own)
+    assert rel_err(logit2.cpu(), want) < 3 * tol
