@@ -8,7 +8,7 @@ fam = collections.defaultdict(lambda: dict(launches=0, dram_bytes=0.0, us=0.0))
 seen = set()
 for r in csv.DictReader(lines):
     n = r["Kernel Name"]
-    f = ("conv_tcgen05" if "conv_tc_kernel" in n else "memory_read" if "memory_read_tc" in n else "memory_read_combine" if "combine" in n
+    f = ("conv_tcgen05" if "conv_tc_" in n else "memory_read" if "memory_read_tc" in n else "memory_read_combine" if "combine" in n
          else "gn_apply" if "gn_apply" in n else "conv_ffma" if ("conv_simt" in n or "smallm" in n) else "splitk_finish" if "splitk" in n
          else "upsample" if "upsample" in n else "other")
     v = float(r["Metric Value"].replace(",", ""))
