@@ -99,6 +99,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO print to stdout)
+        # go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.set_grad_enabled(False)
@@ -147,6 +150,10 @@ def run_b200(args):
     ms_dev = timed(lambda i: step(i, dev))
     launches = ops.launch_count() + model.engine.replayed_launches - l0
     clk = clocks.stop()
+    if dist is not None:                                   # whole-job count, like `value`
+        lt = torch.tensor([float(launches)], device="cuda")
+        dist.all_reduce(lt)
+        launches = int(lt.item())
 
     def e2e_step(i):
         a, fg, bg = host[i % n_src]
