@@ -105,6 +105,35 @@ def memory_read_cases(helpers):
     return out
 
 
+def stm_standalone_inputs(H=88, W=120, seed=5):
+    """the inputs of tests/test_gpu_frames.py::test_trimap_wrapper_standalone (re-drawn there from the same seed)"""
+    g = torch.Generator().manual_seed(seed)
+    frames = [torch.rand(1, 3, H, W, generator=g) for _ in range(3)]
+    tri = torch.nn.functional.one_hot(torch.randint(0, 3, (1, H, W), generator=g), 3).permute(0, 3, 1, 2).float()
+    alpha = torch.rand(1, 1, H, W, generator=g)
+    hid = torch.randn(1, 16, H, W, generator=g) * 0.5
+    return frames, tri, alpha, hid
+
+
+def stm_standalone_cases(helpers, state_dict):
+    """``FullModel_eval.forward(memorize=True)`` / ``(segment=True)`` of the reference called directly
+    (models/trimap/model.py:247-264) on a size that exercises the pad-16 of STM.memorize / STM.segment."""
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4))
+    mt = helpers.get_model_trimap(cfg, "Test", dilate_kernel=12)
+    mt.load_state_dict({k[len("trimap."):]: v for k, v in state_dict.items() if k.startswith("trimap.")})   # strict
+    mt.eval()
+    frames, tri, alpha, hid = stm_standalone_inputs()
+    out, keys, vals = {}, [], []
+    for i, f in enumerate(frames[:2]):
+        mem = mt(alpha, None, f, tri=tri, memorize=True, hid=hid)
+        out[f"m{i}_key"] = mem["key"][0, 0, :, 0].numpy().copy()
+        out[f"m{i}_val"] = mem["val"][0, 0, :, 0].numpy().copy()
+        keys.append(mem["key"]); vals.append(mem["val"])
+    bank = {"key": torch.cat(keys, dim=3), "val": torch.cat(vals, dim=3)}
+    out["seg_logit"] = mt(None, frames[2], None, segment=True, memories=bank)[0].numpy().copy()
+    return out
+
+
 def main():
     from otvm_b200.fixtures import make_state_dict
     torch.set_grad_enabled(False)
@@ -113,8 +142,13 @@ def main():
     gdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gdir, exist_ok=True)
 
-    np.savez_compressed(os.path.join(gdir, "memory_read.npz"), **memory_read_cases(helpers))
-    print("memory_read.npz")
+    only = sys.argv[1:]
+    if not only or "memory_read" in only:
+        np.savez_compressed(os.path.join(gdir, "memory_read.npz"), **memory_read_cases(helpers))
+        print("memory_read.npz")
+    if not only or "stm_standalone" in only:
+        np.savez_compressed(os.path.join(gdir, "stm_standalone.npz"), **stm_standalone_cases(helpers, make_state_dict("tempered")))
+        print("stm_standalone.npz")
 
     jobs = [  # name, kind, H, W, frames, max_mem, keep, stride
         ("clip_tempered_256", "tempered", 256, 256, 3, 8, None, 1),
@@ -122,7 +156,6 @@ def main():
         ("clip_tempered_120x152", "tempered", 120, 152, 3, 2, None, 1),     # pad-to-32 path + eviction (T<=2)
         ("clip_tempered_512_T8", "tempered", 512, 512, 10, 8, (8, 9), 4),   # BASELINE configs[1], strided sample
     ]
-    only = sys.argv[1:]
     for name, kind, H, W, n, mm, keep, stride in jobs:
         if only and name not in only:
             continue

@@ -149,3 +149,29 @@ def test_clip_sharding_two_ranks_gloo():
                         "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "_gloo_worker.py")],
                        env=env, capture_output=True, text=True, timeout=240)
     assert "OK 2" in r.stdout, r.stdout + r.stderr
+
+
+def test_trimap_wrapper_runs_alone_and_has_no_cpu_fallback():
+    """FullModel_eval (models/trimap/model.py:173) holds exactly the `trimap.*` keys, loads them strictly, packs the
+    STM weights without the alpha network, and refuses to compute on a CPU device (no fallback path exists)"""
+    import types
+    import otvm_b200
+    from otvm_b200.engine import FramePlan, PackedWeights
+    from otvm_b200.fixtures import make_state_dict
+    sd = make_state_dict("tempered")
+    tri_sd = {k[len("trimap."):]: v for k, v in sd.items() if k.startswith("trimap.")}
+    cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4))
+    mt = otvm_b200.get_model_trimap(cfg, "Test", 12)
+    assert set(mt.state_dict()) == set(tri_sd)
+    mt.load_state_dict(tri_sd)                                   # strict
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        mt(None, torch.zeros(1, 3, 32, 32), None, segment=True, memories={"key": None, "val": None})
+    with pytest.raises(NotImplementedError):
+        mt(torch.zeros(1, 1, 1, 32, 32), torch.zeros(1, 1, 3, 32, 32), torch.zeros(1, 1, 3, 32, 32))
+    w = PackedWeights({"trimap." + k: v for k, v in tri_sd.items()}, torch.bfloat16, "cpu", fba=False)
+    assert not w.norm and "trimap.model.KV_M_r4.Key" in w.conv and not any(k.startswith("NET.") for k in w.conv)
+    assert w.conv["trimap.model.Encoder_M.stem"][0].shape == (64, 7, 7, 32)          # 22 live channels padded to 32
+    # STM.memorize / STM.segment pad to 16 (STM.py:204,241), the eval frame to 32 (models/alpha/model.py:408-410)
+    p16, p32 = FramePlan(88, 120, torch.float32, "cpu", multiple=16), FramePlan(88, 120, torch.float32, "cpu")
+    assert (p16.Hp, p16.Wp, p16.pad_top, p16.pad_left) == (96, 128, 4, 4)
+    assert (p32.Hp, p32.Wp) == (96, 128)

@@ -95,3 +95,30 @@ def test_clip_padded_120x152_with_eviction():
 @pytest.mark.skipif(os.environ.get("OTVM_SLOW", "0") != "1", reason="set OTVM_SLOW=1 (10 frames at 512x512 on CPU)")
 def test_clip_tempered_512_T8():
     _check_clip("clip_tempered_512_T8", "tempered")
+
+
+def _stm_standalone_inputs(H=88, W=120, seed=5):
+    """same draw as oracle/make_golden.py::stm_standalone_inputs and tests/test_gpu_frames.py"""
+    g = torch.Generator().manual_seed(seed)
+    frames = [torch.rand(1, 3, H, W, generator=g) for _ in range(3)]
+    tri = torch.nn.functional.one_hot(torch.randint(0, 3, (1, H, W), generator=g), 3).permute(0, 3, 1, 2).float()
+    alpha = torch.rand(1, 1, H, W, generator=g)
+    hid = torch.randn(1, 16, H, W, generator=g) * 0.5
+    return frames, tri, alpha, hid
+
+
+def test_stm_memorize_segment_match_reference_wrapper():
+    """oracle STM.memorize / STM.segment == the reference's FullModel_eval.forward(memorize=) / (segment=) called
+    directly (models/trimap/model.py:247-264) on an 88x120 frame (pad-16 path); golden from the unmodified reference"""
+    g = golden("stm_standalone")
+    sd = make_state_dict("tempered")
+    frames, tri, alpha, hid = _stm_standalone_inputs()
+    keys, vals = [], []
+    with torch.no_grad():
+        for i, f in enumerate(frames[:2]):
+            k4, v4 = O.stm_memorize(sd, f, torch.cat([tri, alpha, hid], dim=1))
+            assert rel_err(k4[0, :, 0], g[f"m{i}_key"]) < TOL and rel_err(v4[0, :, 0], g[f"m{i}_val"]) < TOL
+            keys.append(k4); vals.append(v4)
+        logit, _ = O.stm_segment(sd, frames[2], torch.cat(keys, dim=2), torch.cat(vals, dim=2))
+    assert logit.shape == (1, 3, 88, 120)
+    assert rel_err(logit[0], g["seg_logit"]) < TOL
