@@ -175,3 +175,25 @@ def test_trimap_wrapper_runs_alone_and_has_no_cpu_fallback():
     p16, p32 = FramePlan(88, 120, torch.float32, "cpu", multiple=16), FramePlan(88, 120, torch.float32, "cpu")
     assert (p16.Hp, p16.Wp, p16.pad_top, p16.pad_left) == (96, 128, 4, 4)
     assert (p32.Hp, p32.Wp) == (96, 128)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the B200 arm): one JSON line on stdout with the
+    contract's keys, timed on the oracle port; under torchrun only rank 0 prints"""
+    import json
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--size", "128", "--memory", "2"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == os.cpu_count()
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True, text=True,
+                        timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
