@@ -47,7 +47,11 @@ OTVM_API int64_t otvm_launch_count(void);
 OTVM_API int otvm_device_is_sm100(int device);
 /* Programmatic dependent launch between consecutive kernels of a stream (default on; env OTVM_PDL=0 disables):
  * the next kernel's prologue overlaps the tail of the previous one; also recorded as programmatic edges when
- * the stream is being captured into a CUDA graph. */
+ * the stream is being captured into a CUDA graph.
+ * CONTRACT: parameters (convolution weight / bias, GroupNorm gamma / beta) are treated as constants of the stream:
+ * kernels read them BEFORE they wait for their predecessor (weight tiles are prefetched during the previous
+ * kernel's tail).  A caller that rewrites a parameter buffer on the device must synchronise the stream (or call
+ * otvm_set_pdl(0)) between that write and the next call that reads it.  Activations carry no such restriction. */
 OTVM_API void otvm_set_pdl(int enabled);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (e.g. the per-frame GroupNorm statistics arena) */
 OTVM_API int otvm_zero_async(void* ptr, int64_t bytes, void* stream);
