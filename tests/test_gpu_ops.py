@@ -260,6 +260,31 @@ def test_memory_read_golden_vectors():
     assert ci == 5
 
 
+def test_memory_read_baseline_sizes():
+    """the fused tcgen05 read at BASELINE.json's full sizes -- 512^2 with T=8 (cfg 2) and T=16 (north-star target), 1024^2
+    with T=16 (cfg 3: HW=4096, THW=65536, a 1 GB affinity for the unfused form) -- against softmax(K Q^T / sqrt(128)) V in
+    fp32 on the same bf16-rounded operands (STM.py:153-158); north-star tolerance for bf16: 1e-2 (measured 2.8e-3 .. 4e-3,
+    scripts/bench_read.py)"""
+    ops = _ops()
+    torch.manual_seed(0)
+    for hw_side, T in [(32, 8), (32, 16), (64, 16)]:
+        HW = hw_side * hw_side
+        M = T * HW
+        k = torch.randn(M, 128, device=DEV).bfloat16()
+        v = torch.randn(512, M, device=DEV).bfloat16()
+        q = (torch.randn(1, hw_side, hw_side, 128, device=DEV) * 1.5).bfloat16()
+        out = torch.zeros(1, hw_side, hw_side, 1024, device=DEV, dtype=torch.bfloat16)
+        ws = torch.zeros(ops.memory_read_workspace(M, HW, 128, 512, torch.bfloat16) // 4 + 1, device=DEV)
+        p = torch.softmax((k.float() @ q.view(HW, 128).float().t()) / math.sqrt(128), dim=0)       # [M, HW]
+        want = (v.float() @ p).t()                                                                   # [HW, 512]
+        del p
+        ops.memory_read(k, v, M, q, out[..., :512], M, ws)
+        torch.cuda.synchronize()
+        got = out[0, ..., :512].float().view(HW, 512)
+        assert float((got - want).abs().max() / want.abs().max()) < 1e-2, (hw_side, T)
+        assert float(out[..., 512:].float().abs().max()) == 0.0          # the query-value half is not this kernel's to write
+
+
 TC_CASES = [
     # Cin, Cout, k, pad, dil, H, W   (stride 1: the tcgen05 implicit-GEMM path)
     (3072, 256, 3, 1, 1, 32, 32),
