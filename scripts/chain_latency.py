@@ -13,9 +13,11 @@ NCH = 40
 def chain(shapes, H, W, pdl, reps=20):
     """shapes: list of (Cin, Cout, k, dil) applied cyclically; consecutive shapes must chain (Cout_i == Cin_{i+1})"""
     lib.otvm_set_pdl(1 if pdl else 0)
-    bufs, ws_ = {}, {}
+    # every buffer exists BEFORE the capture (a tensor created inside body() would put its fill kernel into the graph)
+    bufs = {(C, tag): torch.randn(1, H, W, C, device="cuda").bfloat16()
+            for C in {c for sh in shapes for c in sh[:2]} for tag in (0, 1, 2)}
     def t(C, tag):
-        return bufs.setdefault((C, tag), torch.randn(1, H, W, C, device="cuda").bfloat16())
+        return bufs[(C, tag)]
     wts = [((torch.randn(co, k, k, ci, device="cuda") / math.sqrt(ci * k * k)).bfloat16(), torch.zeros(co, device="cuda"))
            for ci, co, k, d in shapes]
     work = torch.empty(16 << 20, dtype=torch.float32, device="cuda")
