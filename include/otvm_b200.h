@@ -10,8 +10,15 @@
  *   - activations are NHWC ("pixel-major"): element (n,y,x,c) of a tensor lives at
  *     base[((n*H + y)*W + x) * ld + c]; `ld` >= C lets a producer write straight into a channel slice of a
  *     wider concat buffer (torch.cat is never materialised by a copy).
- *   - dtype: OTVM_F32 (strict fp32 arithmetic, FFMA) or OTVM_BF16 (bf16 storage, tcgen05 tensor cores with
- *     fp32 accumulation).  Statistics, softmax state and biases are always fp32.
+ *   - dtype: OTVM_F32 (strict fp32 arithmetic, FFMA), OTVM_BF16 (bf16 storage, tcgen05 tensor cores with fp32
+ *     accumulation) or a SPLIT format OTVM_SPLIT_DTYPE(planes, plane_stride_bytes), planes = 2 or 3: every
+ *     activation is the sum of `planes` bf16 tensors ("planes": bf16(v), bf16(v - plane0), ...; 16 / 24 significant
+ *     bits) that are identical views `plane_stride_bytes` apart, i.e. plane k of the tensor at address p lives at
+ *     p + k * plane_stride_bytes.  All split tensors passed to one call share that stride (allocate them from one
+ *     [planes][bytes] arena; the stride is a multiple of 4096).  The tensor cores multiply the planes pairwise
+ *     (3 products for 2 planes, 6 for 3: fp32-grade results at tensor-core rate); this is what lets the tcgen05 path
+ *     meet the reference's fp32 outputs to 1e-2 (2 planes) / 1e-3 (3 planes), which plain bf16 storage cannot
+ *     (DESIGN.md section 4).  Statistics, softmax state and biases are always fp32.
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), re-entrant per stream, and
  *     returns 0 on success or a negative code (see otvm_strerror); it never throws.
  */
@@ -24,14 +31,17 @@
 extern "C" {
 #endif
 
-#define OTVM_ABI_VERSION 3
+#define OTVM_ABI_VERSION 4
 #if defined(__GNUC__)
 #define OTVM_API __attribute__((visibility("default")))
 #else
 #define OTVM_API
 #endif
 
-enum { OTVM_F32 = 0, OTVM_BF16 = 1 };
+enum { OTVM_F32 = 0, OTVM_BF16 = 1, OTVM_BF16X2 = 2, OTVM_BF16X3 = 3 };
+/* dtype word of a split format: low byte = OTVM_BF16X2 / X3, upper bits = plane stride in 4096-byte units */
+#define OTVM_SPLIT_DTYPE(planes, plane_stride_bytes) \
+  ((int32_t)((planes) == 3 ? OTVM_BF16X3 : OTVM_BF16X2) | (int32_t)(((int64_t)(plane_stride_bytes) / 4096) << 8))
 enum { OTVM_ACT_NONE = 0, OTVM_ACT_RELU = 1, OTVM_ACT_LEAKY = 2 };     /* LeakyReLU slope 0.01 (nn default) */
 enum {
   OTVM_OK = 0, OTVM_ERR_ARG = -1, OTVM_ERR_CUDA = -2, OTVM_ERR_UNSUPPORTED = -3, OTVM_ERR_WORKSPACE = -4
@@ -68,7 +78,8 @@ OTVM_API int otvm_zero_async(void* ptr, int64_t bytes, void* stream);
 typedef struct {
   const void* in;      int64_t in_ld;             /* NHWC input, channel stride per pixel (elements)        */
   int32_t N, H, W, Cin;
-  const void* weight;                             /* [Cout][KH][KW][Cin], same dtype as activations          */
+  const void* weight;                             /* [Cout][KH][KW][Cin], same element format as activations */
+                                                  /* (split formats: planes `w_plane_stride` elements apart) */
   const float* bias;                              /* [Cout] fp32 or NULL                                    */
   int32_t Cout, KH, KW, stride, pad, dil;
   void* out;           int64_t out_ps, out_cs;    /* out element (p,co) at out[p*out_ps + co*out_cs]        */
@@ -76,7 +87,7 @@ typedef struct {
   void* out_relu;      int64_t out_relu_ld;       /* optional second NHWC output = ReLU(out) or NULL        */
   int32_t act;                                    /* OTVM_ACT_*                                             */
   int32_t relu_in;                                /* apply ReLU to the input while loading                  */
-  int32_t dtype;                                  /* OTVM_F32 / OTVM_BF16 for in, weight, out, res          */
+  int32_t dtype;                                  /* element format of in, weight, out, res, out_relu        */
   int32_t out_f32;                                /* 1: `out` is fp32 even when dtype is bf16 (heads)       */
   double* gn_stats;                               /* optional [N][32][2] (sum, sumsq) accumulated over out  */
   void* workspace;     int64_t workspace_bytes;   /* optional fp32 scratch: enables split-K for small grids */
@@ -90,6 +101,7 @@ typedef struct {
    * gn_stats_zeroed = 1) and no out_relu; ask otvm_conv2d_can_fuse_gn first (otvm_conv2d returns
    * OTVM_ERR_UNSUPPORTED otherwise and launches nothing). */
   const float* gn_gamma; const float* gn_beta;
+  int64_t w_plane_stride;                         /* split formats: elements between the planes of `weight`  */
 } otvm_conv_params;
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d can run this problem with the GroupNorm fused into the convolution kernel (see gn_gamma) */

@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libotvm_sm100.so")
 
-F32, BF16 = 0, 1
+F32, BF16, BF16X2, BF16X3 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
 
 c_i32, c_i64, c_vp, c_f = C.c_int32, C.c_int64, C.c_void_p, C.c_float
@@ -30,6 +30,7 @@ class ConvParams(C.Structure):
         ("workspace", c_vp), ("workspace_bytes", c_i64),
         ("gn_stats_zeroed", c_i32), ("gn_eps", c_f),
         ("gn_gamma", c_vp), ("gn_beta", c_vp),
+        ("w_plane_stride", c_i64),
     ]
 
 
@@ -97,7 +98,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
-    if lib.otvm_version() != 3:
+    if lib.otvm_version() != 4:
         raise OtvmError("ABI version mismatch")
     _lib = lib
     return lib

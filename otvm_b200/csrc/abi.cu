@@ -82,7 +82,7 @@ static int conv_check(const otvm_conv_params* p) {
   if (p->N <= 0 || p->H <= 0 || p->W <= 0 || p->Cin <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 ||
       p->stride <= 0 || p->dil <= 0 || p->pad < 0 || p->in_ld < p->Cin)
     return OTVM_ERR_ARG;
-  if (p->dtype != OTVM_F32 && p->dtype != OTVM_BF16) return OTVM_ERR_ARG;
+  { const int f = dtype_fmt(p->dtype); if (f < OTVM_F32 || f > OTVM_BF16X3) return OTVM_ERR_ARG; if (f >= OTVM_BF16X2 && (dtype_plane_stride(p->dtype) <= 0 || p->w_plane_stride <= 0)) return OTVM_ERR_ARG; }
   return OTVM_OK;
 }
 

@@ -52,6 +52,92 @@ template <typename T> __host__ __device__ __forceinline__ bool aligned4(const T*
   return (reinterpret_cast<uintptr_t>(p) & (4 * sizeof(T) - 1)) == 0;
 }
 
+// ---- split-bf16 elements ("bf16 x P") --------------------------------------------------------------------
+// A value is the SUM of P bf16 planes: plane 0 = bf16(v), plane 1 = bf16(v - plane 0), plane 2 = bf16(remainder):
+// 8 / 16 / 24 significant bits for P = 1 / 2 / 3.  The planes of one tensor are identical NHWC views `ps` elements
+// apart (all split tensors of a call live in one arena, include/otvm_b200.h "dtype").  The tensor cores multiply
+// planes pairwise (conv_tc.cu), every other kernel reads the sum and writes the split through the accessors below.
+template <int P> struct bx {};                 // element tag: bx<2>, bx<3>
+template <int P> struct BxPtr {
+  bf16* p; int64_t ps;
+  __host__ __device__ BxPtr() : p(nullptr), ps(0) {}
+  __host__ __device__ BxPtr(decltype(nullptr)) : p(nullptr), ps(0) {}
+  __host__ __device__ BxPtr(bf16* p_, int64_t ps_) : p(p_), ps(ps_) {}
+  __host__ __device__ BxPtr operator+(int64_t o) const { return BxPtr(p + o, ps); }
+  __host__ __device__ explicit operator bool() const { return p != nullptr; }
+};
+// pointer type of an element type: raw pointers for float / bf16, BxPtr for split elements
+template <typename T> struct El { typedef T* ptr; typedef const T* cptr; };
+template <int P> struct El<bx<P>> { typedef BxPtr<P> ptr; typedef BxPtr<P> cptr; };
+template <typename T> using ptr_t = typename El<T>::ptr;
+template <typename T> using cptr_t = typename El<T>::cptr;
+template <typename T> struct MkPtr {
+  static __host__ __device__ T* make(void* p, int64_t) { return static_cast<T*>(p); }
+  static __host__ __device__ const T* cmake(const void* p, int64_t) { return static_cast<const T*>(p); }
+};
+template <int P> struct MkPtr<bx<P>> {
+  static __host__ __device__ BxPtr<P> make(void* p, int64_t ps) { return BxPtr<P>(static_cast<bf16*>(p), ps); }
+  static __host__ __device__ BxPtr<P> cmake(const void* p, int64_t ps) { return BxPtr<P>(static_cast<bf16*>(const_cast<void*>(p)), ps); }
+};
+template <typename T> __host__ __device__ __forceinline__ ptr_t<T> mkptr(void* p, int64_t ps) { return MkPtr<T>::make(p, ps); }
+template <typename T> __host__ __device__ __forceinline__ cptr_t<T> mkcptr(const void* p, int64_t ps) { return MkPtr<T>::cmake(p, ps); }
+
+template <int P> __device__ __forceinline__ void load4(BxPtr<P> q, float (&v)[4]) {
+  load4(q.p, v);
+#pragma unroll
+  for (int k = 1; k < P; ++k) {
+    float t[4];
+    load4(q.p + k * q.ps, t);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] += t[j];
+  }
+}
+template <int P> __device__ __forceinline__ void store4(BxPtr<P> q, const float (&v)[4]) {
+  float r[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b = __floats2bfloat162_rn(r[2], r[3]);
+    uint2 t; t.x = *reinterpret_cast<uint32_t*>(&a); t.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(q.p + k * q.ps) = t;
+    r[0] -= __low2float(a); r[1] -= __high2float(a); r[2] -= __low2float(b); r[3] -= __high2float(b);
+  }
+}
+template <int P> __host__ __device__ __forceinline__ bool aligned4(BxPtr<P> q) {
+  return (reinterpret_cast<uintptr_t>(q.p) & 7) == 0 && (q.ps & 3) == 0;
+}
+// one element: ld1(ptr, index) / st1(ptr, index, value)
+__device__ __forceinline__ float ld1(const float* p, int64_t i) { return p[i]; }
+__device__ __forceinline__ float ld1(const bf16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <int P> __device__ __forceinline__ float ld1(BxPtr<P> q, int64_t i) {
+  float v = __bfloat162float(q.p[i]);
+#pragma unroll
+  for (int k = 1; k < P; ++k) v += __bfloat162float(q.p[i + k * q.ps]);
+  return v;
+}
+__device__ __forceinline__ void st1(float* p, int64_t i, float v) { p[i] = v; }
+__device__ __forceinline__ void st1(bf16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+template <int P> __device__ __forceinline__ void st1(BxPtr<P> q, int64_t i, float v) {
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    const bf16 h = __float2bfloat16_rn(v);
+    q.p[i + k * q.ps] = h;
+    v -= __bfloat162float(h);
+  }
+}
+// the value a consumer reads back after a store of `v` (GroupNorm statistics are those of the STORED tensor):
+// exact for fp32, bf16 rounding for one plane, identity (to ~2^-17) for split elements
+template <typename T> __device__ __forceinline__ float stored(float v) { return v; }
+template <> __device__ __forceinline__ float stored<bf16>(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+// dtype word of the C ABI: low byte = element format, bits 8.. = plane stride of split formats in 4 KB units
+__host__ __device__ __forceinline__ int dtype_fmt(int dtype) { return dtype & 0xff; }
+__host__ __device__ __forceinline__ int dtype_planes(int dtype) {
+  const int f = dtype & 0xff;
+  return f == OTVM_BF16X2 ? 2 : f == OTVM_BF16X3 ? 3 : 1;
+}
+// plane stride in ELEMENTS (bf16)
+__host__ __device__ __forceinline__ int64_t dtype_plane_stride(int dtype) { return ((int64_t)((uint32_t)dtype >> 8) * 4096) / 2; }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == OTVM_ACT_RELU) return fmaxf(v, 0.f);
   if (act == OTVM_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;

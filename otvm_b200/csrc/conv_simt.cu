@@ -20,6 +20,7 @@ struct ConvArgs {
   int act, relu_in, out_f32;
   double* gn_stats;
   int64_t M;
+  int64_t ps, wps;             // split formats: plane strides (elements) of activations / weights
 };
 
 constexpr int BM = 64, BN = 64, BK = 16, LDS_PAD = 4;
@@ -32,8 +33,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   __shared__ double gsum[BN][2];   // fp64: sums of fp32 partials are exact -> order-independent
 
   const int t = threadIdx.x;
-  const T* __restrict__ in = static_cast<const T*>(a.in);
-  const T* __restrict__ w = static_cast<const T*>(a.w);
+  const cptr_t<T> in = mkcptr<T>(a.in, a.ps);
+  const cptr_t<T> w = mkcptr<T>(a.w, a.wps);
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
 
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
   const int iy0 = poy * a.stride - a.pad, ix0 = pox * a.stride - a.pad;
   const int co_l = n0 + lrow;
   const bool co_ok = co_l < a.Cout;
-  const T* wrow = w + (int64_t)(co_ok ? co_l : 0) * a.K;
+  const cptr_t<T> wrow = w + (int64_t)(co_ok ? co_l : 0) * a.K;
 
   float ra[4], rb[4];
   auto load_tile = [&](int k0) {
@@ -63,8 +64,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
       int ky = tap / a.KW, kx = tap - ky * a.KW;
       int iy = iy0 + ky * a.dil, ix = ix0 + kx * a.dil;
       if (prow_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-        load4(in + ((int64_t)(pn * a.H + iy) * a.W + ix) * a.in_ld + c, ra);
-      if (co_ok) load4(wrow + k0 + lk, rb);
+        load4(in + (((int64_t)(pn * a.H + iy) * a.W + ix) * a.in_ld + c), ra);
+      if (co_ok) load4(wrow + (k0 + lk), rb);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -74,8 +75,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
           int ky = tap / a.KW, kx = tap - ky * a.KW;
           int iy = iy0 + ky * a.dil, ix = ix0 + kx * a.dil;
           if (prow_ok && iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-            ra[i] = to_f(in[((int64_t)(pn * a.H + iy) * a.W + ix) * a.in_ld + c]);
-          if (co_ok) rb[i] = to_f(wrow[kk]);
+            ra[i] = ld1(in, ((int64_t)(pn * a.H + iy) * a.W + ix) * a.in_ld + c);
+          if (co_ok) rb[i] = ld1(wrow, kk);
         }
       }
     }
@@ -137,14 +138,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         // statistics of what GroupNorm will read back: the value as stored (rounded to T)
-        float q = to_f(from_f<T>(v[j]));
+        float q = stored<T>(v[j]);
         s1[j] += q; s2[j] += q * q;
       }
     }
     if (a.res) {
-      const T* r = static_cast<const T*>(a.res) + p * a.res_ld + c0;
+      const cptr_t<T> r = mkcptr<T>(a.res, a.ps) + (p * a.res_ld + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) v[j] += to_f(r[j]);
+      for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) v[j] += ld1(r, j);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], a.act);
@@ -153,17 +154,17 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvArgs a) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) o[(int64_t)j * a.out_cs] = v[j];
     } else {
-      T* o = static_cast<T*>(a.out) + p * a.out_ps + (int64_t)c0 * a.out_cs;
+      const ptr_t<T> o = mkptr<T>(a.out, a.ps) + (p * a.out_ps + (int64_t)c0 * a.out_cs);
       if (a.out_cs == 1 && vec_ok && aligned4(o)) store4(o, v);
       else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) o[(int64_t)j * a.out_cs] = from_f<T>(v[j]);
+        for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) st1(o, (int64_t)j * a.out_cs, v[j]);
       }
     }
     if (a.out_relu) {
-      T* o = static_cast<T*>(a.out_relu) + p * a.out_relu_ld + c0;
+      const ptr_t<T> o = mkptr<T>(a.out_relu, a.ps) + (p * a.out_relu_ld + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) o[j] = from_f<T>(fmaxf(v[j], 0.f));
+      for (int j = 0; j < 4; ++j) if (c0 + j < a.Cout) st1(o, j, fmaxf(v[j], 0.f));
     }
   }
   if (a.gn_stats) {
@@ -193,8 +194,8 @@ __global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
   __shared__ float part[4][MP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co = blockIdx.x;
-  const T* __restrict__ in = static_cast<const T*>(a.in);
-  const T* __restrict__ wr = static_cast<const T*>(a.w) + (int64_t)co * a.K;
+  const cptr_t<T> in = mkcptr<T>(a.in, a.ps);
+  const cptr_t<T> wr = mkcptr<T>(a.w, a.wps) + (int64_t)co * a.K;
   const int M = (int)a.M;
   float acc[MP];
 #pragma unroll
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
     for (int i = 0; i < MP; ++i) {
       if (i < M) {
         float xv[4];
-        load4(in + (int64_t)i * a.in_ld + k, xv);
+        load4(in + ((int64_t)i * a.in_ld + k), xv);
         acc[i] = fmaf(wv[0], xv[0], acc[i]); acc[i] = fmaf(wv[1], xv[1], acc[i]);
         acc[i] = fmaf(wv[2], xv[2], acc[i]); acc[i] = fmaf(wv[3], xv[3], acc[i]);
       }
@@ -224,11 +225,11 @@ __global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
     float s1 = 0.f, s2 = 0.f;
     for (int i = lane; i < M; i += 32) {
       float v = part[0][i] + part[1][i] + part[2][i] + part[3][i] + (a.bias ? a.bias[co] : 0.f);
-      const float qv = to_f(from_f<T>(v));
+      const float qv = stored<T>(v);
       s1 += qv; s2 += qv * qv;
       v = apply_act(v, a.act);
       if (a.out_f32) static_cast<float*>(a.out)[(int64_t)i * a.out_ps + (int64_t)co * a.out_cs] = v;
-      else static_cast<T*>(a.out)[(int64_t)i * a.out_ps + (int64_t)co * a.out_cs] = from_f<T>(v);
+      else st1(mkptr<T>(a.out, a.ps), (int64_t)i * a.out_ps + (int64_t)co * a.out_cs, v);
     }
     if (a.gn_stats) {
       s1 = warp_sum(s1); s2 = warp_sum(s2);
@@ -244,8 +245,8 @@ __global__ void __launch_bounds__(128) conv1x1_smallm_kernel(const ConvArgs a) {
 template <typename T>
 static int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
   dim3 grid(ceil_div(a.M, BM), ceil_div(a.Cout, BN));
-  const T* in = static_cast<const T*>(a.in);
-  const T* w = static_cast<const T*>(a.w);
+  const cptr_t<T> in = mkcptr<T>(a.in, a.ps);
+  const cptr_t<T> w = mkcptr<T>(a.w, a.wps);
   bool fast = (a.Cin % BK == 0) && (a.in_ld % 4 == 0) && aligned4(in) && aligned4(w);
   if (fast && a.KH == 1 && a.KW == 1 && a.stride == 1 && a.pad == 0 && a.M <= 40 && a.K % 16 == 0 && !a.res && !a.out_relu &&
       !a.relu_in) {
@@ -270,7 +271,8 @@ int conv2d_simt(const otvm_conv_params* p, cudaStream_t s) {
   a.stride = p->stride; a.pad = p->pad; a.dil = p->dil; a.K = p->KH * p->KW * p->Cin;
   a.out = p->out; a.out_ps = p->out_ps; a.out_cs = p->out_cs;
   a.res = p->res; a.res_ld = p->res_ld; a.out_relu = p->out_relu; a.out_relu_ld = p->out_relu_ld;
-  a.act = p->act; a.relu_in = p->relu_in; a.out_f32 = p->out_f32 || p->dtype == OTVM_F32;
+  a.act = p->act; a.relu_in = p->relu_in; a.out_f32 = p->out_f32 || dtype_fmt(p->dtype) == OTVM_F32;
+  a.ps = dtype_plane_stride(p->dtype); a.wps = p->w_plane_stride;
   a.gn_stats = p->gn_stats;
   a.M = (int64_t)p->N * a.Ho * a.Wo;
   if (a.M <= 0 || a.Cout <= 0) return OTVM_OK;
@@ -278,12 +280,14 @@ int conv2d_simt(const otvm_conv_params* p, cudaStream_t s) {
     if (p->N != 1 || p->Cout % 32 != 0) return OTVM_ERR_UNSUPPORTED;
     if (!p->gn_stats_zeroed) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
   }
-  if (p->dtype == OTVM_F32) return launch_conv_simt<float>(a, s);
-  if (p->dtype == OTVM_BF16) {
-    // out_f32 with bf16 inputs: kernel's T is bf16 for in/weight/res, `out` written as float
-    return launch_conv_simt<bf16>(a, s);
+  // (out_f32 with bf16 / split inputs: the kernel's T covers in / weight / res, `out` is written as float)
+  switch (dtype_fmt(p->dtype)) {
+    case OTVM_F32: return launch_conv_simt<float>(a, s);
+    case OTVM_BF16: return launch_conv_simt<bf16>(a, s);
+    case OTVM_BF16X2: return launch_conv_simt<bx<2>>(a, s);
+    case OTVM_BF16X3: return launch_conv_simt<bx<3>>(a, s);
+    default: return OTVM_ERR_ARG;
   }
-  return OTVM_ERR_ARG;
 }
 
 }  // namespace otvm

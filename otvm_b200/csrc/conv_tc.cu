@@ -1,4 +1,17 @@
-// tcgen05 implicit-GEMM convolution for sm_100a (bf16 in, fp32 accumulate in TMEM).
+// tcgen05 implicit-GEMM convolution for sm_100a (bf16 planes in, fp32 accumulate in TMEM).
+//
+// Split-bf16 operands: an activation / weight is the sum of P bf16 planes (P = 1, 2, 3: 8 / 16 / 24 significant bits,
+// common.cuh).  A pipeline stage holds the P planes of the A tile and the P planes of the B tile, and the MMA warp
+// issues the plane products (a0 b0 | + a0 b1 + a1 b0 | + a1 b1 + a0 b2 + a2 b0) into ONE fp32 accumulator: fp32-grade
+// convolutions at tensor-core rate, 3x / 6x the MMA work of plain bf16 but the same TMEM / epilogue / tile traffic
+// per output.  The cross-plane products go to a SECOND accumulator (columns BN..2BN-1) that the epilogue adds in fp32:
+// the tensor core truncates (rounds toward zero) every time it adds an instruction's products to the accumulator, a
+// bias of ~half an ulp per MMA that grows linearly with the number of instructions (measured: three planes in one
+// accumulator were LESS exact than two, 8.5e-5 vs 5.9e-5 on the 9216-deep key projection); the cross terms are 2^-8 of
+// the result, so their truncation is harmless in an accumulator of their own and the main one sees one product per K
+// step again.  The epilogue splits the fp32 result back into planes.  The reference is fp32 end to end
+// (models/trimap/STM.py, models/alpha/FBA/models.py) and the random-weight networks amplify storage rounding: plain
+// bf16 misses its outputs by 0.3-0.7 in the max norm, two planes reach ~5e-4.
 //
 // GEMM view: M = output pixels, N = Cout, K = (ky, kx, ci).  One CTA computes a 128-pixel x BN-channel tile; the
 // 128 pixels are a TH x TW rectangle of the output map, so for every filter tap the A operand is ONE 4-D TMA
@@ -38,6 +51,11 @@ struct ConvTcArgs {
   int halo, na;                // na = patch ring slots
   uint32_t patch_bytes, b_off; // patch slot size (1024-aligned); byte offset of the B ring behind the patch ring
   uint32_t row_bytes;          // KC * 2
+  // split-bf16: planes per operand, plane products per K step (1 / 3 / 6), bytes of ONE operand plane inside a stage
+  // (a_bytes = planes * a_plane, b_bytes = planes * b_plane, a patch-ring slot = planes * patch_bytes)
+  int planes, npair;
+  uint32_t a_plane, b_plane;
+  int64_t act_plane;           // elements between the planes of out / res / out_relu in global memory
   const float* bias;
   void* out; int64_t out_ps, out_cs;
   const bf16* res; int64_t res_ld;
@@ -48,7 +66,6 @@ struct ConvTcArgs {
   double gn_inv_cnt;           // 1 / elements per GroupNorm group
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
   // persistent patch-mode kernel (conv_tc_persist_kernel): tiles walked per CTA, smem carve-up
-  int vec_store;               // one-wave grids: 16-byte global stores straight from registers (no staging tile / TMA store)
   int ntiles;                  // tiles_x * tiles_y * N
   uint32_t p_off, stage_off;   // byte offsets of the patch ring and of the two epilogue staging tiles (weights sit at 0)
 };
@@ -83,6 +100,25 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   return v;
 }
 
+// plane products of a K step, in issue order: (A plane, B plane) of product i = (kPairA >> 4i & 15, kPairB >> 4i & 15);
+// the first 1 / 3 / 6 entries are the products of 1 / 2 / 3 planes (terms below 2^-16 / 2^-24 of the result dropped)
+constexpr uint32_t kPairA = 0x201100u, kPairB = 0x021010u;
+
+// 8 fp32 values -> `planes` bf16 planes, 16 bytes each at base + plane * stride (x is consumed)
+__device__ __forceinline__ void split_store8(uint8_t* base, uint32_t stride, int planes, float (&x)[8]) {
+#pragma unroll 1
+  for (int pl = 0; pl < planes; ++pl) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+      pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+      x[2 * e] -= __low2float(h); x[2 * e + 1] -= __high2float(h);
+    }
+    *reinterpret_cast<uint4*>(base + (size_t)pl * stride) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
 template <int BN, int GN, int EPI, bool HALO>
 __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
@@ -106,7 +142,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   long long* dbg = a.dbg ? a.dbg + (size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
   if (dbg && threadIdx.x == 0) { dbg[0] = clock64(); dbg[10] = gtime_ns(); }
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+  constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;            // columns of one accumulator
+  const uint32_t tmem_cols = a.planes > 1 ? 2 * ACC_COLS : ACC_COLS;   // split operands: main + cross-term accumulator
 
   // tile coordinates
   int bx = blockIdx.x;
@@ -128,7 +165,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     for (int i = 0; i < 4; ++i) { mbar_init(&a_empty[i], 1); mbar_init(&a_full[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 1) tmem_alloc_n(tmem_slot, tmem_cols);
   for (int i = threadIdx.x; i < 2 * 128; i += kConvThreads) sstat[i] = 0.f;
   for (int i = threadIdx.x; i < BN; i += kConvThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
   tcgen05_before_sync();
@@ -159,13 +196,16 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       // up to `na` chunks ahead of the MMAs, independent of the depth of the weight ring =====
       int as = 0; uint32_t aph = 0;
       const int cx = x0 - a.pad, cy = y0 - a.pad;
-      const uint32_t a_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes;
+      const uint32_t a_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes * (uint32_t)a.planes;
+      const uint32_t slot_bytes = (uint32_t)a.planes * a.patch_bytes;
       const int c0 = it0 / 9, c1 = c0 + num_k / 9;
       for (int chunk = c0; chunk < c1; ++chunk) {
         mbar_wait(&a_empty[as], aph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&a_full[as], a_tx);
-          tma_load_4d(smem + (size_t)as * a.patch_bytes, &tmA, &a_full[as], chunk * a.KC, cx, cy, n_img);
+          for (int pl = 0; pl < a.planes; ++pl)
+            tma_load_5d(smem + (size_t)as * slot_bytes + (size_t)pl * a.patch_bytes, &tmA, &a_full[as], chunk * a.KC, cx, cy,
+                        n_img, pl);
         }
         __syncwarp();
         if (++as == a.na) { as = 0; aph ^= 1; }
@@ -174,7 +214,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       // ===== weight producer: one [BN x KC] box per (chunk, tap) =====
       int s = 0; uint32_t ph = 0;
       int tap = 0, chunk = it0 / 9;
-      const uint32_t b_tx = (uint32_t)(BN * a.KC * 2);
+      const uint32_t b_tx = (uint32_t)(BN * a.KC * 2 * a.planes);
       bool waited = false;
       for (int it = 0; it < num_k; ++it) {
         if (it >= a.nstage) {                                  // first ring pass: slots are free, no PDL wait yet
@@ -183,7 +223,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
         if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[s], b_tx);
-          tma_load_2d(smem + a.b_off + (size_t)s * a.b_bytes, &tmB, &full_bar[s], tap * a.Cin + chunk * a.KC, n0);
+          for (int pl = 0; pl < a.planes; ++pl)
+            tma_load_3d(smem + a.b_off + (size_t)s * a.b_bytes + (size_t)pl * a.b_plane, &tmB, &full_bar[s],
+                        tap * a.Cin + chunk * a.KC, n0, pl);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1; }
@@ -198,7 +240,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       const int ksteps = a.KC / 16;
       const uint64_t adesc0 = make_smem_desc(base, (uint32_t)pw * a.row_bytes, a.layout_type);
       const uint64_t bdesc0 = make_smem_desc(base + a.b_off, a.sbo, a.layout_type);
-      const uint32_t bstage16 = a.b_bytes >> 4, patch16 = a.patch_bytes >> 4;
+      const uint32_t bstage16 = a.b_bytes >> 4, patch16 = ((uint32_t)a.planes * a.patch_bytes) >> 4;
+      const uint32_t aplane16 = a.patch_bytes >> 4, bplane16 = a.b_plane >> 4;
       const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
       int s = 0; uint32_t ph = 0, soff = 0, aoff = 0, toff = 0, aph = 0; int as = 0, kx = 0, ky = 0;
       for (int it = 0; it < num_k; ++it) {
@@ -207,9 +250,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         tcgen05_after_sync();
         const bool last_tap = kx == 2 && ky == 2;
         if (elect_one()) {
-          const uint64_t ad = adesc0 + aoff + toff, bd = bdesc0 + soff;
-          umma_bf16(tmem_base, ad, bd, idesc, it != 0);
-          for (int k = 1; k < ksteps; ++k) umma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, 1u);
+          const uint64_t ad0 = adesc0 + aoff + toff, bd0 = bdesc0 + soff;
+          for (int pr = 0; pr < a.npair; ++pr) {
+            const uint64_t ad = ad0 + ((kPairA >> (4 * pr)) & 15u) * aplane16, bd = bd0 + ((kPairB >> (4 * pr)) & 15u) * bplane16;
+            // (product 0 -> main accumulator, cross-plane products -> the second one)
+            const uint32_t dt = pr == 0 ? tmem_base : tmem_base + ACC_COLS;
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(dt, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, pr == 0 ? (it | k) != 0 : (it | (pr - 1) | k) != 0);
+          }
           umma_commit(&empty_bar[s]);
           if (last_tap) umma_commit(&a_empty[as]);             // all 9 taps of this chunk have read the patch
           if (it == num_k - 1) umma_commit(accum_bar);
@@ -234,7 +282,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     if (it0 != 0) { const int tap = it0 / a.nchunk; chunk = it0 - tap * a.nchunk; ky = tap / a.KW; kx = tap - ky * a.KW; }
     const int cx = x0 * a.stride - a.pad, cy = y0 * a.stride - a.pad;
     int c0 = chunk * a.KC, xx = cx + kx * a.dil, yy = cy + ky * a.dil;
-    const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2);
+    const uint32_t tx_bytes = a.a_bytes + (uint32_t)(BN * a.KC * 2 * a.planes);
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
     const uint32_t gbytes = (uint32_t)a.ksub * stage_bytes;            // one ring slot = ksub consecutive {A,B} stages
     uint32_t fa = full0, ea = empty0, sa = base, ph = 1;
@@ -252,8 +300,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       if (two) advance();
       if (elect_one()) {
         mbar_arrive_expect_tx_a(fa, two ? 2 * tx_bytes : tx_bytes);
-        tma_load_4d_a(sa, &tmA, fa, c0a, xa, ya, n_img);
-        if (two) tma_load_4d_a(sa + stage_bytes, &tmA, fa, c0b, xb, yb, n_img);
+        for (int pl = 0; pl < a.planes; ++pl) tma_load_5d_a(sa + (uint32_t)pl * a.a_plane, &tmA, fa, c0a, xa, ya, n_img, pl);
+        if (two) tma_load_5d_a(sa + stage_bytes, &tmA, fa, c0b, xb, yb, n_img, 0);      // (ksub = 2 only with one plane)
         if (dbg && it == 0) dbg[2] = clock64();
       }
       __syncwarp();
@@ -277,8 +325,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         mbar_wait_a(ea, ph);
       }
       if (elect_one()) {
-        tma_load_2d_a(sb, &tmB, fa, k0, n0);
-        if (two) tma_load_2d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, n0);
+        for (int pl = 0; pl < a.planes; ++pl) tma_load_3d_a(sb + (uint32_t)pl * a.b_plane, &tmB, fa, k0, n0, pl);
+        if (two) tma_load_3d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, n0, 0);
       }
       __syncwarp();
       it += two ? 2 : 1;
@@ -293,7 +341,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
     const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
     const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0, hi = (uint32_t)(adesc0 >> 32);   // same SBO / layout
-    const uint32_t stage16 = stage_bytes >> 4;
+    const uint32_t stage16 = stage_bytes >> 4, aplane16 = a.a_plane >> 4, bplane16 = a.b_plane >> 4;
     const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar), accum_a = smem_u32(accum_bar);
     auto mma_loop = [&](auto ks_tag) {
       constexpr int KS = decltype(ks_tag)::value;
@@ -310,6 +358,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, it != 0);
 #pragma unroll
           for (int k = 1; k < KS; ++k) umma_bf16_lh(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, 1u);
+#pragma unroll
+          for (int pr = 1; pr < 6; ++pr) {                     // cross-plane products of split operands
+            if (pr < a.npair) {
+              const uint32_t ap = a_lo + ((kPairA >> (4 * pr)) & 15u) * aplane16, bp = b_lo + ((kPairB >> (4 * pr)) & 15u) * bplane16;
+#pragma unroll
+              for (int k = 0; k < KS; ++k)
+                umma_bf16_lh(tmem_base + ACC_COLS, ap + 2 * k, hi, bp + 2 * k, hi, idesc, (it | (pr - 1) | k) != 0);
+            }
+          }
           if (two) {
 #pragma unroll
             for (int k = 0; k < KS; ++k)
@@ -347,7 +404,9 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     constexpr int CH = BN >= 32 ? 32 : 16;                   // columns per TMEM load
     const int cg = GN != GN_NONE ? a.Cout / 32 : 0;          // channels per GroupNorm group
     const int cgc = cg < CH ? cg : CH;
-    float* sred = reinterpret_cast<float*>(smem + 128u * BN * 2u);   // behind the staging tile, inside the drained stages
+    constexpr uint32_t TILE = 128u * BN * 2u;                  // one bf16 staging tile (one plane of the output tile)
+    const uint32_t nplane = (uint32_t)a.planes;
+    float* sred = reinterpret_cast<float*>(smem + nplane * TILE);     // behind the staging tiles, inside the drained stages
     // act(v) = max(v,0) + slope*min(v,0): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
     const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
     mbar_wait(accum_bar, 0);
@@ -364,6 +423,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
         else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
         tmem_wait_ld();
+        if (nplane > 1) {                                    // + cross-plane accumulator
+          uint32_t raw2[CH];
+          if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
+          else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+        }
         float qv[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) qv[j] = valid ? __uint_as_float(raw[j]) + sbias[c + j] : 0.f;
@@ -434,6 +501,14 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
       }
       tmem_wait_ld();
+      if (nplane > 1) {                                      // + cross-plane accumulator
+        uint32_t raw2[CH];
+        if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
+        else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      }
       if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
       float v[CH];
 #pragma unroll
@@ -447,10 +522,16 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         for (int j = 0; j < CH; ++j) v[j] = fmaf(v[j], sstat[c + j], sstat[128 + c + j]);
       }
       if constexpr (GN == GN_STATS) {
-        // statistics of the values GroupNorm will read back (rounded to bf16); rows outside the image count 0
+        // statistics of the values GroupNorm will read back (one plane: rounded to bf16; split: the fp32 value to
+        // 2^-17); rows outside the image count 0
         float qv[CH];
+        if (nplane == 1) {
 #pragma unroll
-        for (int j = 0; j < CH; ++j) qv[j] = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+          for (int j = 0; j < CH; ++j) qv[j] = valid ? __bfloat162float(__float2bfloat16_rn(v[j])) : 0.f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH; ++j) qv[j] = valid ? v[j] : 0.f;
+        }
         const int slot0 = c / cgc;
         switch (cgc) {
           case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
@@ -462,49 +543,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         }
       }
       if constexpr (kRes) {
+#pragma unroll 1
+        for (uint32_t pl = 0; pl < nplane; ++pl) {
+          if (pl != 0) {                                       // further planes of a split residual
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res + (int64_t)pl * a.act_plane + pix * a.res_ld + cbase);
 #pragma unroll
-        for (int j = 0; j < CH / 8; ++j) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+            for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+          }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += __low2float(h[e]); v[8 * j + 2 * e + 1] += __high2float(h[e]); }
+          for (int j = 0; j < CH / 8; ++j) {
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += __low2float(h[e]); v[8 * j + 2 * e + 1] += __high2float(h[e]); }
+          }
         }
       }
 #pragma unroll
       for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
       if constexpr (!kDirect) {
-        if (a.vec_store) {
-          // experiment (OTVM_CONV_VEC_STORE=1, off by default): 16-byte stores straight from registers instead of the
-          // staging tile + proxy fence + barrier + TMA store + read-wait tail.  It shortens the CTA's epilogue by ~600
-          // cycles (scripts/conv_ts3.py) but the frame got SLOWER (416.6 vs 421.6 frames/s, two runs each): the
-          // quarter-sector stores of 32 lanes x 16 bytes cost the consumers more than the tail saved.
-          if (valid) {
-            bf16* op = static_cast<bf16*>(a.out) + pix * a.out_ps + cbase;
-#pragma unroll
-            for (int j = 0; j < CH / 8; ++j) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              if (cbase + 8 * j < a.Cout) *reinterpret_cast<uint4*>(op + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            }
-            if constexpr (kRelu2) {
-              bf16* rp2 = a.out_relu + pix * a.out_relu_ld + cbase;
-#pragma unroll
-              for (int j = 0; j < CH / 8; ++j) {
-                uint32_t pk[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(v[8 * j + 2 * e], 0.f), fmaxf(v[8 * j + 2 * e + 1], 0.f));
-                  pk[e] = *reinterpret_cast<uint32_t*>(&h);
-                }
-                if (cbase + 8 * j < a.Cout) *reinterpret_cast<uint4*>(rp2 + 8 * j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              }
-            }
-          }
-          continue;
-        }
         // swizzled staging tile(s): [BN/64][128 rows][min(BN,64) ch]; 16-byte chunk j of row r lands at the address the
         // TMA swizzle expects, so 8 consecutive rows cover all 32 banks (conflict-free 16 B stores).  Rows outside
         // the image are staged too and clipped by the tensor store.
@@ -514,21 +570,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           const int cc = c + 8 * j;
           uint32_t off = (uint32_t)(cc >> 6) * (128u * ROWB) + (uint32_t)r * ROWB + (uint32_t)(cc & 63) * 2u;
           off ^= ((off >> 7) & MASK) << 4;
-          uint32_t pk[4];
+          float x8[8];
+          if constexpr (kRelu2) {                              // second output = ReLU(out): tiles nplane .. 2 nplane - 1
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            for (int e = 0; e < 8; ++e) x8[e] = fmaxf(v[8 * j + e], 0.f);
+            split_store8(smem + nplane * TILE + off, TILE, a.planes, x8);
           }
-          *reinterpret_cast<uint4*>(smem + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          if constexpr (kRelu2) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(fmaxf(v[8 * j + 2 * e], 0.f), fmaxf(v[8 * j + 2 * e + 1], 0.f));
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            *reinterpret_cast<uint4*>(smem + 128u * BN * 2u + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          }
+          for (int e = 0; e < 8; ++e) x8[e] = v[8 * j + e];
+          split_store8(smem + off, TILE, a.planes, x8);
         }
       } else if (valid) {
         // direct stores: fp32 heads ([P][8] / [P][12]) and the channel-major value bank (lanes = consecutive pixels)
@@ -538,23 +588,34 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
         } else {
           bf16* op = static_cast<bf16*>(a.out) + pix * a.out_ps + (int64_t)cbase * a.out_cs;
+#pragma unroll 1
+          for (uint32_t pl = 0; pl < nplane; ++pl, op += a.act_plane) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < CH; ++j) {
+              const bf16 h = __float2bfloat16_rn(v[j]);
+              if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = h;
+              v[j] -= __bfloat162float(h);
+            }
+          }
         }
       }
     }
     if (dbg && threadIdx.x == 64) dbg[9] = clock64();
-    if (!kDirect && !a.vec_store) {
+    if (!kDirect) {
       fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync 2, 128;" ::: "memory");
       if (threadIdx.x == 64) {
         constexpr int NSUB = BN > 64 ? BN / 64 : 1;
         constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2;
+#pragma unroll 1
+        for (uint32_t pl = 0; pl < nplane; ++pl) {
 #pragma unroll
-        for (int sub = 0; sub < NSUB; ++sub) {
-          if (n0 + sub * 64 >= a.Cout) break;
-          tma_store_4d(&tmO, smem + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img);
-          if constexpr (kRelu2) tma_store_4d(&tmR, smem + 128u * BN * 2u + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img);
+          for (int sub = 0; sub < NSUB; ++sub) {
+            if (n0 + sub * 64 >= a.Cout) break;
+            tma_store_5d(&tmO, smem + pl * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
+            if constexpr (kRelu2)
+              tma_store_5d(&tmR, smem + (nplane + pl) * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
+          }
         }
         tma_store_commit_and_wait();
       }
@@ -581,7 +642,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   if (dbg && threadIdx.x == 0) { dbg[7] = clock64(); dbg[12] = gtime_ns(); }
   if (warp == 1) {
     tcgen05_after_sync();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc_n(tmem_base, tmem_cols);
   }
 }
 
@@ -645,7 +706,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       mbar_arrive_expect_tx(w_full, (uint32_t)(9 * a.nchunk) * (uint32_t)(BN * a.KC * 2));
       for (int chunk = 0; chunk < a.nchunk; ++chunk)
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_2d(smem + (size_t)(chunk * 9 + tap) * a.b_bytes, &tmB, w_full, tap * a.Cin + chunk * a.KC, 0);
+          tma_load_3d(smem + (size_t)(chunk * 9 + tap) * a.b_bytes, &tmB, w_full, tap * a.Cin + chunk * a.KC, 0, 0);
     }
     __syncwarp();
   }
@@ -670,7 +731,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
         mbar_wait(&p_empty[slot], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&p_full[slot], p_tx);
-          tma_load_4d(smem + a.p_off + (size_t)slot * a.patch_bytes, &tmA, &p_full[slot], chunk * a.KC, cx, cy, n_img);
+          tma_load_5d(smem + a.p_off + (size_t)slot * a.patch_bytes, &tmA, &p_full[slot], chunk * a.KC, cx, cy, n_img, 0);
         }
         __syncwarp();
         if (++slot == a.na) { slot = 0; ph ^= 1; }
@@ -803,7 +864,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
       if (leader) {
-        tma_store_4d(&tmO, stg, 0, x0, y0, n_img);            // clips ragged tiles
+        tma_store_5d(&tmO, stg, 0, x0, y0, n_img, 0);         // clips ragged tiles
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (q == 3) OTVM_PSTAMP(2 * j + g, 6);
@@ -847,11 +908,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
 
 // split-K second pass: sum the fp32 partial tiles and run the fused epilogue (bias, GroupNorm statistics of the
 // stored values, residual, activation, optional ReLU'd second output) on the 4 channels each thread owns
+template <typename T>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, int S, int64_t M, int Cout,
-                                                            const float* __restrict__ bias, const bf16* __restrict__ res,
+                                                            const float* __restrict__ bias, cptr_t<T> res,
                                                             int64_t res_ld, int act, void* __restrict__ out, int64_t out_ps,
-                                                            int64_t out_cs, int out_f32, bf16* __restrict__ out_relu,
-                                                            int64_t out_relu_ld, double* __restrict__ gn_stats) {
+                                                            int64_t out_cs, int out_f32, ptr_t<T> out_relu,
+                                                            int64_t out_relu_ld, double* __restrict__ gn_stats, int64_t ps) {
   pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ double sstat[32][2];      // fp64 partials: (near-)exact sums, so the atomic order does not change the result
   const int c4n = Cout >> 2;
@@ -872,7 +934,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     if (gn_stats) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        const float q0 = __bfloat162float(__float2bfloat16_rn(v[2 * h])), q1 = __bfloat162float(__float2bfloat16_rn(v[2 * h + 1]));
+        const float q0 = stored<T>(v[2 * h]), q1 = stored<T>(v[2 * h + 1]);
         if (cg >= 2) {
           atomicAdd(&sstat[(c + 2 * h) / cg][0], (double)q0 + (double)q1);
           atomicAdd(&sstat[(c + 2 * h) / cg][1], (double)q0 * q0 + (double)q1 * q1);
@@ -884,7 +946,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     }
     if (res) {
       float r[4];
-      load4(res + p * res_ld + c, r);
+      load4(res + (p * res_ld + c), r);
 #pragma unroll
       for (int j = 0; j < 4; ++j) v[j] += r[j];
     }
@@ -895,16 +957,16 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[(int64_t)j * out_cs] = v[j];
     } else {
-      bf16* o = static_cast<bf16*>(out) + p * out_ps + (int64_t)c * out_cs;
+      const ptr_t<T> o = mkptr<T>(out, ps) + (p * out_ps + (int64_t)c * out_cs);
       if (out_cs == 1 && aligned4(o)) store4(o, v);
       else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[(int64_t)j * out_cs] = __float2bfloat16_rn(v[j]);
+        for (int j = 0; j < 4; ++j) st1(o, (int64_t)j * out_cs, v[j]);
       }
     }
     if (out_relu) {
       float rl[4] = {fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f)};
-      store4(out_relu + p * out_relu_ld + c, rl);
+      store4(out_relu + (p * out_relu_ld + c), rl);
     }
   }
   if (gn_stats) {
@@ -926,11 +988,6 @@ static int conv_halo_mode() {
   return g_conv_halo;
 }
 
-static int g_conv_vec_store = -2;         // one-wave grids store straight from registers (default 0: measured 416.6 vs 421.6 frames/s)
-static int conv_vec_store_mode() {
-  if (g_conv_vec_store == -2) { const char* e = getenv("OTVM_CONV_VEC_STORE"); g_conv_vec_store = e ? atoi(e) : 0; }
-  return g_conv_vec_store;
-}
 static int g_conv_ksub = -2;              // K-chunks per barrier pair on one-wave grids: 2 (default) or 1
 static int conv_ksub_mode() {
   if (g_conv_ksub == -2) { const char* e = getenv("OTVM_CONV_KSUB"); g_conv_ksub = e ? atoi(e) : 2; }
@@ -994,7 +1051,8 @@ static int conv_tc_epi(const otvm_conv_params* p, int bn) {
 }
 
 bool conv2d_tc_supported(const otvm_conv_params* p) {
-  if (p->dtype != OTVM_BF16 || p->stride > 2 || p->relu_in) return false;
+  const int fmt = dtype_fmt(p->dtype);
+  if ((fmt != OTVM_BF16 && fmt != OTVM_BF16X2 && fmt != OTVM_BF16X3) || p->stride > 2 || p->relu_in) return false;
   if (p->Cin % 16 != 0 || p->in_ld % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(p->in) & 15) || (reinterpret_cast<uintptr_t>(p->weight) & 15)) return false;
   const int Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
@@ -1037,7 +1095,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     const int regs_per_warp = ((regs * 32 + 255) / 256) * 256;
     const int by_regs = 65536 / (regs_per_warp * (kConvThreads / 32));
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
-    const int tmem_cols = BN < 32 ? 32 : BN;
+    const int tmem_cols = (BN < 32 ? 32 : BN) * (a.planes > 1 ? 2 : 1);
     int occ = by_regs < by_smem ? by_regs : by_smem;
     if (occ > 512 / tmem_cols) occ = 512 / tmem_cols;
     if (occ > 2) occ = 2;
@@ -1074,7 +1132,7 @@ static int launch_conv_persist_k(int ksteps, const CUtensorMap& tmA, const CUten
 static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int bn, int epi, int gn,
                             const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t s) {
   const int mode = conv_persist_mode();
-  if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
+  if (mode == 0 || !a0.halo || a0.planes != 1 || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
   if (gn == GN_STATS && p->Cout != 64) return 0;
   if (a0.KC != 64 && a0.KC != 32) return 0;
   ConvTcArgs a = a0;
@@ -1125,7 +1183,13 @@ static int dispatch_conv_tc(int gn, int epi, const CUtensorMap& tmA, const CUten
 
 int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   ConvTcArgs a;
-  a.vec_store = 0; a.ntiles = 0; a.p_off = 0; a.stage_off = 0;
+  a.ntiles = 0; a.p_off = 0; a.stage_off = 0;
+  const int fmt = dtype_fmt(p->dtype);
+  a.planes = dtype_planes(p->dtype);
+  a.npair = a.planes == 1 ? 1 : a.planes == 2 ? 3 : 6;
+  a.act_plane = dtype_plane_stride(p->dtype);
+  if (a.planes > 1 && (a.act_plane <= 0 || p->w_plane_stride <= 0)) return OTVM_ERR_ARG;
+  (void)fmt;
   a.N = p->N; a.H = p->H; a.W = p->W; a.Cin = p->Cin; a.Cout = p->Cout; a.KH = p->KH; a.KW = p->KW;
   a.pad = p->pad; a.dil = p->dil; a.stride = p->stride;
   a.Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
@@ -1141,11 +1205,17 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   const int halo_mode = conv_halo_mode();              // -1 auto, 0 never, 1 whenever the shape allows
   a.halo = halo_mode != 0 && p->KH == 3 && p->KW == 3 && p->stride == 1 && p->dil <= 4 &&
            (halo_mode == 1 || (p->Cout <= 64 && p->Cin <= 128));
+  const int bn = pick_bn(p);
   if (a.halo) {
     a.TW = 8; a.TH = 16;
     a.patch_bytes = (((uint32_t)(a.TW + 2 * p->dil) * (a.TH + 2 * p->dil) * a.row_bytes) + 1023u) & ~1023u;
     a.na = a.nchunk > 1 ? 2 : 1;
-  } else {
+    // the patch ring (planes x na patches) + at least two weight stages must fit one CTA; else one box per tap
+    const uint32_t wstage = (uint32_t)a.planes * (((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u);
+    if ((uint32_t)a.na * a.planes * a.patch_bytes + 2 * wstage > 200u * 1024u) a.na = 1;
+    if ((uint32_t)a.na * a.planes * a.patch_bytes + 2 * wstage > 200u * 1024u) a.halo = 0;
+  }
+  if (!a.halo) {
     int tw = 8; while (tw * 2 <= a.Wo && tw < 128) tw *= 2;
     a.TW = tw; a.TH = 128 / tw;
     a.patch_bytes = 0; a.na = 0;
@@ -1154,10 +1224,11 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.tw_shift = 0; while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
   a.tiles_x_magic = magic(a.tiles_x); a.tiles_y_magic = magic(a.tiles_y);     // exact for n * d < 2^32 (n < 2^16 tiles)
-  const int bn = pick_bn(p);
-  a.a_bytes = a.halo ? 0u : 128u * a.KC * 2;
-  a.b_bytes = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
-  a.b_off = (uint32_t)a.na * a.patch_bytes;
+  a.a_plane = a.halo ? 0u : 128u * a.KC * 2;
+  a.b_plane = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
+  a.a_bytes = (uint32_t)a.planes * a.a_plane;
+  a.b_bytes = (uint32_t)a.planes * a.b_plane;
+  a.b_off = (uint32_t)a.na * (uint32_t)a.planes * a.patch_bytes;
   a.sbo = 8u * a.KC * 2;
   a.layout_type = a.KC == 64 ? 2u : a.KC == 32 ? 4u : 6u;
   const uint32_t stage = a.a_bytes + a.b_bytes;
@@ -1167,11 +1238,14 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   const int budget_kb = g_conv_budget_kb;   // dev override of the multi-wave ring budget (KB)
   // multi-wave grids: narrow tiles (BN <= 64) have short K loops and are bound by per-CTA latency, so they trade ring
   // depth for residency (4+ CTAs per SM); patch mode keeps 3 weight stages behind the patch ring
-  uint32_t budget = ctas <= sm_count() ? 190u * 1024u
+  // split operands: a stage is `planes` times larger, so the ring always takes one CTA's worth of shared memory (ring()
+  // clamps it to the K iterations: short-K layers stay small and still co-reside)
+  uint32_t budget = ctas <= sm_count() ? (a.planes > 1 ? 200u * 1024u : 190u * 1024u)
                   : budget_kb > 0 ? (uint32_t)budget_kb * 1024u
                   : a.halo ? a.b_off + 3 * a.b_bytes
+                  : a.planes > 1 ? 200u * 1024u
                   : bn <= 64 ? 48u * 1024u : 96u * 1024u;
-  if (a.halo && a.b_off + 3 * a.b_bytes > budget) budget = 190u * 1024u;
+  if (a.halo && a.b_off + 3 * a.b_bytes > budget) budget = 200u * 1024u;
   const int num_k = a.KH * a.KW * a.nchunk;
   // K-chunk groups: a one-wave grid is paced by the per-stage round trip of its single-thread loops (wait, elect,
   // issue, commit: ~420 cycles per 128x128x64 stage against 256 cycles of tensor work, scripts/conv_ts3.py), so there
@@ -1187,7 +1261,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     if (n < 2) n = 2;
     return n;
   };
-  int ksub = (!a.halo && ctas <= sm_count() && num_k >= 8 && conv_ksub_mode() >= 2) ? 2 : 1;
+  int ksub = (!a.halo && a.planes == 1 && ctas <= sm_count() && num_k >= 8 && conv_ksub_mode() >= 2) ? 2 : 1;
   // split-K: a grid that fills less than half of the SMs walks K serially at TMA/L2 latency; slice K across
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
   int nsplit = 1;
@@ -1229,21 +1303,24 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
                                : a.KC == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
   CUtensorMap tmA, tmB;
   {
-    uint64_t dims[4] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N};
-    uint64_t str[3] = {(uint64_t)p->in_ld * 2, (uint64_t)p->W * p->in_ld * 2, (uint64_t)p->H * p->W * p->in_ld * 2};
+    // (the plane of a split tensor is the outermost dimension; one plane: a dimension of extent 1)
+    const uint64_t img_bytes = (uint64_t)p->N * p->H * p->W * p->in_ld * 2;
+    uint64_t dims[5] = {(uint64_t)p->Cin, (uint64_t)p->W, (uint64_t)p->H, (uint64_t)p->N, (uint64_t)a.planes};
+    uint64_t str[4] = {(uint64_t)p->in_ld * 2, (uint64_t)p->W * p->in_ld * 2, (uint64_t)p->H * p->W * p->in_ld * 2,
+                       a.planes > 1 ? (uint64_t)a.act_plane * 2 : img_bytes};
     // stride-2 convolutions: TMA traversal stride 2 along W and H (a box of 2*TW x 2*TH input pixels yields TW x TH)
-    uint32_t box[4] = {(uint32_t)a.KC, (uint32_t)(a.TW * p->stride), (uint32_t)(a.TH * p->stride), 1};
+    uint32_t box[5] = {(uint32_t)a.KC, (uint32_t)(a.TW * p->stride), (uint32_t)(a.TH * p->stride), 1, 1};
     if (a.halo) { box[1] = (uint32_t)(a.TW + 2 * p->dil); box[2] = (uint32_t)(a.TH + 2 * p->dil); }
-    uint32_t es[4] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1};
-    int rc = make_tmap_bf16(&tmA, p->in, 4, dims, str, box, swz, es);
+    uint32_t es[5] = {1, (uint32_t)p->stride, (uint32_t)p->stride, 1, 1};
+    int rc = make_tmap_bf16(&tmA, p->in, 5, dims, str, box, swz, es);
     if (rc) return rc;
   }
   {
     const uint64_t K = (uint64_t)p->KH * p->KW * p->Cin;
-    uint64_t dims[2] = {K, (uint64_t)p->Cout};
-    uint64_t str[1] = {K * 2};
-    uint32_t box[2] = {(uint32_t)a.KC, (uint32_t)bn};
-    int rc = make_tmap_bf16(&tmB, p->weight, 2, dims, str, box, swz);
+    uint64_t dims[3] = {K, (uint64_t)p->Cout, (uint64_t)a.planes};
+    uint64_t str[2] = {K * 2, a.planes > 1 ? (uint64_t)p->w_plane_stride * 2 : K * 2 * (uint64_t)p->Cout};
+    uint32_t box[3] = {(uint32_t)a.KC, (uint32_t)bn, 1};
+    int rc = make_tmap_bf16(&tmB, p->weight, 3, dims, str, box, swz);
     if (rc) return rc;
   }
   // epilogue through shared memory + TMA tensor store when the destination is a 16-byte aligned bf16 NHWC view
@@ -1253,15 +1330,17 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   if (tma_store) {
     const CUtensorMapSwizzle oswz = boxc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : boxc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    uint64_t dims[4] = {(uint64_t)p->Cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)p->N};
-    uint32_t box[4] = {(uint32_t)boxc, (uint32_t)a.TW, (uint32_t)a.TH, 1};
-    uint64_t str[3] = {(uint64_t)p->out_ps * 2, (uint64_t)a.Wo * p->out_ps * 2, (uint64_t)a.Ho * a.Wo * p->out_ps * 2};
-    int rc = make_tmap_bf16(&tmO, p->out, 4, dims, str, box, oswz);
+    uint64_t dims[5] = {(uint64_t)p->Cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)p->N, (uint64_t)a.planes};
+    uint32_t box[5] = {(uint32_t)boxc, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
+    uint64_t str[4] = {(uint64_t)p->out_ps * 2, (uint64_t)a.Wo * p->out_ps * 2, (uint64_t)a.Ho * a.Wo * p->out_ps * 2,
+                       a.planes > 1 ? (uint64_t)a.act_plane * 2 : (uint64_t)p->N * a.Ho * a.Wo * p->out_ps * 2};
+    int rc = make_tmap_bf16(&tmO, p->out, 5, dims, str, box, oswz);
     if (rc) return rc;
     if (p->out_relu) {
-      uint64_t str2[3] = {(uint64_t)p->out_relu_ld * 2, (uint64_t)a.Wo * p->out_relu_ld * 2,
-                          (uint64_t)a.Ho * a.Wo * p->out_relu_ld * 2};
-      rc = make_tmap_bf16(&tmR, p->out_relu, 4, dims, str2, box, oswz);
+      uint64_t str2[4] = {(uint64_t)p->out_relu_ld * 2, (uint64_t)a.Wo * p->out_relu_ld * 2,
+                          (uint64_t)a.Ho * a.Wo * p->out_relu_ld * 2,
+                          a.planes > 1 ? (uint64_t)a.act_plane * 2 : (uint64_t)p->N * a.Ho * a.Wo * p->out_relu_ld * 2};
+      rc = make_tmap_bf16(&tmR, p->out_relu, 5, dims, str2, box, oswz);
       if (rc) return rc;
     }
   }
@@ -1283,15 +1362,18 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     if (rc) return rc;
     const int64_t total = Mtot * (p->Cout / 4);
     int g = (int)((total + 255) / 256); if (g > sm_count() * 8) g = sm_count() * 8;
-    launch_k(splitk_finish_kernel, g, 256, 0, s, static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout, p->bias,
-                                           static_cast<const bf16*>(p->res), p->res_ld, p->act, p->out, p->out_ps,
-                                           p->out_cs, p->out_f32, static_cast<bf16*>(p->out_relu), p->out_relu_ld,
-                                           p->gn_stats);
+    const int64_t ps = a.act_plane;
+#define OTVM_FINISH(T)                                                                                              \
+    launch_k(splitk_finish_kernel<T>, g, 256, 0, s, static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout,  \
+             p->bias, mkcptr<T>(p->res, ps), p->res_ld, p->act, p->out, p->out_ps, p->out_cs, p->out_f32,            \
+             mkptr<T>(p->out_relu, ps), p->out_relu_ld, p->gn_stats, ps)
+    if (a.planes == 1) OTVM_FINISH(bf16); else if (a.planes == 2) OTVM_FINISH(bx<2>); else OTVM_FINISH(bx<3>);
+#undef OTVM_FINISH
     OTVM_LAUNCH_CHECK();
     return OTVM_OK;
   }
   size_t pipe = (size_t)a.b_off + (size_t)a.nstage * ksub * stage;
-  const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1);
+  const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1) * a.planes;
   size_t need = tma_store ? staging : 0;
   if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
@@ -1299,7 +1381,6 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.aux_off = (uint32_t)pipe;
   const int gn = fuse_gn ? GN_FUSED : p->gn_stats != nullptr ? GN_STATS : GN_NONE;
   const int epi = conv_tc_epi(p, bn);
-  a.vec_store = tma_store && ctas <= sm_count() && conv_vec_store_mode() != 0;
   if (fuse_gn) {
     const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
     const int64_t resident = (int64_t)sm_count() * (per_sm > 2 ? 2 : per_sm);

@@ -57,7 +57,7 @@ template <typename T>
 __global__ void dilate_cols_onehot_kernel(const uint8_t* __restrict__ rows, const float* __restrict__ a, int H, int W,
                                           int Hp, int Wp, int pad_top, int pad_left, int r,
                                           float* __restrict__ img, float* __restrict__ tri3, MeanStd ms,
-                                          T* __restrict__ imgn, int64_t imgn_ld) {
+                                          ptr_t<T> imgn, int64_t imgn_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)Hp * Wp;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
@@ -215,7 +215,7 @@ __global__ void trimap_classes_kernel(const float* __restrict__ tri, int64_t tri
 
 template <typename T>
 __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* __restrict__ d2, int64_t P,
-                                   MeanStd ms, T* __restrict__ x11, int64_t x11_ld, T* __restrict__ cat_dst,
+                                   MeanStd ms, ptr_t<T> x11, int64_t x11_ld, ptr_t<T> cat_dst,
                                    int64_t cat_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   // trimap_transform, utils/utils.py:25-39: exp(-d^2 / (2 (sigma L)^2)), sigma in {.02,.08,.16}, L = 320
@@ -241,12 +241,12 @@ __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* 
     v[9] = e[3]; v[10] = e[4];                        // soft bg, soft fg (:51)
 #pragma unroll
     for (int c = 11; c < 16; ++c) v[c] = 0.f;
-    T* o = x11 + p * x11_ld;
+    ptr_t<T> o = x11 + p * x11_ld;
 #pragma unroll
     for (int c = 0; c < 16; c += 4) { float q4[4] = {v[c], v[c + 1], v[c + 2], v[c + 3]}; store4(o + c, q4); }
     if (cat_dst) {                                    // cat(.., conv_out[-6][:, :3], img, two_chan_trimap) (:377-378)
       float q0[4] = {v[0], v[1], v[2], e[0]}, q1[4] = {e[1], e[2], e[3], e[4]};
-      store4(cat_dst + p * cat_ld, q0); store4(cat_dst + p * cat_ld + 4, q1);
+      store4(cat_dst + p * cat_ld, q0); store4(cat_dst + (p * cat_ld + 4), q1);
     }
   }
 }
@@ -255,17 +255,17 @@ __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* 
 // clamp / sigmoid / fba_fusion (FBA/models.py:279-288)
 // ---------------------------------------------------------------------------------------------------
 template <typename TR, typename TA>
-__global__ void fba_head_kernel(const TR* __restrict__ raw, int64_t raw_ld, const float* __restrict__ extras,
-                                int64_t P, float* __restrict__ out7, TA* __restrict__ alpha_dst, int64_t alpha_ld) {
+__global__ void fba_head_kernel(cptr_t<TR> raw, int64_t raw_ld, const float* __restrict__ extras,
+                                int64_t P, float* __restrict__ out7, ptr_t<TA> alpha_dst, int64_t alpha_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
-    const TR* r = raw + p * raw_ld;
-    float al = fminf(fmaxf(to_f(r[0]), 0.f), 1.f);
+    cptr_t<TR> r = raw + p * raw_ld;
+    float al = fminf(fmaxf(ld1(r, 0), 0.f), 1.f);
     float F[3], B[3], img[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      F[c] = 1.f / (1.f + expf(-to_f(r[1 + c])));
-      B[c] = 1.f / (1.f + expf(-to_f(r[4 + c])));
+      F[c] = 1.f / (1.f + expf(-ld1(r, 1 + c)));
+      B[c] = 1.f / (1.f + expf(-ld1(r, 4 + c)));
       img[c] = extras[p * 8 + c];
     }
     float num = 0.f, den = 0.f, Fo[3], Bo[3];
@@ -284,7 +284,7 @@ __global__ void fba_head_kernel(const TR* __restrict__ raw, int64_t raw_ld, cons
     float* o = out7 + p * 8;
     *reinterpret_cast<float4*>(o) = make_float4(a2, Fo[0], Fo[1], Fo[2]);
     *reinterpret_cast<float4*>(o + 4) = make_float4(Bo[0], Bo[1], Bo[2], 0.f);
-    if (alpha_dst) alpha_dst[p * alpha_ld] = from_f<TA>(a2);
+    if (alpha_dst) st1(alpha_dst, p * alpha_ld, a2);
   }
 }
 
@@ -293,9 +293,9 @@ __global__ void fba_head_kernel(const TR* __restrict__ raw, int64_t raw_ld, cons
 // ---------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t raw_ld, const float* __restrict__ fused,
-                                     const T* __restrict__ hid, int64_t hid_ld, const float* __restrict__ extras,
+                                     cptr_t<T> hid, int64_t hid_ld, const float* __restrict__ extras,
                                      int Hp, int Wp, int H, int W, int pad_top, int pad_left, MeanStd ms,
-                                     T* __restrict__ mem_in, int64_t mem_ld, float* __restrict__ alpha_out,
+                                     ptr_t<T> mem_in, int64_t mem_ld, float* __restrict__ alpha_out,
                                      float* __restrict__ trimap_out) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t P = (int64_t)Hp * Wp, Pc = (int64_t)H * W;
@@ -309,20 +309,20 @@ __global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t ra
     const float al = fused[p * 8];
     if (mem_in) {
       // Encoder_M input order (STM.py:56-67): frame(3, normalised), unknown, fg, alpha, hid(16)
-      T* o = mem_in + p * mem_ld;
+      ptr_t<T> o = mem_in + p * mem_ld;
       float v[8];
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[c] = (extras[p * 8 + c] - ms.mean[c]) / ms.std[c];
       v[3] = t1; v[4] = t2; v[5] = al;
-      const T* h = hid + p * hid_ld;
-      v[6] = to_f(h[0]); v[7] = to_f(h[1]);
+      cptr_t<T> h = hid + p * hid_ld;
+      v[6] = ld1(h, 0); v[7] = ld1(h, 1);
       { float q[4] = {v[0], v[1], v[2], v[3]}; store4(o, q); }
       { float q[4] = {v[4], v[5], v[6], v[7]}; store4(o + 4, q); }
       for (int c = 2; c < 14; c += 4) {
-        float q[4] = {to_f(h[c]), to_f(h[c + 1]), to_f(h[c + 2]), to_f(h[c + 3])};
+        float q[4] = {ld1(h, c), ld1(h, c + 1), ld1(h, c + 2), ld1(h, c + 3)};
         store4(o + 6 + c, q);
       }
-      { float q[4] = {to_f(h[14]), to_f(h[15]), 0.f, 0.f}; store4(o + 20, q); }
+      { float q[4] = {ld1(h, 14), ld1(h, 15), 0.f, 0.f}; store4(o + 20, q); }
     }
     int yp = (int)(p / Wp), xp = (int)(p - (int64_t)yp * Wp);
     int y = yp - pad_top, x = xp - pad_left;
@@ -337,6 +337,18 @@ __global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t ra
 }  // namespace otvm
 
 using namespace otvm;
+
+#define DISPATCH_DTYPE(dtype, STMT)                                            \
+  do {                                                                         \
+    const int64_t ps = dtype_plane_stride(dtype); (void)ps;                    \
+    switch (dtype_fmt(dtype)) {                                                \
+      case OTVM_F32: { typedef float T; STMT; break; }                         \
+      case OTVM_BF16: { typedef bf16 T; STMT; break; }                         \
+      case OTVM_BF16X2: { typedef bx<2> T; STMT; break; }                      \
+      case OTVM_BF16X3: { typedef bx<3> T; STMT; break; }                      \
+      default: return OTVM_ERR_ARG;                                            \
+    }                                                                          \
+  } while (0)
 
 static MeanStd make_ms(const float* mean_std) {
   MeanStd ms;
@@ -358,13 +370,8 @@ extern "C" int otvm_preprocess(const float* a, const float* fg, const float* bg,
   OTVM_LAUNCH_CHECK();
   launch_k(dilate_rows_kernel, grid1d(P, 256), 256, 0, s, unk, H, W, radius, rows);
   OTVM_LAUNCH_CHECK();
-  if (dtype == OTVM_F32)
-    launch_k(dilate_cols_onehot_kernel<float>, grid1d((int64_t)Hp * Wp, 256), 256, 0, s, 
-        rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<float*>(imgn), imgn_ld);
-  else if (dtype == OTVM_BF16)
-    launch_k(dilate_cols_onehot_kernel<bf16>, grid1d((int64_t)Hp * Wp, 256), 256, 0, s, 
-        rows, a, H, W, Hp, Wp, pad_top, pad_left, radius, img, tri3, ms, static_cast<bf16*>(imgn), imgn_ld);
-  else return OTVM_ERR_ARG;
+  DISPATCH_DTYPE(dtype, launch_k(dilate_cols_onehot_kernel<T>, grid1d((int64_t)Hp * Wp, 256), 256, 0, s, rows, a, H, W, Hp, Wp,
+                                 pad_top, pad_left, radius, img, tri3, ms, mkptr<T>(imgn, ps), imgn_ld));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -389,13 +396,8 @@ extern "C" int otvm_trimap_encode(const float* tri_in, int64_t tri_ld, int32_t i
   int rc = edt_launch(seeds, Hp, Wp, 2, d2, scratch, s);
   if (rc) return rc;
   MeanStd ms = make_ms(mean_std);
-  if (dtype == OTVM_F32)
-    launch_k(trimap_pack_kernel<float>, grid1d(P, 256), 256, 0, s, extras, d2, P, ms, static_cast<float*>(x11), x11_ld,
-                                                             static_cast<float*>(cat_dst), cat_ld);
-  else if (dtype == OTVM_BF16)
-    launch_k(trimap_pack_kernel<bf16>, grid1d(P, 256), 256, 0, s, extras, d2, P, ms, static_cast<bf16*>(x11), x11_ld,
-                                                            static_cast<bf16*>(cat_dst), cat_ld);
-  else return OTVM_ERR_ARG;
+  DISPATCH_DTYPE(dtype, launch_k(trimap_pack_kernel<T>, grid1d(P, 256), 256, 0, s, extras, d2, P, ms, mkptr<T>(x11, ps), x11_ld,
+                                 mkptr<T>(cat_dst, ps), cat_ld));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -405,14 +407,12 @@ extern "C" int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int
   if (!raw || !extras || !out7) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int g = grid1d(P, 256);
-  const bool rf = raw_f32 || dtype == OTVM_F32;
-  if (dtype == OTVM_F32)
-    launch_k(fba_head_kernel<float, float>, g, 256, 0, s, (const float*)raw, raw_ld, extras, P, out7, (float*)alpha_dst, alpha_ld);
-  else if (dtype == OTVM_BF16 && rf)
-    launch_k(fba_head_kernel<float, bf16>, g, 256, 0, s, (const float*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
-  else if (dtype == OTVM_BF16)
-    launch_k(fba_head_kernel<bf16, bf16>, g, 256, 0, s, (const bf16*)raw, raw_ld, extras, P, out7, (bf16*)alpha_dst, alpha_ld);
-  else return OTVM_ERR_ARG;
+  if (raw_f32 || dtype_fmt(dtype) == OTVM_F32)
+    DISPATCH_DTYPE(dtype, (launch_k(fba_head_kernel<float, T>, g, 256, 0, s, (const float*)raw, raw_ld, extras, P, out7,
+                                    mkptr<T>(alpha_dst, ps), alpha_ld)));
+  else
+    DISPATCH_DTYPE(dtype, (launch_k(fba_head_kernel<T, T>, g, 256, 0, s, mkcptr<T>(raw, ps), raw_ld, extras, P, out7,
+                                    mkptr<T>(alpha_dst, ps), alpha_ld)));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -426,13 +426,8 @@ extern "C" int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const floa
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   MeanStd ms = make_ms(mean_std);
   int g = grid1d((int64_t)Hp * Wp, 256);
-  if (dtype == OTVM_F32)
-    launch_k(frame_outputs_kernel<float>, g, 256, 0, s, raw10, raw_ld, fused, (const float*)hid, hid_ld, extras, Hp, Wp, H, W,
-                                                  pad_top, pad_left, ms, (float*)mem_in, mem_ld, alpha_out, trimap_out);
-  else if (dtype == OTVM_BF16)
-    launch_k(frame_outputs_kernel<bf16>, g, 256, 0, s, raw10, raw_ld, fused, (const bf16*)hid, hid_ld, extras, Hp, Wp, H, W,
-                                                 pad_top, pad_left, ms, (bf16*)mem_in, mem_ld, alpha_out, trimap_out);
-  else return OTVM_ERR_ARG;
+  DISPATCH_DTYPE(dtype, launch_k(frame_outputs_kernel<T>, g, 256, 0, s, raw10, raw_ld, fused, mkcptr<T>(hid, ps), hid_ld, extras,
+                                 Hp, Wp, H, W, pad_top, pad_left, ms, mkptr<T>(mem_in, ps), mem_ld, alpha_out, trimap_out));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }

@@ -26,6 +26,7 @@ struct ReadArgs {
   int nsplit, blocks_per_split;
   float scale_log2;
   float* o_part; float* ml_part;
+  int64_t ps;                  // split formats: plane stride (elements)
 };
 
 template <typename T>
@@ -39,15 +40,15 @@ __global__ void __launch_bounds__(256) memory_read_simt_kernel(const ReadArgs a)
 
   const int t = threadIdx.x, ty = t >> 4, tx = t & 15;
   const int q0 = blockIdx.x * RQ, c0 = blockIdx.y * RDV, split = blockIdx.z;
-  const T* __restrict__ keys = static_cast<const T*>(a.keys);
-  const T* __restrict__ vals = static_cast<const T*>(a.vals);
-  const T* __restrict__ query = static_cast<const T*>(a.query);
+  const cptr_t<T> keys = mkcptr<T>(a.keys, a.ps);
+  const cptr_t<T> vals = mkcptr<T>(a.vals, a.ps);
+  const cptr_t<T> query = mkcptr<T>(a.query, a.ps);
 
   // Q tile (zero rows beyond HW)
   for (int v = t; v < RQ * (RDE / 4); v += 256) {
     int r = v / (RDE / 4), k = (v % (RDE / 4)) * 4;
     float q[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q0 + r < a.HW) load4(query + (int64_t)(q0 + r) * a.q_ld + k, q);
+    if (q0 + r < a.HW) load4(query + ((int64_t)(q0 + r) * a.q_ld + k), q);
     *reinterpret_cast<float4*>(&Qs[r * QP + k]) = make_float4(q[0], q[1], q[2], q[3]);
   }
 
@@ -70,17 +71,17 @@ __global__ void __launch_bounds__(256) memory_read_simt_kernel(const ReadArgs a)
     for (int v = t; v < RK * (RDE / 4); v += 256) {
       int r = v / (RDE / 4), k = (v % (RDE / 4)) * 4;
       float q[4] = {0.f, 0.f, 0.f, 0.f};
-      if (key0 + r < a.M) load4(keys + (int64_t)(key0 + r) * RDE + k, q);
+      if (key0 + r < a.M) load4(keys + ((int64_t)(key0 + r) * RDE + k), q);
       *reinterpret_cast<float4*>(&Ks[r * QP + k]) = make_float4(q[0], q[1], q[2], q[3]);
     }
     for (int v = t; v < RDV * (RK / 4); v += 256) {
       int c = v / (RK / 4), j = (v % (RK / 4)) * 4;
       float q[4] = {0.f, 0.f, 0.f, 0.f};
-      const T* src = vals + (int64_t)(c0 + c) * a.ldv + key0 + j;
+      const cptr_t<T> src = vals + ((int64_t)(c0 + c) * a.ldv + key0 + j);
       if (vec_v && key0 + j + 3 < a.M) load4(src, q);
       else {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) if (key0 + j + e < a.M) q[e] = to_f(src[e]);
+        for (int e = 0; e < 4; ++e) if (key0 + j + e < a.M) q[e] = ld1(src, e);
       }
       *reinterpret_cast<float4*>(&Vs[c * PP + j]) = make_float4(q[0], q[1], q[2], q[3]);
     }
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256) memory_read_simt_kernel(const ReadArgs a)
 template <typename T>
 __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* __restrict__ o_part,
                                                                   const float* __restrict__ ml_part, int nsplit,
-                                                                  int HW, int Do, T* __restrict__ out, int64_t out_ld) {
+                                                                  int HW, int Do, ptr_t<T> out, int64_t out_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = Do >> 2;
   const int64_t total = (int64_t)HW * c4n;
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* _
     const float inv = 1.f / l;
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] *= inv;
-    store4(out + (int64_t)q * out_ld + c, acc);
+    store4(out + ((int64_t)q * out_ld + c), acc);
   }
 }
 
@@ -223,12 +224,16 @@ int read_combine(const otvm_read_params* p, int nsplit, cudaStream_t s) {
   float* ml_part = o_part + (int64_t)nsplit * p->HW * p->Do;
   int64_t total = (int64_t)p->HW * (p->Do / 4);
   int g = ceil_div(total, 256);
-  if (p->dtype == OTVM_F32)
-    launch_k(memory_read_combine_kernel<float>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do,
-                                                        static_cast<float*>(p->out), p->out_ld);
-  else
-    launch_k(memory_read_combine_kernel<bf16>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do,
-                                                       static_cast<bf16*>(p->out), p->out_ld);
+  const int64_t ps = dtype_plane_stride(p->dtype);
+  switch (dtype_fmt(p->dtype)) {
+#define OTVM_COMBINE(T) launch_k(memory_read_combine_kernel<T>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do, mkptr<T>(p->out, ps), p->out_ld)
+    case OTVM_F32: OTVM_COMBINE(float); break;
+    case OTVM_BF16: OTVM_COMBINE(bf16); break;
+    case OTVM_BF16X2: OTVM_COMBINE(bx<2>); break;
+    case OTVM_BF16X3: OTVM_COMBINE(bx<3>); break;
+#undef OTVM_COMBINE
+    default: return OTVM_ERR_ARG;
+  }
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -243,11 +248,14 @@ static int read_simt_t(const otvm_read_params* p, cudaStream_t s) {
   a.scale_log2 = (float)(1.4426950408889634 / sqrt((double)p->De));
   a.o_part = static_cast<float*>(p->workspace);
   a.ml_part = a.o_part + (int64_t)a.nsplit * p->HW * p->Do;
+  a.ps = dtype_plane_stride(p->dtype);
   size_t smem = sizeof(float) * (RQ * QP + RK * QP + RQ * PP + RDV * PP);
   static bool attr_set = false;
   if (!attr_set) {
     OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bx<2>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bx<3>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   dim3 grid(ceil_div(p->HW, RQ), p->Do / RDV, a.nsplit);
@@ -258,9 +266,13 @@ static int read_simt_t(const otvm_read_params* p, cudaStream_t s) {
 
 int memory_read_simt(const otvm_read_params* p, cudaStream_t s) {
   if (p->De != RDE || p->Do % RDV != 0 || p->q_ld % 4 != 0 || p->out_ld % 4 != 0) return OTVM_ERR_UNSUPPORTED;
-  if (p->dtype == OTVM_F32) return read_simt_t<float>(p, s);
-  if (p->dtype == OTVM_BF16) return read_simt_t<bf16>(p, s);
-  return OTVM_ERR_ARG;
+  switch (dtype_fmt(p->dtype)) {
+    case OTVM_F32: return read_simt_t<float>(p, s);
+    case OTVM_BF16: return read_simt_t<bf16>(p, s);
+    case OTVM_BF16X2: return read_simt_t<bx<2>>(p, s);
+    case OTVM_BF16X3: return read_simt_t<bx<3>>(p, s);
+    default: return OTVM_ERR_ARG;
+  }
 }
 
 }  // namespace otvm

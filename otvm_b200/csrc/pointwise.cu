@@ -5,6 +5,8 @@
 
 namespace otvm {
 
+static inline int launched() { OTVM_LAUNCH_CHECK(); return OTVM_OK; }
+
 static inline int grid_for(int64_t work_items, int block) {
   int64_t need = (work_items + block - 1) / block;
   int64_t cap = (int64_t)sm_count() * 8;
@@ -33,11 +35,37 @@ __device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
   *reinterpret_cast<uint4*>(p) = t;
 }
 
+template <int P> __device__ __forceinline__ void load8(BxPtr<P> q, float (&v)[8]) {
+  load8(q.p, v);
+#pragma unroll
+  for (int k = 1; k < P; ++k) {
+    float t[8];
+    load8(q.p + k * q.ps, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+}
+template <int P> __device__ __forceinline__ void store8(BxPtr<P> q, const float (&v)[8]) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+      r[2 * i] -= __low2float(h[i]); r[2 * i + 1] -= __high2float(h[i]);
+    }
+    *reinterpret_cast<uint4*>(q.p + k * q.ps) = t;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (n, group) sum and sum of squares in fp64 (fp32 partials per thread/block).
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
+__global__ void __launch_bounds__(256) gn_stats_kernel(cptr_t<T> x, int64_t ld, int64_t HW, int C,
                                                        double* __restrict__ stats) {
   pdl_sync();                                  // PDL contract (common.cuh)
   __shared__ float part[32][2];
@@ -51,7 +79,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
   if (threadIdx.x < 32) { part[threadIdx.x][0] = 0.f; part[threadIdx.x][1] = 0.f; }
   __syncthreads();
   float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-  const T* base = x + (int64_t)n * HW * ld + cq * 4;
+  cptr_t<T> base = x + ((int64_t)n * HW * ld + cq * 4);
   for (; idx < total; idx += nthreads) {
     int64_t pix = idx / c4n;
     float v[4];
@@ -72,12 +100,12 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
 // GroupNorm apply: every thread owns 8 fixed channels (scale/shift live in registers) and walks the pixels with
 // 16-byte accesses, 4 pixels in flight per thread; a warp touches 512 contiguous bytes of one or more pixels.
 template <typename T, bool RES>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, int64_t ld, int64_t HW, int C,
+__global__ void __launch_bounds__(256) gn_apply_kernel(cptr_t<T> x, int64_t ld, int64_t HW, int C,
                                                        const double* __restrict__ stats,
                                                        const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, float eps,
-                                                       const T* __restrict__ res, int64_t res_ld, int act,
-                                                       T* __restrict__ out, int64_t out_ld, double inv_cnt) {
+                                                       cptr_t<T> res, int64_t res_ld, int act,
+                                                       ptr_t<T> out, int64_t out_ld, double inv_cnt) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int n = blockIdx.y;
   const int tpp = C >> 3;                         // threads per pixel (divides 256)
@@ -102,9 +130,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
     sh[j] = beta[cv + j] - g_mean[g] * sc[j];
   }
   const float slope = act == OTVM_ACT_NONE ? 1.f : act == OTVM_ACT_RELU ? 0.f : 0.01f;
-  const T* xb = x + (int64_t)n * HW * ld + cv;
-  const T* rb = RES ? res + (int64_t)n * HW * res_ld + cv : nullptr;
-  T* ob = out + (int64_t)n * HW * out_ld + cv;
+  cptr_t<T> xb = x + ((int64_t)n * HW * ld + cv);
+  cptr_t<T> rb = res + (RES ? (int64_t)n * HW * res_ld + cv : 0);
+  ptr_t<T> ob = out + ((int64_t)n * HW * out_ld + cv);
   const int64_t stride = (int64_t)gridDim.x * ppb;
   for (int64_t p0 = (int64_t)blockIdx.x * ppb + threadIdx.x / tpp; p0 < HW; p0 += 4 * stride) {
     float v[4][8], r[4][8];
@@ -130,7 +158,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 }
 
 template <typename T>
-static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* stats, cudaStream_t s) {
+static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* stats, int64_t ps, cudaStream_t s) {
   OTVM_CUDA_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * N, s));
   int c4n = C / 4;
   int64_t total = (int64_t)HW * c4n;
@@ -139,7 +167,7 @@ static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* s
   int64_t want = (int64_t)sm_count() * 4 * 256;
   int64_t threads = ((total < want ? total : want) + lcm - 1) / lcm * lcm;
   dim3 grid((unsigned)(threads / 256), N);
-  launch_k(gn_stats_kernel<T>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats);
+  launch_k(gn_stats_kernel<T>, grid, 256, 0, s, mkcptr<T>(x, ps), ld, HW, C, stats);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -147,7 +175,7 @@ static int gn_stats_t(const void* x, int64_t ld, int N, int HW, int C, double* s
 template <typename T>
 static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const double* stats, const float* gamma,
                       const float* beta, float eps, const void* res, int64_t res_ld, int act, void* out,
-                      int64_t out_ld, cudaStream_t s) {
+                      int64_t out_ld, int64_t ps, cudaStream_t s) {
   const int tpp = C / 8, ppb = 256 / tpp;
   const double inv_cnt = 1.0 / ((double)HW * (double)(C / 32));      // elements per (sample, group)
   int64_t blocks = ((int64_t)HW + (int64_t)ppb * 4 - 1) / ((int64_t)ppb * 4);
@@ -156,11 +184,11 @@ static int gn_apply_t(const void* x, int64_t ld, int N, int HW, int C, const dou
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, N);
   if (res)
-    launch_k(gn_apply_kernel<T, true>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
-                                                  static_cast<const T*>(res), res_ld, act, static_cast<T*>(out), out_ld, inv_cnt);
+    launch_k(gn_apply_kernel<T, true>, grid, 256, 0, s, mkcptr<T>(x, ps), ld, HW, C, stats, gamma, beta, eps,
+                                                  mkcptr<T>(res, ps), res_ld, act, mkptr<T>(out, ps), out_ld, inv_cnt);
   else
-    launch_k(gn_apply_kernel<T, false>, grid, 256, 0, s, static_cast<const T*>(x), ld, HW, C, stats, gamma, beta, eps,
-                                                   nullptr, 0, act, static_cast<T*>(out), out_ld, inv_cnt);
+    launch_k(gn_apply_kernel<T, false>, grid, 256, 0, s, mkcptr<T>(x, ps), ld, HW, C, stats, gamma, beta, eps,
+                                                   nullptr, 0, act, mkptr<T>(out, ps), out_ld, inv_cnt);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -178,11 +206,11 @@ __device__ __forceinline__ void src_index(float scale, int dst, int in_size, int
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in, int64_t in_ld, int Hi, int Wi,
+__global__ void __launch_bounds__(256) upsample_kernel(cptr_t<T> in, int64_t in_ld, int Hi, int Wi,
                                                        int C, int Ho, int Wo, float sy, float sx,
-                                                       const T* __restrict__ add, int64_t add_ld,
-                                                       T* __restrict__ out, int64_t out_ld,
-                                                       T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+                                                       cptr_t<T> add, int64_t add_ld,
+                                                       ptr_t<T> out, int64_t out_ld,
+                                                       ptr_t<T> out_relu, int64_t out_relu_ld, int N) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * c4n;
@@ -195,7 +223,7 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
     int y0, y1, x0, x1; float ly, lx;
     src_index(sy, oy, Hi, y0, y1, ly);
     src_index(sx, ox, Wi, x0, x1, lx);
-    const T* b = in + (int64_t)n * Hi * Wi * in_ld + c;
+    cptr_t<T> b = in + ((int64_t)n * Hi * Wi * in_ld + c);
     float v00[4], v01[4], v10[4], v11[4], o[4];
     load4(b + ((int64_t)y0 * Wi + x0) * in_ld, v00);
     load4(b + ((int64_t)y0 * Wi + x1) * in_ld, v01);
@@ -206,25 +234,25 @@ __global__ void __launch_bounds__(256) upsample_kernel(const T* __restrict__ in,
     for (int j = 0; j < 4; ++j) o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
     if (add) {
       float a[4];
-      load4(add + pix * add_ld + c, a);
+      load4(add + (pix * add_ld + c), a);
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = a[j] + o[j];
     }
-    store4(out + pix * out_ld + c, o);
+    store4(out + (pix * out_ld + c), o);
     if (out_relu) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
-      store4(out_relu + pix * out_relu_ld + c, o);
+      store4(out_relu + (pix * out_relu_ld + c), o);
     }
   }
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) upsample8_kernel(const T* __restrict__ in, int64_t in_ld, int Hi, int Wi,
+__global__ void __launch_bounds__(256) upsample8_kernel(cptr_t<T> in, int64_t in_ld, int Hi, int Wi,
                                                         int C, int Ho, int Wo, float sy, float sx,
-                                                        const T* __restrict__ add, int64_t add_ld,
-                                                        T* __restrict__ out, int64_t out_ld,
-                                                        T* __restrict__ out_relu, int64_t out_relu_ld, int N) {
+                                                        cptr_t<T> add, int64_t add_ld,
+                                                        ptr_t<T> out, int64_t out_ld,
+                                                        ptr_t<T> out_relu, int64_t out_relu_ld, int N) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int c8n = C >> 3;
   const int64_t total = (int64_t)N * Ho * Wo * c8n;
@@ -237,31 +265,31 @@ __global__ void __launch_bounds__(256) upsample8_kernel(const T* __restrict__ in
     int y0, y1, x0, x1; float ly, lx;
     src_index(sy, oy, Hi, y0, y1, ly);
     src_index(sx, ox, Wi, x0, x1, lx);
-    const T* b = in + (int64_t)n * Hi * Wi * in_ld + c;
+    cptr_t<T> b = in + ((int64_t)n * Hi * Wi * in_ld + c);
     float v00[8], v01[8], v10[8], v11[8], o[8], a8[8];
     load8(b + ((int64_t)y0 * Wi + x0) * in_ld, v00);
     load8(b + ((int64_t)y0 * Wi + x1) * in_ld, v01);
     load8(b + ((int64_t)y1 * Wi + x0) * in_ld, v10);
     load8(b + ((int64_t)y1 * Wi + x1) * in_ld, v11);
-    if (add) load8(add + pix * add_ld + c, a8);
+    if (add) load8(add + (pix * add_ld + c), a8);
     const float hy = 1.f - ly, hx = 1.f - lx;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       o[j] = hy * (hx * v00[j] + lx * v01[j]) + ly * (hx * v10[j] + lx * v11[j]);
       if (add) o[j] = a8[j] + o[j];
     }
-    store8(out + pix * out_ld + c, o);
+    store8(out + (pix * out_ld + c), o);
     if (out_relu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
-      store8(out_relu + pix * out_relu_ld + c, o);
+      store8(out_relu + (pix * out_relu_ld + c), o);
     }
   }
 }
 
 // scalar-channel variant writing fp32 (NHWC with out_ld, or NCHW planes): the 3-channel STM logits (STM.py:136)
 template <typename T>
-__global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restrict__ in, int64_t in_ld, int Hi,
+__global__ void __launch_bounds__(256) upsample_scalar_kernel(cptr_t<T> in, int64_t in_ld, int Hi,
                                                               int Wi, int C, int Ho, int Wo, float sy, float sx,
                                                               float* __restrict__ out, int64_t out_ld, int nchw) {
   pdl_sync();                                  // PDL contract (common.cuh)
@@ -274,8 +302,8 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restric
     src_index(sx, ox, Wi, x0, x1, lx);
     const float hy = 1.f - ly, hx = 1.f - lx;
     for (int c = 0; c < C; ++c) {
-      float v00 = to_f(in[((int64_t)y0 * Wi + x0) * in_ld + c]), v01 = to_f(in[((int64_t)y0 * Wi + x1) * in_ld + c]);
-      float v10 = to_f(in[((int64_t)y1 * Wi + x0) * in_ld + c]), v11 = to_f(in[((int64_t)y1 * Wi + x1) * in_ld + c]);
+      float v00 = ld1(in, ((int64_t)y0 * Wi + x0) * in_ld + c), v01 = ld1(in, ((int64_t)y0 * Wi + x1) * in_ld + c);
+      float v10 = ld1(in, ((int64_t)y1 * Wi + x0) * in_ld + c), v11 = ld1(in, ((int64_t)y1 * Wi + x1) * in_ld + c);
       float o = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
       if (nchw) out[(int64_t)c * total + pix] = o; else out[pix * out_ld + c] = o;
     }
@@ -286,8 +314,8 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(const T* __restric
 // MaxPool2d(3, 2, 1)
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, int64_t in_ld, int N, int H, int W,
-                                                      int C, int Ho, int Wo, T* __restrict__ out, int64_t out_ld) {
+__global__ void __launch_bounds__(256) maxpool_kernel(cptr_t<T> in, int64_t in_ld, int N, int H, int W,
+                                                      int C, int Ho, int Wo, ptr_t<T> out, int64_t out_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = C >> 2;
   const int64_t total = (int64_t)N * Ho * Wo * c4n;
@@ -307,12 +335,12 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, 
         int ix = ox * 2 - 1 + dx;
         if (ix < 0 || ix >= W) continue;
         float v[4];
-        load4(in + ((int64_t)(n * H + iy) * W + ix) * in_ld + c, v);
+        load4(in + (((int64_t)(n * H + iy) * W + ix) * in_ld + c), v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
       }
     }
-    store4(out + pix * out_ld + c, m);
+    store4(out + (pix * out_ld + c), m);
   }
 }
 
@@ -325,7 +353,7 @@ __device__ __forceinline__ int bin_start(int b, int s, int L) { return (b * L) /
 __device__ __forceinline__ int bin_end(int b, int s, int L) { return ((b + 1) * L + s - 1) / s; }
 
 template <typename T>
-__global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in, int64_t in_ld, int H, int W, int C,
+__global__ void __launch_bounds__(128) ppm_rows_kernel(cptr_t<T> in, int64_t in_ld, int H, int W, int C,
                                                        float* __restrict__ rows) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int y = blockIdx.x, n = blockIdx.z;
@@ -336,7 +364,7 @@ __global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in,
   for (int b = 0; b < 12; ++b)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
-  const T* row = in + ((int64_t)(n * H + y) * W) * in_ld + c;
+  cptr_t<T> row = in + (((int64_t)(n * H + y) * W) * in_ld + c);
   for (int x = 0; x < W; ++x) {
     float v[4];
     load4(row + (int64_t)x * in_ld, v);
@@ -360,7 +388,7 @@ __global__ void __launch_bounds__(128) ppm_rows_kernel(const T* __restrict__ in,
 
 template <typename T>
 __global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict__ rows, int H, int W, int C,
-                                                        T* __restrict__ out) {
+                                                        ptr_t<T> out) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int cell = blockIdx.x, n = blockIdx.z;          // 0..49: scale-major, row-major inside a scale
   const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
@@ -380,14 +408,14 @@ __global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict_
   const float inv = 1.f / (float)((y1 - y0) * (bin_end(bx, s, W) - bin_start(bx, s, W)));
 #pragma unroll
   for (int j = 0; j < 4; ++j) acc[j] *= inv;
-  store4(out + ((int64_t)n * 50 + cell) * C + c, acc);
+  store4(out + (((int64_t)n * 50 + cell) * C + c), acc);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // layout conversion at the boundary
 // ------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t HW, T* __restrict__ out,
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t HW, ptr_t<T> out,
                                     int64_t out_ld, int N) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t total = (int64_t)N * HW * C;
@@ -395,18 +423,18 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, int C, int64_t
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
     int c = (int)(idx % C); int64_t pix = idx / C;             // pix = n*HW + p
     int64_t n = pix / HW, p = pix - n * HW;
-    out[pix * out_ld + c] = from_f<T>(in[(n * C + c) * HW + p]);
+    st1(out, pix * out_ld + c, in[(n * C + c) * HW + p]);
   }
 }
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t in_ld, int C, int64_t HW,
+__global__ void nhwc_to_nchw_kernel(cptr_t<T> in, int64_t in_ld, int C, int64_t HW,
                                     float* __restrict__ out, int N) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int64_t total = (int64_t)N * HW * C;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
     int64_t p = idx % HW; int64_t r = idx / HW; int c = (int)(r % C); int64_t n = r / C;
-    out[idx] = to_f(in[(n * HW + p) * in_ld + c]);
+    out[idx] = ld1(in, (n * HW + p) * in_ld + c);
   }
 }
 
@@ -414,14 +442,24 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int64_t in_ld, int
 
 using namespace otvm;
 
-#define DISPATCH_DTYPE(dtype, CALL_F32, CALL_BF16) \
-  do { if ((dtype) == OTVM_F32) return CALL_F32; if ((dtype) == OTVM_BF16) return CALL_BF16; return OTVM_ERR_ARG; } while (0)
+// CALL is an expression template in the element type T; `ps` (plane stride in elements) is in scope for mkptr
+#define DISPATCH_DTYPE(dtype, CALL)                                            \
+  do {                                                                         \
+    const int64_t ps = dtype_plane_stride(dtype); (void)ps;                    \
+    switch (dtype_fmt(dtype)) {                                                \
+      case OTVM_F32: { typedef float T; return CALL; }                         \
+      case OTVM_BF16: { typedef bf16 T; return CALL; }                         \
+      case OTVM_BF16X2: { typedef bx<2> T; return CALL; }                      \
+      case OTVM_BF16X3: { typedef bx<3> T; return CALL; }                      \
+      default: return OTVM_ERR_ARG;                                            \
+    }                                                                          \
+  } while (0)
 
 extern "C" int otvm_gn_stats(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
                              double* stats, void* stream) {
   if (!x || !stats || C % 32 != 0 || C % 4 != 0 || ld % 4 != 0) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, gn_stats_t<float>(x, ld, N, HW, C, stats, s), gn_stats_t<bf16>(x, ld, N, HW, C, stats, s));
+  DISPATCH_DTYPE(dtype, gn_stats_t<T>(x, ld, N, HW, C, stats, ps, s));
 }
 
 extern "C" int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, int32_t C, int32_t dtype,
@@ -432,21 +470,19 @@ extern "C" int otvm_gn_apply(const void* x, int64_t ld, int32_t N, int32_t HW, i
     return OTVM_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(res)) & 15) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype,
-                 gn_apply_t<float>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, s),
-                 gn_apply_t<bf16>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, s));
+  DISPATCH_DTYPE(dtype, gn_apply_t<T>(x, ld, N, HW, C, stats, gamma, beta, eps, res, res_ld, act, out, out_ld, ps, s));
 }
 
 template <typename T>
 static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int C, int Ho, int Wo,
                       const void* add, int64_t add_ld, void* out, int64_t out_ld, void* out_relu,
-                      int64_t out_relu_ld, int out_nchw_f32, cudaStream_t s) {
+                      int64_t out_relu_ld, int out_nchw_f32, int64_t ps, cudaStream_t s) {
   // ATen: scale = in/out computed in float (F.interpolate with an integer scale_factor gives the same value)
   float sy = (float)Hi / (float)Ho, sx = (float)Wi / (float)Wo;
   if (out_nchw_f32 || C % 4 != 0) {
     if (add || out_relu || N != 1) return OTVM_ERR_UNSUPPORTED;
     launch_k(upsample_scalar_kernel<T>, grid_for((int64_t)Ho * Wo, 256), 256, 0, s, 
-        static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo, sy, sx, static_cast<float*>(out), out_ld,
+        mkcptr<T>(in, ps), in_ld, Hi, Wi, C, Ho, Wo, sy, sx, static_cast<float*>(out), out_ld,
         out_nchw_f32 == 1);
   } else {
     if (in_ld % 4 || out_ld % 4 || (add && add_ld % 4) || (out_relu && out_relu_ld % 4)) return OTVM_ERR_ARG;
@@ -456,18 +492,18 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
                          reinterpret_cast<uintptr_t>(out_relu)) & 15);
     if (wide) {
       int64_t total8 = (int64_t)N * Ho * Wo * (C / 8);
-      launch_k(upsample8_kernel<T>, grid_for(total8, 256), 256, 0, s, static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
-                                                                sy, sx, static_cast<const T*>(add), add_ld,
-                                                                static_cast<T*>(out), out_ld,
-                                                                static_cast<T*>(out_relu), out_relu_ld, N);
+      launch_k(upsample8_kernel<T>, grid_for(total8, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, Hi, Wi, C, Ho, Wo,
+                                                                sy, sx, mkcptr<T>(add, ps), add_ld,
+                                                                mkptr<T>(out, ps), out_ld,
+                                                                mkptr<T>(out_relu, ps), out_relu_ld, N);
       OTVM_LAUNCH_CHECK();
       return OTVM_OK;
     }
     int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-    launch_k(upsample_kernel<T>, grid_for(total, 256), 256, 0, s, static_cast<const T*>(in), in_ld, Hi, Wi, C, Ho, Wo,
-                                                           sy, sx, static_cast<const T*>(add), add_ld,
-                                                           static_cast<T*>(out), out_ld,
-                                                           static_cast<T*>(out_relu), out_relu_ld, N);
+    launch_k(upsample_kernel<T>, grid_for(total, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, Hi, Wi, C, Ho, Wo,
+                                                           sy, sx, mkcptr<T>(add, ps), add_ld,
+                                                           mkptr<T>(out, ps), out_ld,
+                                                           mkptr<T>(out_relu, ps), out_relu_ld, N);
   }
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -479,20 +515,17 @@ extern "C" int otvm_upsample_bilinear(const void* in, int64_t in_ld, int32_t N, 
                                       int32_t out_nchw_f32, void* stream) {
   if (!in || !out) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype,
-                 upsample_t<float>(in, in_ld, N, Hi, Wi, C, Ho, Wo, add, add_ld, out, out_ld, out_relu, out_relu_ld,
-                                   out_nchw_f32, s),
-                 upsample_t<bf16>(in, in_ld, N, Hi, Wi, C, Ho, Wo, add, add_ld, out, out_ld, out_relu, out_relu_ld,
-                                  out_nchw_f32, s));
+  DISPATCH_DTYPE(dtype, upsample_t<T>(in, in_ld, N, Hi, Wi, C, Ho, Wo, add, add_ld, out, out_ld, out_relu, out_relu_ld,
+                                      out_nchw_f32, ps, s));
 }
 
 template <typename T>
 static int maxpool_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, int64_t out_ld,
-                     cudaStream_t s) {
+                     int64_t ps, cudaStream_t s) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-  launch_k(maxpool_kernel<T>, grid_for(total, 256), 256, 0, s, static_cast<const T*>(in), in_ld, N, H, W, C, Ho, Wo,
-                                                        static_cast<T*>(out), out_ld);
+  launch_k(maxpool_kernel<T>, grid_for(total, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, N, H, W, C, Ho, Wo,
+                                                        mkptr<T>(out, ps), out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -501,17 +534,16 @@ extern "C" int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32
                                  void* out, int64_t out_ld, int32_t dtype, void* stream) {
   if (!in || !out || C % 4 || in_ld % 4 || out_ld % 4) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, maxpool_t<float>(in, in_ld, N, H, W, C, out, out_ld, s),
-                 maxpool_t<bf16>(in, in_ld, N, H, W, C, out, out_ld, s));
+  DISPATCH_DTYPE(dtype, maxpool_t<T>(in, in_ld, N, H, W, C, out, out_ld, ps, s));
 }
 
 template <typename T>
 static int ppm_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, float* scratch,
-                 cudaStream_t s) {
+                 int64_t ps, cudaStream_t s) {
   dim3 g1(H, ceil_div(C / 4, 128), N), g2(50, ceil_div(C / 4, 128), N);
-  launch_k(ppm_rows_kernel<T>, g1, 128, 0, s, static_cast<const T*>(in), in_ld, H, W, C, scratch);
+  launch_k(ppm_rows_kernel<T>, g1, 128, 0, s, mkcptr<T>(in, ps), in_ld, H, W, C, scratch);
   OTVM_LAUNCH_CHECK();
-  launch_k(ppm_cells_kernel<T>, g2, 128, 0, s, scratch, H, W, C, static_cast<T*>(out));
+  launch_k(ppm_cells_kernel<T>, g2, 128, 0, s, scratch, H, W, C, mkptr<T>(out, ps));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
@@ -520,28 +552,19 @@ extern "C" int otvm_ppm_pool(const void* in, int64_t in_ld, int32_t N, int32_t H
                              float* scratch, int32_t dtype, void* stream) {
   if (!in || !out || !scratch || C % 4 || in_ld % 4) return OTVM_ERR_ARG;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  DISPATCH_DTYPE(dtype, ppm_t<float>(in, in_ld, N, H, W, C, out, scratch, s),
-                 ppm_t<bf16>(in, in_ld, N, H, W, C, out, scratch, s));
+  DISPATCH_DTYPE(dtype, ppm_t<T>(in, in_ld, N, H, W, C, out, scratch, ps, s));
 }
 
 extern "C" int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
                                  int32_t dtype, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int g = grid_for((int64_t)N * HW * C, 256);
-  if (dtype == OTVM_F32) launch_k(nchw_to_nhwc_kernel<float>, g, 256, 0, s, in, C, HW, static_cast<float*>(out), out_ld, N);
-  else if (dtype == OTVM_BF16) launch_k(nchw_to_nhwc_kernel<bf16>, g, 256, 0, s, in, C, HW, static_cast<bf16*>(out), out_ld, N);
-  else return OTVM_ERR_ARG;
-  OTVM_LAUNCH_CHECK();
-  return OTVM_OK;
+  DISPATCH_DTYPE(dtype, (launch_k(nchw_to_nhwc_kernel<T>, g, 256, 0, s, in, C, HW, mkptr<T>(out, ps), out_ld, N), launched()));
 }
 
 extern "C" int otvm_nhwc_to_nchw(const void* in, int64_t in_ld, int32_t N, int32_t C, int32_t HW, float* out,
                                  int32_t dtype, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int g = grid_for((int64_t)N * HW * C, 256);
-  if (dtype == OTVM_F32) launch_k(nhwc_to_nchw_kernel<float>, g, 256, 0, s, static_cast<const float*>(in), in_ld, C, HW, out, N);
-  else if (dtype == OTVM_BF16) launch_k(nhwc_to_nchw_kernel<bf16>, g, 256, 0, s, static_cast<const bf16*>(in), in_ld, C, HW, out, N);
-  else return OTVM_ERR_ARG;
-  OTVM_LAUNCH_CHECK();
-  return OTVM_OK;
+  DISPATCH_DTYPE(dtype, (launch_k(nhwc_to_nchw_kernel<T>, g, 256, 0, s, mkcptr<T>(in, ps), in_ld, C, HW, out, N), launched()));
 }

@@ -24,6 +24,13 @@ import torch
 
 from . import ops
 from .ops import ACT_LEAKY, ACT_NONE, ACT_RELU
+from .split import SplitArena, split_planes, to_float
+
+# precision modes: name -> (activation dtype, bf16 planes per value).  "bf16x2" / "bf16x3" store every activation and
+# weight as 2 / 3 bf16 planes and multiply them pairwise on the tensor cores (split.py): fp32-grade results, which the
+# fp32 reference needs, at 3 / 6 tcgen05 products per K step.  "fp32" is the FFMA path.
+PRECISION_MODES = {"fp32": (torch.float32, 0), "bf16": (torch.bfloat16, 1), "bf16x2": (torch.bfloat16, 2),
+                   "bf16x3": (torch.bfloat16, 3), "fast": (torch.bfloat16, 2), "strict": (torch.bfloat16, 3)}
 
 DE, DO = 128, 512          # key / value channels (STM.py:184-185)
 BN_EPS = 1e-5
@@ -40,9 +47,10 @@ def _ws(w: torch.Tensor) -> torch.Tensor:
 class PackedWeights:
     """state_dict -> kernel-ready tensors on ``device`` in ``dtype``."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device, fba: bool = True):
-        """``fba=False`` packs the trimap-propagation network only (a stand-alone ``FullModel_eval``)."""
-        self.dtype, self.device = dtype, device
+    def __init__(self, sd: Dict[str, torch.Tensor], dtype: torch.dtype, device, fba: bool = True, planes: int = 1):
+        """``fba=False`` packs the trimap-propagation network only (a stand-alone ``FullModel_eval``).
+        ``planes`` > 1: bf16 weights are stored split, [planes][Cout][KH][KW][Cin]."""
+        self.dtype, self.device, self.planes = dtype, device, planes
         self.conv: Dict[str, tuple] = {}
         self.norm: Dict[str, tuple] = {}
         # stem channel padding: the tcgen05 path needs Cin % 16 == 0 (one 32-byte swizzle span per pixel)
@@ -54,7 +62,8 @@ class PackedWeights:
             cout, cin, kh, kw = w.shape
             if cin_pad and cin_pad > cin:
                 w = torch.cat([w, w.new_zeros(cout, cin_pad - cin, kh, kw)], dim=1)
-            wp = w.permute(0, 2, 3, 1).contiguous().to(device=device, dtype=dtype)
+            wp = w.permute(0, 2, 3, 1).contiguous()
+            wp = split_planes(wp, planes).to(device) if bf and planes > 1 else wp.to(device=device, dtype=dtype)
             bp = b.contiguous().to(device=device, dtype=torch.float32) if b is not None else None
             self.conv[name] = (wp, bp)
 
@@ -131,11 +140,14 @@ class PackedWeights:
 class FramePlan:
     """Device buffers for one padded frame size (allocated once, reused every frame)."""
 
-    def __init__(self, H, W, dtype, device, multiple=32):
+    def __init__(self, H, W, dtype, device, multiple=32, arena=None):
+        """``arena``: every buffer of the plan's activation dtype is carved from it (one plane stride for all split
+        tensors of the plan, split.py); ``device='meta'`` + a meta arena = planning pass that only adds up sizes."""
         self.H, self.W = H, W
+        self.arena, self.bank, self.stm_banks = arena, None, {}
         self.Hp, self.Wp = H + (multiple - H % multiple) % multiple, W + (multiple - W % multiple) % multiple
         self.pad_top, self.pad_left = (self.Hp - H) // 2, (self.Wp - W) // 2     # models/alpha/common.py:17-19
-        self.dtype, self.device = dtype, device
+        self.dtype, self.device = dtype, torch.device(device)
         self.bufs: Dict[str, torch.Tensor] = {}
         # GroupNorm statistics arena: one [32][2] fp64 slot per normalised convolution, zeroed ONCE per frame
         # (one memset node instead of one in front of each of the 66 convolutions)
@@ -150,9 +162,12 @@ class FramePlan:
     def buf(self, name, shape, dtype=None, zero=False):
         t = self.bufs.get(name)
         if t is None:
-            alloc = torch.zeros if zero else torch.empty
-            t = alloc(shape, dtype=dtype or self.dtype, device=self.device)
-            if not zero and t.is_floating_point() and os.environ.get("OTVM_DEBUG_POISON") == "1":
+            dt = dtype or self.dtype
+            if dt == torch.bfloat16 and self.arena is not None:
+                t = self.arena.alloc(shape, zero=zero)
+            else:
+                t = (torch.zeros if zero else torch.empty)(shape, dtype=dt, device=self.device)
+            if not zero and t.is_floating_point() and os.environ.get("OTVM_DEBUG_POISON") == "1" and not t.is_meta:
                 t.fill_(float("nan"))               # dev: a kernel reading bytes nobody wrote shows up as NaN
             self.bufs[name] = t
         assert tuple(t.shape) == tuple(shape), (name, t.shape, shape)
@@ -170,10 +185,14 @@ class MemoryBank:
     P.V contraction).
     """
 
-    def __init__(self, hw, cap, dtype, device):
-        self.hw, self.cap = hw, cap
-        self.keys = torch.zeros(cap * hw, DE, dtype=dtype, device=device)
-        self.vals = torch.zeros(DO, cap * hw, dtype=dtype, device=device)
+    def __init__(self, hw, cap, dtype, device, arena=None):
+        self.hw, self.cap, self.arena = hw, cap, arena
+        if arena is not None and dtype == torch.bfloat16:
+            self.keys = arena.alloc((cap * hw, DE), zero=True)
+            self.vals = arena.alloc((DO, cap * hw), zero=True)
+        else:
+            self.keys = torch.zeros(cap * hw, DE, dtype=dtype, device=device)
+            self.vals = torch.zeros(DO, cap * hw, dtype=dtype, device=device)
         self.order = []                 # logical (oldest..newest) -> physical slot
 
     @property
@@ -202,6 +221,26 @@ class MemoryBank:
     def key_slot(self, s):
         return self.keys[s * self.hw:(s + 1) * self.hw]
 
+    def store(self, key, val):
+        """overwrite the bank with fp32 tensors key [T*hw, De], val [Do, T*hw] (boundary / tests; PyTorch)"""
+        n = key.shape[0]
+        for dst, src in ((self.keys[:n], key), (self.vals[:, :n], val)):
+            if self.arena is not None and dst.dtype == torch.bfloat16:
+                self.arena.write(dst, src)
+            else:
+                dst.copy_(src)
+
+    def key_tensor(self, T=None):
+        """fp32 [1,1,De,T,h*w] copy of the held keys in LOGICAL order (reference layout, models/alpha/model.py:472)"""
+        order = self.order if T is None else list(range(T))
+        k = to_float(self.keys).view(self.cap, self.hw, DE)[order]
+        return k.permute(2, 0, 1).reshape(1, 1, DE, len(order), self.hw)
+
+    def val_tensor(self, T=None):
+        order = self.order if T is None else list(range(T))
+        v = to_float(self.vals).view(DO, self.cap, self.hw)[:, order]
+        return v.reshape(1, 1, DO, len(order), self.hw)
+
     def val_slot_ptr_offset(self, s):
         return s * self.hw
 
@@ -219,7 +258,7 @@ class _Fork:
 
     def __enter__(self):
         eng = self.eng
-        if eng.fork_enabled and ops.PROFILER is None:
+        if eng.fork_enabled and ops.PROFILER is None and not ops.DRY:
             self.stream = eng.streams.get(self.tag)
             if self.stream is None:
                 self.stream = eng.streams[self.tag] = torch.cuda.Stream(device=eng.device)
@@ -243,12 +282,13 @@ class _Fork:
 
 
 class Engine:
-    def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16, fba=True):
+    def __init__(self, state_dict, dtype=torch.float32, device="cuda", bank_capacity=16, fba=True, planes=None):
         self.dtype, self.device = dtype, torch.device(device)
-        self.w = PackedWeights(state_dict, dtype, self.device, fba=fba)
+        self.planes = (planes or 1) if dtype == torch.bfloat16 else 0
+        self.w = PackedWeights(state_dict, dtype, self.device, fba=fba, planes=max(self.planes, 1))
+        self.workspaces: Dict[str, torch.Tensor] = {}      # split-K scratch per stream tag (shared by all plans)
         self.bank_capacity = bank_capacity
         self.plans: Dict[tuple, FramePlan] = {}
-        self.banks: Dict[tuple, MemoryBank] = {}
         self.use_graphs = os.environ.get("OTVM_CUDA_GRAPHS", "1") != "0"
         # deferred memorize: frame t's Encoder_M / KV_M pass (STM.py:201-228) only feeds frame t+1's Memory.read, so
         # it is issued at the START of frame t+1 on a side stream, concurrently with Encoder_Q / KV_Q of t+1 (both
@@ -264,17 +304,49 @@ class Engine:
         self.replayed_launches = 0                 # kernels executed through graph replays (bench.py gpu_launches)
 
     # ------------------------------------------------------------------------------------------------
+    def _new_plan(self, H, W, multiple, dry_fn) -> FramePlan:
+        """bf16 modes: a planning pass (meta tensors, ops.DRY) walks the frame once to add up every activation buffer,
+        then ONE arena [planes][bytes] is allocated for the plan (all split tensors share its plane stride)."""
+        arena = None
+        if self.dtype == torch.bfloat16:
+            probe = FramePlan(H, W, self.dtype, "meta", multiple, arena=SplitArena(self.planes, 0, "meta"))
+            ops.DRY = True
+            try:
+                dry_fn(probe)
+            finally:
+                ops.DRY = False
+            arena = SplitArena(self.planes, probe.arena.off, self.device)
+        return FramePlan(H, W, self.dtype, self.device, multiple, arena=arena)
+
     def plan(self, H, W) -> FramePlan:
         k = (H, W)
         if k not in self.plans:
-            self.plans[k] = FramePlan(H, W, self.dtype, self.device)
+            self.plans[k] = self._new_plan(H, W, 32, self._dry_frame)
         return self.plans[k]
 
     def bank(self, pl: FramePlan) -> MemoryBank:
-        k = (pl.Hp, pl.Wp)
-        if k not in self.banks:
-            self.banks[k] = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), self.bank_capacity, self.dtype, self.device)
-        return self.banks[k]
+        if pl.bank is None:
+            pl.bank = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), self.bank_capacity, self.dtype, pl.device, pl.arena)
+        return pl.bank
+
+    def _dry_frame(self, pl: FramePlan):
+        """every buffer a frame can touch: first frame (with a user trimap) and a steady-state frame with a memorize pass"""
+        H, W = pl.H, pl.W
+        bank = self.bank(pl)
+        for n, shp in (("in_a", (H, W)), ("in_fg", (3, H, W)), ("in_bg", (3, H, W))):
+            pl.buf(n, shp, torch.float32)
+        for first in (True, False):
+            tri = torch.empty(3, H, W, device="meta") if first else None
+            self._frame_body(pl, bank, first_frame=first, slot=0, radius=1, user_tri=tri, pending=None if first else 0)
+
+    def workspace(self, pl) -> torch.Tensor:
+        """64 MB fp32 split-K scratch of the current stream tag (concurrent branches never share one)"""
+        if pl.device.type == "meta":
+            return torch.empty(16, dtype=torch.float32, device="meta")
+        ws = self.workspaces.get(self._ws_tag)
+        if ws is None:
+            ws = self.workspaces[self._ws_tag] = torch.empty(16 << 20, dtype=torch.float32, device=self.device)
+        return ws
 
     def fork(self, tag):
         return _Fork(self, tag)
@@ -283,12 +355,12 @@ class Engine:
     def _conv(self, pl, name, x, out_name=None, *, out=None, cout_f32=False, stride=1, pad=0, dil=1, **kw):
         w, b = self.w.conv[name]
         N, H, W, _ = x.shape
-        kh = w.shape[1]
+        kh, cout = w.shape[-3], w.shape[-4]
         Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         if out is None:
-            out = pl.buf(out_name or name, (N, Ho, Wo, w.shape[0]))
-        ws = pl.buf("conv_splitk_ws." + self._ws_tag, (16 << 20,), torch.float32)   # 64 MB split-K scratch per stream
+            out = pl.buf(out_name or name, (N, Ho, Wo, cout))
+        ws = self.workspace(pl)
         return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, workspace=ws, **kw)
 
     def _tv_bottleneck(self, pl, p, x, stride, out=None):
@@ -328,10 +400,10 @@ class Engine:
         g, b = self.w.norm[norm]
         w = self.w.conv[conv][0]
         N, H, W, _ = x.shape
-        kh = w.shape[1]
+        kh, cout = w.shape[-3], w.shape[-4]
         Ho = (H + 2 * pad - dil * (kh - 1) - 1) // stride + 1
         Wo = (W + 2 * pad - dil * (kh - 1) - 1) // stride + 1
-        raw = pl.buf(raw_name or conv, (N, Ho, Wo, w.shape[0]))
+        raw = pl.buf(raw_name or conv, (N, Ho, Wo, cout))
         dst = out if out is not None else raw
         # one kernel when the grid is a single co-resident wave: statistics, grid barrier, normalise from TMEM.
         # Only while nothing else is in flight on another stream: two grid-synchronising kernels sharing the SMs
@@ -386,7 +458,10 @@ class Engine:
         ws = pl.buf(f"read_ws.{bank.cap}", (ws_bytes // 4,), torch.float32)
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)      # deferred memorize of the previous frame has landed
-        ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws)
+        # strict mode (three planes): the fused tcgen05 read multiplies two planes per operand (2^-16), and with the
+        # reference-like ill-conditioned attention of random weights (logits of several hundred) that is 6e-5 on the read
+        # and 1.4e-3 on alpha after the softmax / FBA amplification -- the fp32 FFMA read keeps strict mode inside 1e-3
+        ops.memory_read(bank.keys, bank.vals, bank.vals.shape[1], qk, m4in[..., :DO], M, ws, force_simt=self.planes == 3)
         fv.join()
         return self._stm_decoder(pl, m4in, skips)
 
@@ -443,8 +518,21 @@ class Engine:
         """buffers for STM.memorize / STM.segment called on their own: pad to 16 (STM.py:204,241), not 32"""
         k = ("stm", H, W)
         if k not in self.plans:
-            self.plans[k] = FramePlan(H, W, self.dtype, self.device, multiple=16)
+            self.plans[k] = self._new_plan(H, W, 16, self._dry_stm)
         return self.plans[k]
+
+    def _stm_bank(self, pl: FramePlan) -> MemoryBank:
+        """bank of a stand-alone STM plan (the caller passes the memories in; capacity = bank_capacity frames)"""
+        if pl.bank is None:
+            pl.bank = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), self.bank_capacity, self.dtype, pl.device, pl.arena)
+        return pl.bank
+
+    def _dry_stm(self, pl: FramePlan):
+        pl.buf("mem_in", (1, pl.Hp, pl.Wp, self.w.cin_mem), zero=True)
+        pl.buf("imgn", (1, pl.Hp, pl.Wp, self.w.cin_img), zero=True)
+        bank = self._stm_bank(pl)
+        self.memorize(pl, bank, 0)
+        self.segment(pl, bank)
 
     def stm_memorize(self, frame, masks):
         """STM.memorize (STM.py:201-228): frame [1,3,H,W] RGB in [0,1], masks [1,20,H,W] = trimap 3 | alpha 1 | hidden 16
@@ -460,11 +548,11 @@ class Engine:
         x = torch.cat([f, m[:, 1:]], dim=1).contiguous()                         # rgb 3 | unknown | fg | alpha | hidden 16
         mem_in = pl.buf("mem_in", (1, pl.Hp, pl.Wp, self.w.cin_mem), zero=True)
         ops.nchw_to_nhwc(x, mem_in[..., :22])
-        bank = MemoryBank((pl.Hp // 16) * (pl.Wp // 16), 1, self.dtype, self.device)
+        bank = self._stm_bank(pl)
         self.memorize(pl, bank, 0)
         h, w = pl.Hp // 16, pl.Wp // 16
-        key = bank.keys.float().view(h, w, DE).permute(2, 0, 1).reshape(1, 1, DE, 1, h, w).contiguous()
-        val = bank.vals.float().view(1, 1, DO, 1, h, w).contiguous()
+        key = bank.key_tensor(1).view(1, 1, DE, 1, h, w).contiguous()
+        val = bank.val_tensor(1).view(1, 1, DO, 1, h, w).contiguous()
         return key, val
 
     def stm_segment(self, frame, keys, values):
@@ -481,9 +569,12 @@ class Engine:
         T = keys.shape[3]
         hw = (pl.Hp // 16) * (pl.Wp // 16)
         assert keys.shape[-2:] == (pl.Hp // 16, pl.Wp // 16), "memory and query frame sizes differ"
-        bank = MemoryBank(hw, T, self.dtype, self.device)
-        bank.keys.copy_(keys[0, 0].permute(1, 2, 3, 0).reshape(T * hw, DE))
-        bank.vals.copy_(values[0, 0].reshape(DO, T * hw))
+        bank = self._stm_bank(pl)
+        if T > bank.cap:
+            raise ValueError(f"{T} memory frames exceed the bank capacity {bank.cap} (set OTVM_BANK_CAPACITY)")
+        # (values arrive [Do, T, h*w] contiguous; the bank's channel rows are cap*hw long, frames 0..T-1 first)
+        bank.store(keys[0, 0].permute(1, 2, 3, 0).reshape(T * hw, DE).to(self.device),
+                   values[0, 0].reshape(DO, T * hw).to(self.device))
         bank.order = list(range(T))
         logits = self.segment(pl, bank)
         out = logits[0, lh:lh + H, lw:lw + W, :3].permute(2, 0, 1).unsqueeze(0).contiguous()
@@ -561,7 +652,7 @@ class Engine:
         f32 = torch.float32
         join = None
         if pending is not None:
-            if ops.PROFILER is None:
+            if ops.PROFILER is None and not ops.DRY:
                 if "memorize" not in self.streams:
                     self.streams["memorize"] = torch.cuda.Stream(device=self.device)
                 join = self.streams["memorize"]

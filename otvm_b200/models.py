@@ -19,12 +19,16 @@ import os
 import torch
 from torch import nn
 
-from .engine import Engine
+from .engine import PRECISION_MODES, Engine
 from .spec import state_spec
 
 _PARAM_ROLES = ("conv_w", "conv_b", "norm_w", "norm_b")
 _TORCH_DT = {"float32": torch.float32, "int64": torch.int64}
-PRECISIONS = {"fp32": torch.float32, "bf16": torch.bfloat16}
+# precision modes (engine.PRECISION_MODES): "bf16x2" (alias "fast", the default) and "bf16x3" ("strict") run every
+# contraction on the tcgen05 tensor cores with split-bf16 operands and meet the fp32 reference to 1e-2 / 1e-3; "bf16" is
+# plain bf16 storage (fastest, but it misses the reference by up to 0.7 on alpha: DESIGN.md section 4); "fp32" = FFMA.
+PRECISIONS = PRECISION_MODES
+DEFAULT_PRECISION = "bf16x2"
 
 
 class _Node(nn.Module):
@@ -89,8 +93,9 @@ class FullModel_eval(nn.Module):
             if dev.type != "cuda":
                 raise RuntimeError("otvm_b200 runs on a CUDA device only (no CPU fallback): call model.cuda()")
             sd = {"trimap." + k: v for k, v in self.state_dict().items()}
-            precision = getattr(self, "precision", None) or os.environ.get("OTVM_PRECISION", "bf16")
-            self._engine = Engine(sd, PRECISIONS[precision], dev, fba=False)
+            precision = getattr(self, "precision", None) or os.environ.get("OTVM_PRECISION", DEFAULT_PRECISION)
+            dtype, planes = PRECISIONS[precision]
+            self._engine = Engine(sd, dtype, dev, int(os.environ.get("OTVM_BANK_CAPACITY", "16")), fba=False, planes=planes)
         return self._engine
 
     @torch.no_grad()
@@ -129,10 +134,25 @@ class EvalModel(nn.Module):
         self.memory_update = False
         _grow(self, "")
         self.trimap = trimap
-        self.precision = precision or os.environ.get("OTVM_PRECISION", "bf16")
+        self.precision = precision or os.environ.get("OTVM_PRECISION", DEFAULT_PRECISION)
+        assert self.precision in PRECISIONS, self.precision
         self.bank_capacity = int(os.environ.get("OTVM_BANK_CAPACITY", "16"))
         self._engine = None
-        self.memories = {"key": None, "val": None}
+        self._last_plan = None
+
+    @property
+    def memories(self):
+        """``{'key': [1,1,128,T,h,w], 'val': [1,1,512,T,h,w]}`` fp32 copies of the bank in the reference's layout and
+        order (models/alpha/model.py:425-429,472-493), or ``None`` entries before the first frame.  The engine owns
+        the bank (pre-allocated slots, in-place replacement, possibly split-bf16 storage and a deferred memorize
+        pass): reading this property first runs a pending pass, so what is returned is complete."""
+        pl = self._last_plan
+        if self._engine is None or pl is None or pl.bank is None or pl.bank.T == 0:
+            return {"key": None, "val": None}
+        self._engine.flush(pl)
+        h, w = pl.Hp // 16, pl.Wp // 16
+        b = pl.bank
+        return {"key": b.key_tensor().view(1, 1, -1, b.T, h, w), "val": b.val_tensor().view(1, 1, -1, b.T, h, w)}
 
     # -- parameter changes invalidate the packed weights -------------------------------------------------
     def load_state_dict(self, *a, **k):
@@ -155,7 +175,8 @@ class EvalModel(nn.Module):
             dev = self.IMG_MEAN.device
             if dev.type != "cuda":
                 raise RuntimeError("otvm_b200 runs on a CUDA device only (no CPU fallback): call model.cuda()")
-            self._engine = Engine(self.state_dict(), PRECISIONS[self.precision], dev, self.bank_capacity)
+            dtype, planes = PRECISIONS[self.precision]
+            self._engine = Engine(self.state_dict(), dtype, dev, self.bank_capacity, planes=planes)
         return self._engine
 
     @torch.no_grad()
@@ -182,9 +203,7 @@ class EvalModel(nn.Module):
                                                 memorize=memorize, max_memory_num=max_memory_num,
                                                 radius=self.DILATION_KERNEL, user_tri=user_tri)
         self.memory_update = memorize
-        pl = eng.plan(H, W)
-        bank = eng.bank(pl)
-        self.memories = {"key": bank, "val": bank}            # the engine owns the bank (pre-allocated slots)
+        pl = self._last_plan = eng.plan(H, W)
         t3 = tri3.view(pl.Hp, pl.Wp, 4)[pl.pad_top:pl.pad_top + H, pl.pad_left:pl.pad_left + W, :3]
         tri_gt_out = t3.permute(2, 0, 1).reshape(1, 1, 3, H, W)
         if tri_gt is not None:                                 # make_trimap_gt(None, trimap3=tri) (:363-366)

@@ -11,10 +11,21 @@ import os
 
 import torch
 
-from . import _lib
+from . import _lib, split
 from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, F32, ConvParams, ReadParams, check  # noqa: F401
 
-_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+def _dt(t) -> int:
+    """dtype word of the C ABI for an activation tensor: OTVM_F32, OTVM_BF16, or OTVM_SPLIT_DTYPE(planes, stride) when
+    the bf16 tensor is the plane-0 view of a split tensor (:mod:`otvm_b200.split`)"""
+    if t.dtype == torch.float32:
+        return F32
+    assert t.dtype == torch.bfloat16, t.dtype
+    a = split.arena_of(t)
+    return a.dtype_word if a is not None else BF16
+
+
+DRY = False            # planning pass (Engine._measure): wrappers allocate / return without calling the library
 
 
 class Profiler:
@@ -56,8 +67,12 @@ def _timed(key, fn, flops=0.0, nbytes=0.0):
     return r
 
 
+def _planes(t):
+    return max(1, _dt(t) & 0xff) if t.dtype == torch.bfloat16 else 1
+
+
 def _nbytes(*ts):
-    return float(sum(t.shape.numel() * t.element_size() for t in ts if t is not None))
+    return float(sum(t.shape.numel() * t.element_size() * _planes(t) for t in ts if t is not None))
 
 
 def _stream():
@@ -87,8 +102,13 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     nothing of the normalisation is done, the raw convolution (+ statistics) is written to ``gn_raw_out`` and
     ``False`` is returned (the caller follows with :func:`gn_apply`).  Without ``gn_fuse`` the function returns
     ``out``."""
+    if DRY:
+        return out if gn_fuse is None else True
     lib = _lib.load()
     N, H, W, Cx = x.shape
+    wplanes = 1
+    if w.dim() == 5:                       # split weights [planes][Cout][KH][KW][Cin]
+        wplanes, w = w.shape[0], w[0]
     Cout, KH, KW, Cin = w.shape
     assert (cin or Cx) == Cin, (x.shape, w.shape)
     p = ConvParams()
@@ -103,7 +123,9 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
         p.out_ps, p.out_cs = out_strides
     p.res, p.res_ld = (res.data_ptr(), _ld(res)) if res is not None else (None, 0)
     p.out_relu, p.out_relu_ld = (out_relu.data_ptr(), _ld(out_relu)) if out_relu is not None else (None, 0)
-    p.act, p.relu_in, p.dtype = act, int(relu_in), _DT[x.dtype]
+    p.act, p.relu_in, p.dtype = act, int(relu_in), _dt(x)
+    p.w_plane_stride = w.numel()
+    assert wplanes == max(1, p.dtype & 0xff), "weights and activations must have the same number of planes"
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
     p.gn_stats_zeroed = int(gn_stats_zeroed)
@@ -129,8 +151,8 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     key = "conv_tcgen05" if lib.otvm_conv2d_uses_tensor_cores(C.byref(p)) else "conv_ffma"
     if PROFILE_SHAPES:
         key += f" Cin={Cin} Cout={Cout} k={KH} s={stride} d={dil} {H}x{W}"
-    es = x.element_size()
-    nb = (N * H * W * Cin + Cout * KH * KW * Cin) * es + N * Ho * Wo * Cout * out.element_size()
+    es = x.element_size() * _planes(x)
+    nb = (N * H * W * Cin + Cout * KH * KW * Cin) * es + N * Ho * Wo * Cout * out.element_size() * _planes(out)
     _timed(key, lambda: check(lib.otvm_conv2d(C.byref(p), _stream()), "otvm_conv2d"),
            2.0 * N * Ho * Wo * Cout * KH * KW * Cin, float(nb))
     return out if fused is None else fused
@@ -138,23 +160,29 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
 
 def zero_(t):
     """cudaMemsetAsync of a contiguous tensor on the current stream (GroupNorm statistics arena)"""
+    if DRY:
+        return t
     assert t.is_contiguous()
     check(_lib.load().otvm_zero_async(_p(t), t.numel() * t.element_size(), _stream()), "otvm_zero_async")
     return t
 
 
 def gn_stats(x, stats):
+    if DRY:
+        return None
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    _timed("gn_stats", lambda: check(lib.otvm_gn_stats(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats),
+    _timed("gn_stats", lambda: check(lib.otvm_gn_stats(_p(x), _ld(x), N, H * W, Cc, _dt(x), _p(stats),
                                                        _stream()), "otvm_gn_stats"), nbytes=_nbytes(x))
 
 
 def gn_apply(x, stats, gamma, beta, out, *, act=ACT_NONE, res=None, eps=1e-5):
+    if DRY:
+        return out
     lib = _lib.load()
     N, H, W, Cc = x.shape
     _timed("gn_apply", lambda: check(
-        lib.otvm_gn_apply(_p(x), _ld(x), N, H * W, Cc, _DT[x.dtype], _p(stats), _p(gamma), _p(beta), eps,
+        lib.otvm_gn_apply(_p(x), _ld(x), N, H * W, Cc, _dt(x), _p(stats), _p(gamma), _p(beta), eps,
                           _p(res), _ld(res) if res is not None else 0, act, _p(out), _ld(out), _stream()),
         "otvm_gn_apply"), nbytes=_nbytes(x, out, res))
     return out
@@ -164,6 +192,8 @@ def upsample(x, out, *, add=None, out_relu=None, out_nchw_f32=False):
     """bilinear, align_corners=False.  ``out`` is NHWC [N,Ho,Wo,C] with the dtype of ``x``; when C is not a
     multiple of 4 (the 3 STM logits) ``x`` and ``out`` are fp32 and ``out`` may instead be NCHW planes
     [C,Ho,Wo] (``out_nchw_f32``)."""
+    if DRY:
+        return out
     lib = _lib.load()
     N, Hi, Wi, Cc = x.shape
     if out_nchw_f32:
@@ -177,36 +207,45 @@ def upsample(x, out, *, add=None, out_relu=None, out_nchw_f32=False):
     _timed("upsample", lambda: check(
         lib.otvm_upsample_bilinear(_p(x), _ld(x), N, Hi, Wi, Cc, Ho, Wo, _p(add),
                                    _ld(add) if add is not None else 0, _p(out), old, _p(out_relu),
-                                   _ld(out_relu) if out_relu is not None else 0, _DT[x.dtype],
+                                   _ld(out_relu) if out_relu is not None else 0, _dt(x),
                                    int(out_nchw_f32), _stream()), "otvm_upsample_bilinear"),
         nbytes=_nbytes(x, out, add, out_relu))
     return out
 
 
 def maxpool3x3s2(x, out):
+    if DRY:
+        return out
     lib = _lib.load()
     N, H, W, Cc = x.shape
     _timed("maxpool", lambda: check(lib.otvm_maxpool3x3s2(_p(x), _ld(x), N, H, W, Cc, _p(out), _ld(out),
-                                                          _DT[x.dtype], _stream()), "otvm_maxpool3x3s2"),
+                                                          _dt(x), _stream()), "otvm_maxpool3x3s2"),
            nbytes=_nbytes(x, out))
     return out
 
 
 def ppm_pool(x, out, scratch):
+    if DRY:
+        return out
     lib = _lib.load()
     N, H, W, Cc = x.shape
     _timed("ppm_pool", lambda: check(lib.otvm_ppm_pool(_p(x), _ld(x), N, H, W, Cc, _p(out), _p(scratch),
-                                                       _DT[x.dtype], _stream()), "otvm_ppm_pool"), nbytes=_nbytes(x))
+                                                       _dt(x), _stream()), "otvm_ppm_pool"), nbytes=_nbytes(x))
     return out
 
 
-def memory_read_workspace(M, HW, De, Do, dtype):
-    return int(_lib.load().otvm_memory_read_workspace(M, HW, De, Do, _DT[dtype]))
+def memory_read_workspace(M, HW, De, Do, dtype=None):
+    """bytes of fp32 scratch for :func:`memory_read` (an upper bound over every element format)"""
+    if DRY:
+        return 16
+    return int(_lib.load().otvm_memory_read_workspace(M, HW, De, Do, BF16))
 
 
 def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
     """keys [>=M, De] rows; vals [Do, ldv] channel-major; query NHWC view with De channels; out NHWC view with
     Do channels (a slice of the 2*Do decoder input)."""
+    if DRY:
+        return out
     lib = _lib.load()
     p = ReadParams()
     De, Do = keys.shape[-1], vals.shape[0]
@@ -215,34 +254,40 @@ def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
     p.query, p.q_ld = query.data_ptr(), _ld(query)
     p.out, p.out_ld = out.data_ptr(), _ld(out)
     p.M, p.HW, p.De, p.Do = M, HW, De, Do
-    p.dtype = _DT[keys.dtype]
+    p.dtype = _dt(keys)
     p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     p.force_simt = int(force_simt)
-    es = keys.element_size()
+    es = keys.element_size() * _planes(keys)
     _timed("memory_read", lambda: check(lib.otvm_memory_read(C.byref(p), _stream()), "otvm_memory_read"),
            2.0 * M * HW * (De + Do), float((De + Do) * M * es + De * HW * es + Do * HW * es))
     return out
 
 
 def preprocess(a, fg, bg, H, W, Hp, Wp, pad_top, pad_left, radius, mean_std, img, scaled_img, tri3, imgn, scratch):
+    if DRY:
+        return None
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
     _timed("glue", lambda: check(
         lib.otvm_preprocess(_p(a), _p(fg), _p(bg), H, W, Hp, Wp, pad_top, pad_left, radius, ms, _p(img),
-                            _p(scaled_img), _p(tri3), _p(imgn), _ld(imgn), _DT[imgn.dtype], _p(scratch),
+                            _p(scaled_img), _p(tri3), _p(imgn), _ld(imgn), _dt(imgn), _p(scratch),
                             _stream()), "otvm_preprocess"))
 
 
 def trimap_encode(tri, tri_ld, is_logit, img, Hp, Wp, mean_std, x11, cat_dst, extras, d2, scratch, seeds):
+    if DRY:
+        return None
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
     _timed("trimap_encode_edt", lambda: check(
         lib.otvm_trimap_encode(_p(tri), tri_ld, int(is_logit), _p(img), Hp, Wp, ms, _p(x11), _ld(x11),
-                               _p(cat_dst), _ld(cat_dst) if cat_dst is not None else 0, _DT[x11.dtype],
+                               _p(cat_dst), _ld(cat_dst) if cat_dst is not None else 0, _dt(x11),
                                _p(extras), _p(d2), _p(scratch), _p(seeds), _stream()), "otvm_trimap_encode"))
 
 
 def edt_sq(seed, d2, scratch):
+    if DRY:
+        return d2
     lib = _lib.load()
     H, W = seed.shape
     check(lib.otvm_edt_sq(_p(seed), H, W, _p(d2), _p(scratch), _stream()), "otvm_edt_sq")
@@ -250,31 +295,42 @@ def edt_sq(seed, d2, scratch):
 
 
 def fba_head(raw, raw_ld, dtype, extras, P, out7, alpha_dst=None, alpha_ld=0):
+    if DRY:
+        return None
     lib = _lib.load()
+    # element format of alpha_dst (and of `raw` unless it is fp32)
+    fmt = _dt(alpha_dst) if alpha_dst is not None else (_dt(raw) if raw.dtype != torch.float32 else
+                                                       (F32 if dtype == torch.float32 else BF16))
     _timed("glue", lambda: check(
-        lib.otvm_fba_head(_p(raw), raw_ld, _DT[dtype], int(raw.dtype == torch.float32), _p(extras), P, _p(out7),
+        lib.otvm_fba_head(_p(raw), raw_ld, fmt, int(raw.dtype == torch.float32), _p(extras), P, _p(out7),
                           _p(alpha_dst), alpha_ld, _stream()), "otvm_fba_head"))
 
 
 def frame_outputs(raw10, raw_ld, fused, hid, extras, Hp, Wp, H, W, pad_top, pad_left, mean_std, mem_in,
                   alpha_out, trimap_out):
+    if DRY:
+        return None
     lib = _lib.load()
     ms = (C.c_float * 6)(*mean_std)
     _timed("glue", lambda: check(
         lib.otvm_frame_outputs(_p(raw10), raw_ld, _p(fused), _p(hid), _ld(hid), _p(extras), Hp, Wp, H, W,
                                pad_top, pad_left, ms, _p(mem_in), _ld(mem_in) if mem_in is not None else 0,
-                               _DT[hid.dtype], _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs"))
+                               _dt(hid), _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs"))
 
 
 def nchw_to_nhwc(x, out):
+    if DRY:
+        return out
     lib = _lib.load()
     N, Cc, H, W = x.shape
-    check(lib.otvm_nchw_to_nhwc(_p(x), N, Cc, H * W, _p(out), _ld(out), _DT[out.dtype], _stream()), "nchw_to_nhwc")
+    check(lib.otvm_nchw_to_nhwc(_p(x), N, Cc, H * W, _p(out), _ld(out), _dt(out), _stream()), "nchw_to_nhwc")
     return out
 
 
 def nhwc_to_nchw(x, out):
+    if DRY:
+        return out
     lib = _lib.load()
     N, H, W, Cc = x.shape
-    check(lib.otvm_nhwc_to_nchw(_p(x), _ld(x), N, Cc, H * W, _p(out), _DT[x.dtype], _stream()), "nhwc_to_nchw")
+    check(lib.otvm_nhwc_to_nchw(_p(x), _ld(x), N, Cc, H * W, _p(out), _dt(x), _stream()), "nhwc_to_nchw")
     return out

@@ -3,7 +3,7 @@
 // is loaded once by TMA; for every row shift s = 0..8 the MMA computes D_s = A[s : s+128, :] . W^T from the SAME
 // shared-memory copy, with the descriptor's base_offset field either 0 or (start >> 7) & 7.  The halo-reuse
 // convolution (one input row box feeding the three horizontal filter taps) depends on the answer.
-#include "tc_common.cuh"
+#include "tc_common.cuh"   // -I otvm_b200/csrc (scripts/umma_probe.py)
 
 namespace otvm {
 using namespace tc;

@@ -25,7 +25,9 @@ def build_model(kind, precision, radius=12, capacity=16):
 
 
 def nchw(t):
-    return t.float().permute(0, 3, 1, 2).cpu()
+    """NHWC activation of any element format (fp32, bf16, split bf16) -> NCHW fp32 on the host"""
+    from otvm_b200.split import to_float
+    return to_float(t).permute(0, 3, 1, 2).cpu()
 
 
 def force_bank(model, oracle, H, W):
@@ -36,8 +38,7 @@ def force_bank(model, oracle, H, W):
     eng.flush(pl)                                  # a deferred memorize pass must not land after the overwrite
     key, val = oracle.memories["key"][0, 0], oracle.memories["val"][0, 0]       # [C,T,h,w]
     T = key.shape[1]
-    bank.keys[:T * bank.hw] = key.permute(1, 2, 3, 0).reshape(T * bank.hw, -1).to(bank.keys)
-    bank.vals[:, :T * bank.hw] = val.reshape(val.shape[0], T * bank.hw).to(bank.vals)
+    bank.store(key.permute(1, 2, 3, 0).reshape(T * bank.hw, -1).to(eng.device), val.reshape(val.shape[0], T * bank.hw).to(eng.device))
     bank.order = list(range(T))
 
 
@@ -64,8 +65,9 @@ def compare_frame(model, oracle, out, ref, H, W, first, rel_err=rel_err):
     torch.cuda.synchronize()
     s = bank.order[-1]
     h, w = Hp // 16, Wp // 16
-    e["mem_key"] = rel_err(bank.key_slot(s).float().cpu().view(h, w, -1).permute(2, 0, 1), tr["mem_k"][0, :, 0])
-    e["mem_val"] = rel_err(bank.vals[:, s * bank.hw:(s + 1) * bank.hw].float().cpu().view(-1, h, w), tr["mem_v"][0, :, 0])
+    from otvm_b200.split import to_float
+    e["mem_key"] = rel_err(to_float(bank.key_slot(s)).cpu().view(h, w, -1).permute(2, 0, 1), tr["mem_k"][0, :, 0])
+    e["mem_val"] = rel_err(to_float(bank.vals[:, s * bank.hw:(s + 1) * bank.hw]).cpu().view(-1, h, w), tr["mem_v"][0, :, 0])
     e["alpha"] = rel_err(out[3].cpu(), ref[3])
     e["trimap"] = rel_err(out[1].cpu(), ref[1])
     e["scaled_img"] = rel_err(out[0].cpu(), ref[0])

@@ -7,8 +7,11 @@ from util import golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
-# north star: 1e-3 (fp32) on trimap logits and alpha matte; every compared tensor is held to it.
+# north star: 1e-3 (fp32) / 1e-2 (reduced precision) on trimap logits and alpha matte, scale-relative MAX norm
+# (tests/util.py:rel_err); every compared tensor of a frame is held to it, not only the two outputs.
 FP32_TOL = 1e-3
+# tensor-core modes (otvm_b200/split.py): "bf16x2" is the default / benchmarked mode, "bf16x3" the strict one
+TC_TOL = {"bf16x2": 1e-2, "bf16x3": 1e-3}
 
 
 @pytest.mark.parametrize("kind,H,W", [("tempered", 128, 128), ("default", 128, 128), ("tempered", 120, 152)])
@@ -60,7 +63,7 @@ def test_cuda_graph_replay_matches_eager():
         assert rel_err(a1.cpu(), a0.cpu()) < 1e-3 and rel_err(t1.cpu(), t0.cpu()) < 1e-3
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x2"])
 def test_overlap_and_pdl_do_not_change_results(precision):
     """deferred memorize on the side stream (engine.defer_memorize) and programmatic dependent launch are pure
     scheduling changes: same frames with both switched off must give the same outputs"""
@@ -84,19 +87,31 @@ def test_overlap_and_pdl_do_not_change_results(precision):
         outs[mode] = res
     os.environ["OTVM_OVERLAP"] = "1"
     _lib.load().otvm_set_pdl(1)
-    tol = 1e-3 if precision == "fp32" else 3e-2        # only the order of the GroupNorm-statistics atomics differs
+    tol = 1e-3                                         # only the order of the GroupNorm-statistics atomics differs
     for (a0, t0), (a1, t1) in zip(outs["off"], outs["on"]):
         assert rel_err(a1.cpu(), a0.cpu()) < tol and rel_err(t1.cpu(), t0.cpu()) < tol
 
 
-def test_bf16_frames_teacher_forced():
-    """bf16 storage + tcgen05 (fp32 accumulation) against the fp32 oracle, per frame with the oracle's memory bank.
+@pytest.mark.parametrize("precision", ["bf16x2", "bf16x3"])
+@pytest.mark.parametrize("kind,H,W", [("tempered", 256, 256), ("default", 128, 128), ("tempered", 120, 152)])
+def test_tensor_core_frames_teacher_forced(kind, H, W, precision):
+    """the tcgen05 path (split-bf16 operands, fp32 accumulation) against the fp32 oracle, per frame with the oracle's
+    memory bank: EVERY compared tensor -- propagated trimap logits, Memory.read output, keys / values, conv5, the raw and
+    fused heads, hid, trimap, alpha -- within the north-star tolerance in the MAX norm: 1e-2 for the default two-plane
+    mode, 1e-3 for the strict three-plane mode (measured ~5e-4 / ~1e-5)."""
+    rows = run_clip(kind, precision, H, W, 3, max_mem=2 if H == 120 else 8)
+    tol = TC_TOL[precision]
+    for i, e in enumerate(rows):
+        for k, v in e.items():
+            assert v < tol, (precision, i, k, v, e)
+        assert e["scaled_img"] < 1e-6 and e["tri_gt"] == 0
 
-    North star: 1e-2 for bf16.  The propagated-trimap path (Encoder_Q -> KV -> Memory.read -> Decoder) meets it in
-    the max norm.  The alpha head does not in the max norm and cannot: fba_fusion (FBA/models.py:279-288) divides
-    by sum((F-B)^2)+0.1, which amplifies the ~4e-3 (mean) bf16 noise of the 70-layer GN network ~10x at pixels where
-    F ~ B, so the alpha/fused tensors are held to 1e-2-scale *mean* errors and the pre-fusion heads to 1e-2 mean /
-    1e-1 max ('Numerics')."""
+
+def test_plain_bf16_frames_document_the_gap():
+    """plain bf16 storage (precision="bf16", NOT the default and not the benchmarked mode): the propagated-trimap path
+    stays near 1e-2, but the random-weight FBA network amplifies the 2^-9 storage rounding of ~70 layers and
+    fba_fusion (FBA/models.py:279-288) divides by sum((F-B)^2)+0.1, so alpha is only bounded in the mean.  This test
+    pins those bounds so that the reason for the split-bf16 modes stays measurable."""
     rows = run_clip("tempered", "bf16", 256, 256, 3, with_mean=True)
     for i, e in enumerate(rows):
         for k in ("seg_logit", "read_mem", "q_key"):
@@ -111,7 +126,7 @@ def test_bf16_frames_teacher_forced():
         assert e["scaled_img"][0] < 1e-6 and e["tri_gt"][0] == 0
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 3e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16x2", 1e-3), ("bf16x3", 1e-3), ("bf16", 3e-2)])
 def test_trimap_wrapper_standalone(precision, tol):
     """FullModel_eval.forward(memorize=True) / (segment=True) called directly with the reference's argument meaning
     (models/trimap/model.py:247-264), on a size that needs the pad-16 of STM.memorize / STM.segment (STM.py:204,241),

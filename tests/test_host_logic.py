@@ -137,9 +137,9 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.otvm_version() == 3
+    assert lib.otvm_version() == 4
     assert lib.otvm_strerror(-3).decode().startswith("unsupported")
-    assert ctypes.sizeof(_lib.ConvParams) == 192 and ctypes.sizeof(_lib.ReadParams) == 104   # sizeof() of the C structs
+    assert ctypes.sizeof(_lib.ConvParams) == 200 and ctypes.sizeof(_lib.ReadParams) == 104   # sizeof() of the C structs
 
 
 def test_clip_sharding_two_ranks_gloo():
