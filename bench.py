@@ -305,7 +305,7 @@ def main():
     ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16x2", choices=["bf16x2", "bf16x3", "fast", "strict", "bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true", help="dev: skip the instrumented per-family pass")
     ap.add_argument("--size", type=int, default=512, help="frame height = width (BASELINE configs[2]: 1024)")

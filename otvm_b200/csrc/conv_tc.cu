@@ -54,6 +54,7 @@ struct ConvTcArgs {
   // split-bf16: planes per operand, plane products per K step (1 / 3 / 6), bytes of ONE operand plane inside a stage
   // (a_bytes = planes * a_plane, b_bytes = planes * b_plane, a patch-ring slot = planes * patch_bytes)
   int planes, npair;
+  int wide;                    // split operands: products (a0 b0) and (a0 b1) are ONE MMA of N = 2 BN (see the MMA issuers)
   uint32_t a_plane, b_plane;
   int64_t act_plane;           // elements between the planes of out / res / out_relu in global memory
   const float* bias;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       // SBO = pw pixel rows.  Row-shifted SWIZZLE_* operands are valid because the hardware swizzles on absolute
       // shared-memory address bits (probed on B200: csrc/umma_probe.cu) =====
       constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+      constexpr uint32_t idesc2 = make_idesc_bf16(128, BN < 16 ? 32 : 2 * BN);
       const int ksteps = a.KC / 16;
       const uint64_t adesc0 = make_smem_desc(base, (uint32_t)pw * a.row_bytes, a.layout_type);
       const uint64_t bdesc0 = make_smem_desc(base + a.b_off, a.sbo, a.layout_type);
@@ -251,12 +253,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         const bool last_tap = kx == 2 && ky == 2;
         if (elect_one()) {
           const uint64_t ad0 = adesc0 + aoff + toff, bd0 = bdesc0 + soff;
-          for (int pr = 0; pr < a.npair; ++pr) {
+          // product 0 -> main accumulator, cross-plane products -> the second one (columns ACC_COLS..).  `wide`: the B
+          // planes are contiguous [hi | lo] rows and the two accumulators adjacent columns, so a0 . [b0 | b1] is one
+          // instruction of N = 2 BN writing both (product 1 is then skipped): a third fewer issues per K step, which is
+          // what paces the N <= 64 layers (one thread issues ~55 cycles per instruction, 32 of tensor work)
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base, ad0 + (uint64_t)(2 * k), bd0 + (uint64_t)(2 * k), a.wide ? idesc2 : idesc, (it | k) != 0);
+          for (int pr = a.wide ? 2 : 1; pr < a.npair; ++pr) {
             const uint64_t ad = ad0 + ((kPairA >> (4 * pr)) & 15u) * aplane16, bd = bd0 + ((kPairB >> (4 * pr)) & 15u) * bplane16;
-            // (product 0 -> main accumulator, cross-plane products -> the second one)
-            const uint32_t dt = pr == 0 ? tmem_base : tmem_base + ACC_COLS;
             for (int k = 0; k < ksteps; ++k)
-              umma_bf16(dt, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, pr == 0 ? (it | k) != 0 : (it | (pr - 1) | k) != 0);
+              umma_bf16(tmem_base + ACC_COLS, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                        a.wide ? 1u : (uint32_t)((it | (pr - 1) | k) != 0));
           }
           umma_commit(&empty_bar[s]);
           if (last_tap) umma_commit(&a_empty[as]);             // all 9 taps of this chunk have read the patch
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   } else if (warp == 1) {
     // ----- MMA issuer -----
     constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+    const uint32_t idesc0 = a.wide ? make_idesc_bf16(128, BN < 16 ? 32 : 2 * BN) : idesc;   // see the halo issuer
     const uint64_t adesc0 = make_smem_desc(base, a.sbo, a.layout_type);
     const uint64_t bdesc0 = make_smem_desc(base + a.a_bytes, a.sbo, a.layout_type);
     const uint32_t a_lo0 = (uint32_t)adesc0, b_lo0 = (uint32_t)bdesc0, hi = (uint32_t)(adesc0 >> 32);   // same SBO / layout
@@ -355,16 +363,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         tcgen05_after_sync();
         if (elect_one()) {
           if (dbg && it == 0) dbg[3] = clock64();
-          umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc, it != 0);
+          umma_bf16_lh(tmem_base, a_lo, hi, b_lo, hi, idesc0, it != 0);
 #pragma unroll
-          for (int k = 1; k < KS; ++k) umma_bf16_lh(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc, 1u);
+          for (int k = 1; k < KS; ++k) umma_bf16_lh(tmem_base, a_lo + 2 * k, hi, b_lo + 2 * k, hi, idesc0, 1u);
 #pragma unroll
           for (int pr = 1; pr < 6; ++pr) {                     // cross-plane products of split operands
-            if (pr < a.npair) {
+            if (pr < a.npair && !(pr == 1 && a.wide)) {
               const uint32_t ap = a_lo + ((kPairA >> (4 * pr)) & 15u) * aplane16, bp = b_lo + ((kPairB >> (4 * pr)) & 15u) * bplane16;
 #pragma unroll
               for (int k = 0; k < KS; ++k)
-                umma_bf16_lh(tmem_base + ACC_COLS, ap + 2 * k, hi, bp + 2 * k, hi, idesc, (it | (pr - 1) | k) != 0);
+                umma_bf16_lh(tmem_base + ACC_COLS, ap + 2 * k, hi, bp + 2 * k, hi, idesc,
+                             a.wide ? 1u : (uint32_t)((it | (pr - 1) | k) != 0));
             }
           }
           if (two) {
@@ -1019,7 +1028,8 @@ static int pick_bn(const otvm_conv_params* p) {
     const int64_t tiles = (int64_t)ceil_div(Wo, tw) * ceil_div(Ho, 128 / tw) * p->N;
     const int kc = p->Cin % 64 == 0 ? 64 : p->Cin % 32 == 0 ? 32 : 16;
     const int num_k = p->KH * p->KW * (p->Cin / kc);            // long-K layers keep 128 and slice K instead (split-K)
-    if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k < 48) bn = 64;
+    const int planes = dtype_planes(p->dtype), npair = planes == 1 ? 1 : planes == 2 ? 3 : 6;
+    if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k * npair < 48) bn = 64;
     // (32-channel tiles on the even smaller grids measured slower: 429.6 vs 433.2 frames/s)
   }
   return bn;
@@ -1057,7 +1067,7 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   if ((reinterpret_cast<uintptr_t>(p->in) & 15) || (reinterpret_cast<uintptr_t>(p->weight) & 15)) return false;
   const int Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;
   const int Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
-  if (Wo < 8 || Ho < 1 || (int64_t)Ho * Wo < 64) return false;
+  if (Wo < 8 || Ho < 1) return false;
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
   if (p->gn_stats && (p->N != 1 || p->Cout % 32 != 0)) return false;
   const int bn = pick_bn(p);
@@ -1229,6 +1239,8 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.a_bytes = (uint32_t)a.planes * a.a_plane;
   a.b_bytes = (uint32_t)a.planes * a.b_plane;
   a.b_off = (uint32_t)a.na * (uint32_t)a.planes * a.patch_bytes;
+  // [hi | lo] weight planes are one contiguous 2 BN-row tile when a plane is not padded; BN >= 32: accumulators BN apart
+  a.wide = a.planes > 1 && bn >= 32 && a.b_plane == (uint32_t)bn * a.KC * 2;
   a.sbo = 8u * a.KC * 2;
   a.layout_type = a.KC == 64 ? 2u : a.KC == 32 ? 4u : 6u;
   const uint32_t stage = a.a_bytes + a.b_bytes;
@@ -1258,7 +1270,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     if (n > 8) n = 8;
     const int groups = ceil_div(iters, ksub_);
     if (n > groups) n = groups;
-    if (n < 2) n = 2;
+    if (n < 2) n = groups < 2 ? 1 : 2;      // (a one-iteration K loop needs one stage: the CTA stays small and co-resides)
     return n;
   };
   int ksub = (!a.halo && a.planes == 1 && ctas <= sm_count() && num_k >= 8 && conv_ksub_mode() >= 2) ? 2 : 1;
@@ -1266,10 +1278,13 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
   int nsplit = 1;
   const int64_t Mtot = (int64_t)p->N * a.Ho * a.Wo;
-  if (p->workspace && ctas * 2 <= sm_count() && num_k >= 48 && p->Cout % 4 == 0 &&
+  // (split operands: a K iteration carries npair plane products, so the serial walk is that much longer per iteration)
+  const int num_kp = num_k * a.npair;
+  if (p->workspace && ctas * 2 <= sm_count() && num_kp >= 48 && p->Cout % 4 == 0 &&
       (!p->res || p->res_ld % 4 == 0) && (!p->out_relu || p->out_relu_ld % 4 == 0)) {
     nsplit = (int)(sm_count() / ctas);
-    if (nsplit > num_k / 12) nsplit = num_k / 12;          // >= 12 K iterations per slice: the extra pass must pay off
+    if (nsplit > num_kp / 12) nsplit = num_kp / 12;        // >= 12 K iterations' worth per slice: the extra pass must pay off
+    if (nsplit > num_k) nsplit = num_k;
     if (nsplit > 16) nsplit = 16;
     while (nsplit > 1 && (int64_t)nsplit * Mtot * p->Cout * 4 > p->workspace_bytes) --nsplit;
   }

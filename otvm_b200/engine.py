@@ -606,10 +606,13 @@ class Engine:
         off = 0
         forks = []
         for i, s in enumerate((1, 2, 3, 6)):                # four independent branches
-            cells = pooled[off:off + s * s].view(1, s, s, 2048); off += s * s
+            # (a 1x1 convolution does not care how its pixels are arranged: the 3x3 and 6x6 grids go in as one row of 9 / 36
+            # pixels, wide enough for the tcgen05 kernel's 8-pixel tile rows; 1 and 4 cells stay on the small-M FFMA kernel)
+            shape = (1, 1, s * s, 2048) if s * s >= 8 else (1, s, s, 2048)
+            cells = pooled[off:off + s * s].view(shape); off += s * s
             with self.fork(f"ppm{i}") as fk:
                 y = self._ws_gn(pl, f"NET.decoder.ppm.{i}.1", f"NET.decoder.ppm.{i}.2", cells, act=ACT_LEAKY)
-                ops.upsample(y, cat1[..., 2048 + 256 * i: 2304 + 256 * i])
+                ops.upsample(y.view(1, s, s, 256), cat1[..., 2048 + 256 * i: 2304 + 256 * i])
             forks.append(fk)
         for fk in forks:
             fk.join()
