@@ -63,6 +63,11 @@ OTVM_API int otvm_device_is_sm100(int device);
  * kernel's tail).  A caller that rewrites a parameter buffer on the device must synchronise the stream (or call
  * otvm_set_pdl(0)) between that write and the next call that reads it.  Activations carry no such restriction. */
 OTVM_API void otvm_set_pdl(int enabled);
+/* Sticky device-side error flags of the current device (synchronises the device; `clear` != 0 resets them).
+ *   bit 0: the grid-wide barrier of a GroupNorm-fused convolution (otvm_conv_params.gn_gamma) timed out because a CTA
+ *          of its grid never became resident (something else held the SMs); that launch's output is invalid, the
+ *          stream and the process remain usable.  Returns -1 when the flags cannot be read. */
+OTVM_API int otvm_device_error_flags(int clear);
 /* cudaMemsetAsync(ptr, 0, bytes) on `stream` (e.g. the per-frame GroupNorm statistics arena) */
 OTVM_API int otvm_zero_async(void* ptr, int64_t bytes, void* stream);
 

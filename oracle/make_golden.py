@@ -85,6 +85,21 @@ def run_clip(ma, H, W, n_frames, max_mem, clip=0, keep=None, stride=1):
     return out
 
 
+def user_trimap_cases(ma, H=128, W=128):
+    """two 2-frame clips whose first frame is seeded by ``tri=`` / ``tri_gt=`` (models/alpha/model.py:395-401)"""
+    from otvm_b200.fixtures import make_frame, user_trimap
+    out = {}
+    for kind in ("tri", "tri_gt"):
+        for i in range(2):
+            a, fg, bg = make_frame(3, i, H, W)
+            kw = {kind: user_trimap(kind, H, W)} if i == 0 else {}
+            r = ma(a, fg, bg, first_frame=(i == 0), last_frame=False, memorize=True, max_memory_num=8, **kw)
+            out[f"{kind}_f{i}_alpha"] = r[3][0, 0, 0].numpy().copy()
+            out[f"{kind}_f{i}_trimap"] = r[1][0, 0].numpy().copy()
+            out[f"{kind}_f{i}_tri_gt"] = r[2][0, 0].numpy().copy()
+    return out
+
+
 def memory_read_cases(helpers):
     """Known-answer vectors for ``Memory.forward`` (STM.py:144-163) straight from the reference class."""
     from models.trimap.STM import Memory
@@ -149,6 +164,11 @@ def main():
     if not only or "stm_standalone" in only:
         np.savez_compressed(os.path.join(gdir, "stm_standalone.npz"), **stm_standalone_cases(helpers, make_state_dict("tempered")))
         print("stm_standalone.npz")
+
+    if not only or "user_trimap_128" in only:
+        ma = build_reference(helpers, make_state_dict("tempered"))
+        np.savez_compressed(os.path.join(gdir, "user_trimap_128.npz"), **user_trimap_cases(ma))
+        print("user_trimap_128.npz")
 
     jobs = [  # name, kind, H, W, frames, max_mem, keep, stride
         ("clip_tempered_256", "tempered", 256, 256, 3, 8, None, 1),

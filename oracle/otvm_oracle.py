@@ -348,7 +348,8 @@ def trimap_from_alpha(alpha, radius):
 # --------------------------------------------------------------------------------------------------
 
 class OracleEvalModel:
-    """Same call contract as the reference ``EvalModel`` at stage 4 with ``tri=None, tri_gt=None``."""
+    """Same call contract as the reference ``EvalModel`` at stage 4, including the one-trimap inputs ``tri=`` (a BGR
+    0..255 trimap image) and ``tri_gt=`` (a one-hot / soft 3-channel trimap) that seed frame 0, models/alpha/model.py:395-401."""
 
     IMG_SCALE = 1.0 / 255
 
@@ -361,7 +362,6 @@ class OracleEvalModel:
     @torch.no_grad()
     def __call__(self, a, fg, bg, tri=None, tri_gt=None, first_frame=False, last_frame=False,
                  memorize=False, max_memory_num=2, large_input=False):
-        assert tri is None and tri_gt is None, "oracle covers the eval.py call (tri=None, tri_gt=None)"
         sd = self.sd
         # preprocess_gt :380-389 (the trimap_transform at :377 is dead work: tris_gt is never read)
         gts = a
@@ -369,8 +369,15 @@ class OracleEvalModel:
         bgs = bg.flip([2]) * self.IMG_SCALE
         scaled_imgs = fgs * gts + bgs * (1.0 - gts)
         tri3_gt = torch.stack([trimap_from_alpha(gts[b], self.radius) for b in range(gts.shape[0])])
+        if tri is not None:                                # :395-396 user trimap image, BGR 0..255 -> (bg, un, fg) in [0,1]
+            tri = tri.flip([2]) * self.IMG_SCALE
+        elif tri_gt is not None:                           # :397-399 make_trimap_gt(None, trimap3=tri): argmax -> one-hot
+            tri = tri_gt
+            tri3_gt = F.one_hot(tri_gt.max(dim=2)[1], 3).permute(0, 1, 4, 2, 3).float()
+        else:                                              # :400-401
+            tri = tri3_gt
         img = scaled_imgs.squeeze(0)                       # [1,3,H,W]
-        tri_ = tri3_gt.squeeze(0)                          # [1,3,H,W]
+        tri_ = tri.squeeze(0)                              # [1,3,H,W]
         img, pad = pad_to(img, 32)                         # :408
         if sum(pad) > 0:                                   # :409-410 pad bg with 1, others with 0
             tri_ = torch.cat((F.pad(tri_[:, :1], pad, value=1.0), F.pad(tri_[:, 1:], pad, value=0.0)), 1)

@@ -54,6 +54,7 @@ SIGNATURES = {
     "otvm_launch_count": (c_i64, []),
     "otvm_device_is_sm100": (C.c_int, [C.c_int]),
     "otvm_set_pdl": (None, [C.c_int]),
+    "otvm_device_error_flags": (C.c_int, [C.c_int]),
     "otvm_zero_async": (C.c_int, [c_vp, c_i64, c_vp]),
     "otvm_conv2d": (C.c_int, [C.POINTER(ConvParams), c_vp]),
     "otvm_conv2d_uses_tensor_cores": (C.c_int, [C.POINTER(ConvParams)]),

@@ -23,14 +23,24 @@ bool pdl_enabled() {
   return g_pdl == 1;
 }
 
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
+  static int n[64] = {};
+  const int dev = current_device();
+  if (dev < 0 || dev >= 64) return 148;
+  if (n[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      cudaGetLastError();
+      v = 148;
+    }
+    n[dev] = v;
   }
-  return n;
+  return n[dev];
 }
 
 int conv2d_simt(const otvm_conv_params* p, cudaStream_t s);

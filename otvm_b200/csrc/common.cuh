@@ -178,7 +178,19 @@ inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, si
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
-// number of SMs of the current device (cached)
+// number of SMs of the CURRENT device (cached per device: several devices may be used from one process)
 int sm_count();
+int current_device();                        // cudaGetDevice, -1 on failure
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: remember per (kernel, device) that it was done
+template <auto Kernel>
+inline cudaError_t ensure_dynamic_smem(int bytes) {
+  static bool done[64] = {};
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
+}
 
 }  // namespace otvm

@@ -172,11 +172,7 @@ static int edt_launch(const uint8_t* seed, int H, int W, int nmask, int* d2, int
   OTVM_LAUNCH_CHECK();
   const size_t smem = (size_t)H * 32 * sizeof(int);
   if (smem > 200 * 1024) return OTVM_ERR_UNSUPPORTED;
-  static bool attr = false;
-  if (!attr) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(edt_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  OTVM_CUDA_CHECK((ensure_dynamic_smem<edt_cols_kernel>(200 * 1024)));
   int ysplit = ceil_div(2 * sm_count(), ceil_div(W, 32) * nmask);
   if (ysplit > 32) ysplit = 32;
   if (ysplit < 1) ysplit = 1;

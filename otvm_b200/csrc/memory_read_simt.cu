@@ -250,14 +250,7 @@ static int read_simt_t(const otvm_read_params* p, cudaStream_t s) {
   a.ml_part = a.o_part + (int64_t)a.nsplit * p->HW * p->Do;
   a.ps = dtype_plane_stride(p->dtype);
   size_t smem = sizeof(float) * (RQ * QP + RK * QP + RQ * PP + RDV * PP);
-  static bool attr_set = false;
-  if (!attr_set) {
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bx<2>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_simt_kernel<bx<3>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  OTVM_CUDA_CHECK((ensure_dynamic_smem<memory_read_simt_kernel<T>>((int)smem)));
   dim3 grid(ceil_div(p->HW, RQ), p->Do / RDV, a.nsplit);
   launch_k(memory_read_simt_kernel<T>, grid, 256, smem, s, a);
   OTVM_LAUNCH_CHECK();

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
   uint64_t* p_empty = p_full + 2;          // 2
   uint64_t* o_done = p_empty + 2;          // 1
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
-  bf16* xmax = reinterpret_cast<bf16*>(smem + kOffAux + 256);          // [2 S buffers][4 subs][128 rows], 2 KB
+  float* xmax = reinterpret_cast<float*>(smem + kOffAux + 256);        // [4 subs][128 rows] fp32 row-max exchange, 2 KB
   float* xsum = reinterpret_cast<float*>(smem + kOffAux + 256);        // the same bytes after the loop: [3][128] row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -260,13 +260,15 @@ __global__ void __launch_bounds__(kReadThreads, 1) memory_read_tc_kernel(const _
         for (int i = 4; i < KQ; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(raw[i]));
         mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
       }
-      // the exchanged maxima are rounded UP to bf16 (the buffer must fit beside 224 KB of tiles): any common value
-      // >= the true maximum is a valid softmax reference, and all four threads read the same four numbers
-      bf16* xrow = xmax + (size_t)sb * 4 * TQ + r;         // [sb][sub][row]
-      xrow[sub * TQ] = __float2bfloat16_ru(mx);
+      // The four threads of a row exchange their maxima in fp32 through ONE buffer (2 KB is all that is left beside
+      // 224 KB of tiles), so a second barrier keeps a fast warp from overwriting it for the next super-block.  (Round 1
+      // exchanged bf16 values rounded up in two buffers: with logits of 1e5 and more -- undamped random weights -- the
+      // 2^-8 slack pushed every probability of a row below 2^-126 and the row came out 0/0.)
+      float* xrow = xmax + r;                              // [sub][row]
+      xrow[sub * TQ] = mx;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory");         // the four warps of this lane quarter
-      mx = fmaxf(fmaxf(__bfloat162float(xrow[0]), __bfloat162float(xrow[TQ])),
-                 fmaxf(__bfloat162float(xrow[2 * TQ]), __bfloat162float(xrow[3 * TQ]))) * scale;   // scale > 0
+      mx = fmaxf(fmaxf(xrow[0], xrow[TQ]), fmaxf(xrow[2 * TQ], xrow[3 * TQ])) * scale;            // scale > 0
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + qd) : "memory");
       if (dbg && threadIdx.x == 64 && J == 4) dbg[57] = clock64();
       // lazy rescale: keep the stale max unless it is exceeded by more than 2^8 (p stays <= 256, exact in fp32 sums)
       const bool grow = mx > m_used + kLazyLog2;
@@ -456,7 +458,7 @@ static int memory_read_tc_np(const otvm_read_params* p, cudaStream_t s) {
     uint32_t box[3] = {KB, TDV, 1};
     int rc = make_tmap_bf16(&tmV, p->vals, 3, dims, str, box, vswz); if (rc) return rc;
   }
-  OTVM_CUDA_CHECK(cudaFuncSetAttribute(memory_read_tc_kernel<NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+  OTVM_CUDA_CHECK((ensure_dynamic_smem<memory_read_tc_kernel<NP>>((int)Cfg::kSmem)));
   dim3 grid(ceil_div(p->HW, TQ), p->Do / TDV, a.nsplit);
   CUtensorMap tmO;
   {   // fp32 partial outputs [nsplit][HW][Do]: 32-float (128-byte) rows, 128-row boxes, clipped at HW

@@ -289,6 +289,7 @@ class Engine:
         self.workspaces: Dict[str, torch.Tensor] = {}      # split-K scratch per stream tag (shared by all plans)
         self.bank_capacity = bank_capacity
         self.plans: Dict[tuple, FramePlan] = {}
+        self.max_plans = max(1, int(os.environ.get("OTVM_MAX_PLANS", "3")))
         self.use_graphs = os.environ.get("OTVM_CUDA_GRAPHS", "1") != "0"
         # deferred memorize: frame t's Encoder_M / KV_M pass (STM.py:201-228) only feeds frame t+1's Memory.read, so
         # it is issued at the START of frame t+1 on a side stream, concurrently with Encoder_Q / KV_Q of t+1 (both
@@ -321,8 +322,25 @@ class Engine:
     def plan(self, H, W) -> FramePlan:
         k = (H, W)
         if k not in self.plans:
+            self._evict(k)
             self.plans[k] = self._new_plan(H, W, 32, self._dry_frame)
+        elif next(reversed(self.plans)) != k:
+            self.plans[k] = self.plans.pop(k)              # most recently used last
         return self.plans[k]
+
+    def _evict(self, incoming):
+        """at most ``max_plans`` frame sizes stay resident (OTVM_MAX_PLANS, default 3): a plan owns every activation
+        buffer, its memory bank and its CUDA graphs (GBs at 1024^2), and a dataset walks through many resolutions.
+        The least recently used plan goes first; its memories go with it (the reference drops them per clip too)."""
+        while len(self.plans) >= self.max_plans:
+            old = next(iter(self.plans))
+            pl = self.plans.pop(old)
+            for g in [g for g in self.graphs if (g[0], g[1]) == (pl.H, pl.W)]:
+                del self.graphs[g]
+                self.graph_launches.pop(g, None)
+            self.warm.discard((pl.H, pl.W))
+            self.seen = {g for g in self.seen if (g[0], g[1]) != (pl.H, pl.W)}
+            del pl
 
     def bank(self, pl: FramePlan) -> MemoryBank:
         if pl.bank is None:
@@ -518,6 +536,7 @@ class Engine:
         """buffers for STM.memorize / STM.segment called on their own: pad to 16 (STM.py:204,241), not 32"""
         k = ("stm", H, W)
         if k not in self.plans:
+            self._evict(k)
             self.plans[k] = self._new_plan(H, W, 16, self._dry_stm)
         return self.plans[k]
 

@@ -8,8 +8,9 @@ reference does not exist) without shipping 296 MB of weights.
 
 Two kinds (SURVEY.md §7 hard part 1):
 
-Both kinds damp the last norm of every residual branch (a random WS+GN ResNet is otherwise chaotic, see the
-comment in ``make_state_dict``).
+``"default"`` and ``"tempered"`` damp the last norm of every residual branch (a random WS+GN ResNet is otherwise
+chaotic, see the comment in ``make_state_dict``); ``"undamped"`` is the plain He-style draw with nothing scaled down
+(SURVEY.md section 8(d) as written), used by one parity test that reports what an un-conditioned network does.
 
 * ``"default"``  – He-style fan-in scaling.  Like the reference's own random init the attention is badly
   conditioned: the logits span several hundred, so the space-time softmax is almost one-hot and the
@@ -50,8 +51,9 @@ def _const(name: str, shape):
 
 
 def make_state_dict(kind: str = "tempered", seed: int = 111) -> "OrderedDict[str, torch.Tensor]":
-    assert kind in ("default", "tempered")
+    assert kind in ("default", "tempered", "undamped")
     temper = kind == "tempered"
+    damp = kind != "undamped"
     out: "OrderedDict[str, torch.Tensor]" = OrderedDict()
     for name, e in state_spec().items():
         r = _rs(name, seed)
@@ -72,9 +74,9 @@ def make_state_dict(kind: str = "tempered", seed: int = 111) -> "OrderedDict[str
             v = r.uniform(0.6, 1.4, e.shape).astype(np.float32)
             last = name.endswith(".bn3.weight") or name.endswith(".downsample.1.weight") \
                 or (name.startswith("NET.refine.layer") and name.endswith(".bn2.weight"))
-            if last and name.startswith("trimap."):
+            if damp and last and name.startswith("trimap."):
                 v *= np.float32(0.5)                   # keep the un-normalised BN residual stacks bounded
-            if last and name.startswith("NET.") and not name.endswith(".downsample.1.weight"):
+            if damp and last and name.startswith("NET.") and not name.endswith(".downsample.1.weight"):
                 # A random WS+GN ResNet is chaotic: zero-mean standardised weights cancel the mean of the
                 # post-ReLU activations, so relative noise grows ~1.2x per layer (bf16 rounding reaches 40 %
                 # rms at layer4).  Damping the residual branches keeps the amplification near 10x.
@@ -93,12 +95,20 @@ def make_state_dict(kind: str = "tempered", seed: int = 111) -> "OrderedDict[str
     return out
 
 
-def make_frame(clip: int, i: int, H: int, W: int):
+def make_frame(clip: int, i: int, H: int, W: int, uniform: bool = False):
     """Synthetic eval.py batch (``eval.py:162-176``): ``a [1,1,1,H,W]`` soft disc in [0,1],
     ``fg, bg [1,1,3,H,W]`` BGR in [0,255).  Frames are smooth (low-frequency colour fields plus mild
-    noise) and the disc drifts with ``i`` so consecutive frames resemble a video."""
+    noise) and the disc drifts with ``i`` so consecutive frames resemble a video.  ``uniform=True``: fg / bg are
+    i.i.d. U[0,255) per pixel and the disc is centred (SURVEY.md section 8(d) as written: white-noise images)."""
     r = np.random.RandomState((clip * 10000 + i) & 0xFFFFFFFF)
     yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    if uniform:
+        fgu = r.uniform(0.0, 255.0, (3, H, W)).astype(np.float32)
+        bgu = r.uniform(0.0, 255.0, (3, H, W)).astype(np.float32)
+        radu = np.sqrt((yy - H / 2) ** 2 + (xx - W / 2) ** 2)
+        au = 1.0 - np.clip((radu - H / 4) / (H / 12), 0.0, 1.0)
+        tu = lambda x, c: torch.from_numpy(np.ascontiguousarray(x, np.float32)).view(1, 1, c, H, W)
+        return tu(au, 1), tu(np.minimum(fgu, 254.99), 3), tu(np.minimum(bgu, 254.99), 3)
 
     def field():
         img = np.zeros((3, H, W), np.float32)
@@ -117,3 +127,19 @@ def make_frame(clip: int, i: int, H: int, W: int):
     a = 1.0 - np.clip((rad - H / 4) / (H / 12), 0.0, 1.0)
     t = lambda x, c: torch.from_numpy(np.ascontiguousarray(x, np.float32)).view(1, 1, c, H, W)
     return t(a, 1), t(fg, 3), t(bg, 3)
+
+
+def user_trimap(kind: str, H: int, W: int):
+    """frame-0 trimap a user would draw (eval.py:165-170): a disc-shaped unknown band that is NOT the one derived from
+    the frame's alpha.  kind 'tri': BGR image 0..255 with soft (anti-aliased) class edges, 'tri_gt': one-hot (bg, un, fg)."""
+    yy, xx = np.meshgrid(np.arange(H, dtype=np.float32), np.arange(W, dtype=np.float32), indexing="ij")
+    rad = np.sqrt((yy - 0.47 * H) ** 2 + (xx - 0.52 * W) ** 2)
+    fg = np.clip((0.20 * H - rad) / 3.0 + 0.5, 0.0, 1.0)
+    bg = np.clip((rad - 0.33 * H) / 3.0 + 0.5, 0.0, 1.0)
+    un = 1.0 - fg - bg
+    soft = np.stack([bg, un, fg]).astype(np.float32)                       # (bg, unknown, fg)
+    if kind == "tri_gt":
+        cls = soft.argmax(0)
+        return torch.from_numpy(np.eye(3, dtype=np.float32)[cls].transpose(2, 0, 1).copy()).view(1, 1, 3, H, W)
+    img = np.round(soft[::-1] * 255.0).astype(np.float32)                  # the model flips channel order (:396)
+    return torch.from_numpy(img.copy()).view(1, 1, 3, H, W)

@@ -184,6 +184,12 @@ class EvalModel(nn.Module):
                 memorize=False, max_memory_num=2, large_input=False):
         if a.shape[0] != 1 or a.shape[1] != 1:
             raise NotImplementedError("eval.py feeds one frame at a time (batch 1, sample length 1)")
+        if self.DILATION_KERNEL is None:
+            # the reference draws a random radius in [0, 25] per call when none is given (models/alpha/model.py:352-354);
+            # eval.py always passes one (eval.py:67-72), and a random trimap width has no parity meaning
+            raise NotImplementedError("dilate_kernel=None (random trimap width) is a training-time option; pass the radius")
+        if self.EPS != 0:
+            raise NotImplementedError("eps != 0 (models/alpha/model.py:345-346) is not implemented; eval.py uses EPS = 0")
         eng = self.engine
         H, W = a.shape[-2:]
         dev = self.IMG_MEAN.device

@@ -53,6 +53,11 @@ PROFILER: "Profiler | None" = None
 PROFILE_SHAPES = False          # dev: one profiler key per conv shape
 
 
+def device_error_flags(clear: bool = True) -> int:
+    """sticky device-side error flags (synchronises): bit 0 = a GroupNorm-fused convolution's grid barrier timed out"""
+    return int(_lib.load().otvm_device_error_flags(int(clear)))
+
+
 def launch_count() -> int:
     return int(_lib.load().otvm_launch_count())
 

@@ -80,14 +80,18 @@ def tr_pad(x, Hp, Wp):
     return x
 
 
-def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=True, with_mean=False):
+def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=True, with_mean=False, uniform=False,
+             bank_fill=0):
+    """``bank_fill`` = T > 1: after frame 0 the oracle's bank is grown to T entries (frame 0's memory repeated with a
+    deterministic per-slot perturbation) and forced into the engine, so the next frames read a T-frame bank without
+    running T frames first (1024x1024 / T=16 in seconds)."""
     import otvm_oracle as O
     from otvm_b200.fixtures import make_frame
     model, sd = build_model(kind, precision)
     oracle = O.OracleEvalModel(sd, dilate_kernel=12)
     rows = []
     for i in range(n_frames):
-        a, fg, bg = make_frame(0, i, H, W)
+        a, fg, bg = make_frame(0, i, H, W, uniform=uniform)
         kw = dict(first_frame=(i == 0), last_frame=False, memorize=memorize, max_memory_num=max_mem)
         ref = oracle(a, fg, bg, **kw)
         out = model(a.cuda(), fg.cuda(), bg.cuda(), **kw)
@@ -96,6 +100,12 @@ def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=
         if with_mean:
             e = {k: (v, m) for (k, v), m in zip(e.items(), compare_frame(model, oracle, out, ref, H, W, i == 0, rel_err=mean_err).values())}
         rows.append(e)
-        if teacher:
+        if i == 0 and bank_fill > 1:
+            g = torch.Generator().manual_seed(7)
+            for k in ("key", "val"):
+                m = oracle.memories[k].repeat(1, 1, 1, bank_fill, 1, 1)
+                scale = 1.0 + 0.05 * torch.randn(1, 1, 1, bank_fill, 1, 1, generator=g)
+                oracle.memories[k] = m * scale + 0.05 * m.std() * torch.randn(m.shape, generator=g)
+        if teacher or (i == 0 and bank_fill > 1):
             force_bank(model, oracle, H, W)
     return rows

@@ -543,3 +543,37 @@ def test_conv1x1_on_ppm_cells(s, dtype):
     q = rnd(dtype, nchw(out))[0].double().reshape(32, -1)
     assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 1e-5
     assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 1e-5
+
+
+def test_fused_groupnorm_next_to_foreign_work():
+    """the grid-synchronising GroupNorm-fused convolution while ANOTHER stream keeps the SMs busy (cuBLAS GEMMs the
+    library knows nothing about): its CTAs become resident late, the bounded barrier must simply wait (no trap, no
+    error flag) and the results must equal the quiet run"""
+    ops = _ops()
+    dtype = X2
+    g = torch.Generator().manual_seed(3)
+    Cin, Cout, H, W = 64, 256, 128, 128                       # 256 CTAs: two per SM
+    x = torch.randn(1, Cin, H, W, generator=g); w = torch.randn(Cout, Cin, 1, 1, generator=g) / 8
+    gamma, beta = torch.rand(Cout, generator=g) + 0.5, torch.randn(Cout, generator=g)
+    xd, wd = nhwc(x, dtype), wpack(w, dtype)
+    y = F.relu(F.group_norm(F.conv2d(rnd(dtype, x), rnd(dtype, w)), 32, gamma, beta, 1e-5))
+
+    def run():
+        arena = torch.zeros(72, dtype=torch.float64, device=DEV)
+        out = zeros((1, H, W, Cout), dtype); raw = zeros((1, H, W, Cout), dtype)
+        fused = ops.conv2d(xd, wd, None, out, gn_stats=arena, gn_stats_zeroed=True,
+                           gn_fuse=(gamma.to(DEV), beta.to(DEV), 1e-5), gn_raw_out=raw, act=ops.ACT_RELU)
+        assert fused is True
+        return out
+
+    assert ops.device_error_flags() == 0
+    side = torch.cuda.Stream()
+    a = torch.randn(8192, 8192, device=DEV, dtype=torch.bfloat16)
+    with torch.cuda.stream(side):
+        for _ in range(40):
+            a @ a                                             # ~1 ms each, every SM
+    outs = [run() for _ in range(24)]
+    torch.cuda.synchronize()
+    assert ops.device_error_flags() == 0, "grid barrier of the fused GroupNorm timed out"
+    for o in outs[::7]:
+        assert rel_err(nchw(o), y) < 1e-4

@@ -197,3 +197,48 @@ def test_bench_reference_arm_contract():
     r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference"], capture_output=True, text=True,
                         timeout=600, env=dict(env, RANK="1", WORLD_SIZE="2"))
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_dropin_runs_the_eval_py_sequence(tmp_path):
+    """eval.py:15,41-94 with otvm_b200/dropin first on PYTHONPATH: the REFERENCE's own helpers.py (`from helpers import *`)
+    builds the models through its lazy `import models.trimap.model` / `import models.alpha.model`, which resolve to the
+    B200 classes; strict load_state_dict, DataParallel wrap, model.eval(), format_time -- everything eval.py's main()
+    touches before and after the clip loop.  (A forward needs a GPU: it must raise here, not fall back.)"""
+    script = r'''
+import os, sys, types
+_popen = os.popen
+class _Fake:
+    def read(self): return "24 80"
+os.popen = lambda cmd, *a, **k: _Fake() if str(cmd).startswith("stty") else _popen(cmd, *a, **k)   # helpers.py:211 needs a TTY
+import torch
+from torch import nn
+from helpers import *                                    # eval.py:15 -- the reference's helpers
+import helpers, models.alpha.model as ma_mod, models.trimap.model as mt_mod
+assert helpers.__file__.startswith("/root/reference"), helpers.__file__
+assert "otvm_b200/dropin" in ma_mod.__file__ and "otvm_b200/dropin" in mt_mod.__file__
+cfg = types.SimpleNamespace(TRAIN=types.SimpleNamespace(STAGE=4), SYSTEM=types.SimpleNamespace(RANDOM_SEED=111))
+MODEL = get_model_name(cfg)                              # eval.py:46
+assert MODEL == "s4_OTVM"
+model_trimap = get_model_trimap(cfg, mode='Test', dilate_kernel=12)          # eval.py:74
+model = get_model_alpha(cfg, model_trimap, mode='Test', dilate_kernel=12)    # eval.py:75
+import otvm_b200.models as M
+assert isinstance(model, M.EvalModel) and isinstance(model_trimap, M.FullModel_eval)
+from otvm_b200.fixtures import make_state_dict, make_frame
+model.load_state_dict(make_state_dict("tempered"))       # eval.py:79 (strict)
+model = nn.DataParallel(model)                           # eval.py:80 (no device here: DataParallel is a pass-through)
+model.eval()                                             # eval.py:118
+assert model.module.memories == {"key": None, "val": None}
+a, fg, bg = make_frame(0, 0, 64, 64)
+try:
+    model(a, fg, bg, tri=None, tri_gt=None, first_frame=True, last_frame=False, memorize=False, max_memory_num=5, large_input=False)
+    raise SystemExit("forward ran without a CUDA device: there must be no CPU fallback")
+except RuntimeError as e:
+    assert "CUDA" in str(e), e
+print("done | Total time: {}".format(format_time(12.5)))  # eval.py:94
+'''
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "otvm_b200", "dropin"), ROOT, "/root/reference"]),
+               CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "done | Total time:" in r.stdout

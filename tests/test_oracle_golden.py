@@ -97,6 +97,23 @@ def test_clip_tempered_512_T8():
     _check_clip("clip_tempered_512_T8", "tempered")
 
 
+def test_user_trimap_first_frame():
+    """frame 0 seeded by ``tri=`` (BGR trimap image) or ``tri_gt=`` (one-hot), models/alpha/model.py:395-401: the oracle
+    against the unmodified reference's outputs (tests/golden/user_trimap_128.npz), both frames of each clip"""
+    from otvm_b200.fixtures import make_frame, user_trimap
+    g = golden("user_trimap_128")
+    sd = make_state_dict("tempered")
+    for kind in ("tri", "tri_gt"):
+        model = O.OracleEvalModel(sd, dilate_kernel=12)
+        for i in range(2):
+            a, fg, bg = make_frame(3, i, 128, 128)
+            kw = {kind: user_trimap(kind, 128, 128)} if i == 0 else {}
+            out = model(a, fg, bg, first_frame=(i == 0), last_frame=False, memorize=True, max_memory_num=8, **kw)
+            assert rel_err(out[3][0, 0, 0], g[f"{kind}_f{i}_alpha"]) < TOL, (kind, i)
+            assert rel_err(out[1][0, 0], g[f"{kind}_f{i}_trimap"]) < TOL, (kind, i)
+            assert rel_err(out[2][0, 0], g[f"{kind}_f{i}_tri_gt"]) < TOL, (kind, i)
+
+
 def _stm_standalone_inputs(H=88, W=120, seed=5):
     """same draw as oracle/make_golden.py::stm_standalone_inputs and tests/test_gpu_frames.py"""
     g = torch.Generator().manual_seed(seed)
