@@ -1037,8 +1037,7 @@ static int pick_bn(const otvm_conv_params* p) {
     const int64_t tiles = (int64_t)ceil_div(Wo, tw) * ceil_div(Ho, 128 / tw) * p->N;
     const int kc = p->Cin % 64 == 0 ? 64 : p->Cin % 32 == 0 ? 32 : 16;
     const int num_k = p->KH * p->KW * (p->Cin / kc);            // long-K layers keep 128 and slice K instead (split-K)
-    const int planes = dtype_planes(p->dtype), npair = planes == 1 ? 1 : planes == 2 ? 3 : 6;
-    if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k * npair < 48) bn = 64;
+    if (tiles * ceil_div(Cout, 128) * 2 <= sm_count() && num_k < 48) bn = 64;
     // (32-channel tiles on the even smaller grids measured slower: 429.6 vs 433.2 frames/s)
   }
   return bn;
@@ -1278,8 +1277,10 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   // blockIdx.z, write fp32 partial tiles to the caller's workspace and finish with a small fused-epilogue kernel
   int nsplit = 1;
   const int64_t Mtot = (int64_t)p->N * a.Ho * a.Wo;
-  // (split operands: a K iteration carries npair plane products, so the serial walk is that much longer per iteration)
-  const int num_kp = num_k * a.npair;
+  // (measured with split operands, 3 plane products per K iteration: lowering this threshold to num_k * 3 >= 48 made the
+  // 16-36 iteration layers SLOWER, 206 vs 224 frames/s -- they are bound by their fixed costs, not by the K walk, and the
+  // workspace round trip + finish kernel add to those)
+  const int num_kp = num_k;
   if (p->workspace && ctas * 2 <= sm_count() && num_kp >= 48 && p->Cout % 4 == 0 &&
       (!p->res || p->res_ld % 4 == 0) && (!p->out_relu || p->out_relu_ld % 4 == 0)) {
     nsplit = (int)(sm_count() / ctas);

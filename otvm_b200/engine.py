@@ -290,6 +290,8 @@ class Engine:
         self.bank_capacity = bank_capacity
         self.plans: Dict[tuple, FramePlan] = {}
         self.max_plans = max(1, int(os.environ.get("OTVM_MAX_PLANS", "3")))
+        self.copy_stream_enabled = os.environ.get("OTVM_COPY_STREAM", "1") != "0"
+        self.copy_stream = None
         self.use_graphs = os.environ.get("OTVM_CUDA_GRAPHS", "1") != "0"
         # deferred memorize: frame t's Encoder_M / KV_M pass (STM.py:201-228) only feeds frame t+1's Memory.read, so
         # it is issued at the START of frame t+1 on a side stream, concurrently with Encoder_Q / KV_Q of t+1 (both
@@ -525,6 +527,41 @@ class Engine:
         self._conv(pl, "trimap.model.KV_M_r4.Key", r4, out=kdst, pad=1)
         fv.join()
 
+    def _stage_inputs(self, pl: FramePlan, a, fg, bg):
+        """bring a / fg / bg into the plan's static input buffers (what the CUDA graphs read).
+
+        Host tensors (eval.py hands the loader's CPU tensors over) go through a COPY STREAM into one of two staging
+        sets: the H2D of frame t+1 (7 fp32 planes, 7.3 MB at 512^2) then overlaps the kernels of frame t instead of
+        sitting in front of them on the compute stream, and only a device-to-device copy (a few us) stays in stream
+        order.  A staging set is reused once the D2D copy that last read it has been issued two frames earlier."""
+        H, W = pl.H, pl.W
+        f32 = torch.float32
+        dst = [pl.buf("in_a", (H, W), f32), pl.buf("in_fg", (3, H, W), f32), pl.buf("in_bg", (3, H, W), f32)]
+        src = [a, fg, bg]
+        if all(t.device.type == "cuda" for t in src) or not self.copy_stream_enabled:
+            for d, t in zip(dst, src):
+                d.copy_(t, non_blocking=True)
+            return
+        if self.copy_stream is None:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+        k = pl.stage_idx = (getattr(pl, "stage_idx", 1) + 1) % 2
+        stage = [pl.buf(f"stage{k}.{n}", tuple(d.shape), f32) for n, d in zip("afb", dst)]
+        cur = torch.cuda.current_stream()
+        if not hasattr(pl, "stage_done"):
+            pl.stage_done = [None, None]
+        with torch.cuda.stream(self.copy_stream):
+            if pl.stage_done[k] is not None:
+                self.copy_stream.wait_event(pl.stage_done[k])       # the D2D copy of frame t-2 has read this set
+            for d, t in zip(stage, src):
+                d.copy_(t, non_blocking=True)                       # pinned source: truly asynchronous
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        cur.wait_event(ready)
+        for d, t in zip(dst, stage):
+            d.copy_(t, non_blocking=True)
+        pl.stage_done[k] = torch.cuda.Event()
+        pl.stage_done[k].record(cur)
+
     def flush(self, pl: FramePlan):
         """Run a deferred memorize pass now (anything that looks at the bank outside ``frame`` calls this)."""
         if pl.pending is not None:
@@ -732,10 +769,7 @@ class Engine:
         H, W = a.shape[-2:]
         pl = self.plan(H, W)
         bank = self.bank(pl)
-        f32 = torch.float32
-        pl.buf("in_a", (H, W), f32).copy_(a, non_blocking=True)
-        pl.buf("in_fg", (3, H, W), f32).copy_(fg, non_blocking=True)
-        pl.buf("in_bg", (3, H, W), f32).copy_(bg, non_blocking=True)
+        self._stage_inputs(pl, a, fg, bg)
         if first_frame:
             bank.reset()
             pl.pending = None                        # the reference drops the old memories too (:425-429)
