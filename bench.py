@@ -305,6 +305,7 @@ def run_b200(args):
                             "conv_tflops_algorithmic": round(CONV_GFLOP_512 * 4 / (ms / 24), 1)}
             del c
             torch.cuda.empty_cache()
+        line["frame_io"] = frame_io_bench(model.precision)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], line["parity"] = run_reference_sample(3, 1, parity_precision=model.precision)
     if rank == 0:
@@ -354,6 +355,64 @@ def read_microbench(precision, pk):
             "hbm_frac": round(nbytes / (ms * 1e-3) / 1e9 / pk["hbm"], 4),
             "workload": "512x512 frame, T=16: HW=1024 queries x THW=16384 memory locations, L2 flushed between launches",
             "plane_products_per_k_step": 1 if planes == 1 else 3, "ffma": simt, "peak_source": pk["src"]}
+
+
+def frame_io_bench(precision, n=96):
+    """the same clip from PNG files to PNG mattes, (a) with otvm_b200.frame_io (decoder /
+    writer threads, 8-bit transfers, device-side unpack / conversion) and (b) the way eval.py does it (decode, fp32
+    conversion and upload, synchronous fp32 read-back, host conversion and imwrite on the main thread,
+    dataset.py:857-920 + eval.py:195-217).  Same model, same frames; frames/s of the whole loop."""
+    import shutil
+    import tempfile
+    try:
+        import cv2
+        import numpy as np
+    except Exception as e:                      # no OpenCV on this box: nothing to measure
+        return {"unavailable": repr(e)}
+    from otvm_b200.frame_io import run_sequence
+    d = tempfile.mkdtemp(prefix="otvm_io_")
+    try:
+        r = np.random.RandomState(0)
+        yy, xx = np.mgrid[0:H, 0:W]
+        base_f = r.randint(0, 256, (H, W, 4)).astype(np.uint8); base_b = r.randint(0, 256, (H, W, 3)).astype(np.uint8)
+        fgs, bgs = [], []
+        for i in range(n):
+            f = np.roll(base_f, 3 * i, axis=1)
+            f[..., 3] = np.clip(255 - (np.hypot(yy - H / 2, xx - W / 2 - i) - H / 4) * 12, 0, 255).astype(np.uint8)
+            fp, bp = os.path.join(d, f"fg_{i:04d}.png"), os.path.join(d, f"bg_{i:04d}.png")
+            cv2.imwrite(fp, f); cv2.imwrite(bp, np.roll(base_b, 2 * i, axis=0))
+            fgs.append(fp); bgs.append(bp)
+        model = build(precision)
+        kw = dict(max_memory_num=T_MEM, memory_skip_frame=1)
+        run_sequence(model, fgs[:12], bgs[:12], os.path.join(d, "warm"), **kw)       # graphs / plans
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_sequence(model, fgs, bgs, os.path.join(d, "out"), **kw)
+        torch.cuda.synchronize()
+        t_pipe = time.perf_counter() - t0
+        os.makedirs(os.path.join(d, "ref"), exist_ok=True)
+        t0 = time.perf_counter()
+        for i in range(n):                      # eval.py's own sequence of host steps around the same model
+            _f = cv2.imread(fgs[i], cv2.IMREAD_UNCHANGED)
+            fg = np.float32(_f[..., :-1]); a = np.float32(_f[..., -1:]) / 255.
+            bg = np.float32(cv2.imread(bgs[i], cv2.IMREAD_COLOR))
+            t = lambda x: torch.from_numpy(x).permute(2, 0, 1).unsqueeze(0).unsqueeze(0).float()
+            torch.cuda.synchronize()
+            out = model(t(a).cuda(), t(fg).cuda(), t(bg).cuda(), first_frame=(i == 0), last_frame=(i == n - 1),
+                        memorize=False, max_memory_num=T_MEM)
+            torch.cuda.synchronize()
+            img = (out[3] * 255).byte().cpu().squeeze(0).squeeze(0).squeeze(0).numpy()
+            cv2.imwrite(os.path.join(d, "ref", f"fg_{i:04d}.png"), img)
+        t_ref = time.perf_counter() - t0
+        same = all(np.abs(cv2.imread(os.path.join(d, "out", f"fg_{i:04d}.png"), cv2.IMREAD_UNCHANGED).astype(int) -
+                          cv2.imread(os.path.join(d, "ref", f"fg_{i:04d}.png"), cv2.IMREAD_UNCHANGED).astype(int)).max() <= 1
+                   for i in range(0, n, 7))
+        return {"value": round(n / t_pipe, 2), "unit": "frames/s", "frames": n, "frame": [H, W],
+                "what": "PNG files -> decode -> model -> 8-bit matte -> PNG files, wall clock of the whole clip",
+                "pipelined": "otvm_b200.frame_io: 2 decoder + 2 writer threads, 7 B/px upload, 1 B/px read-back",
+                "eval_py_style_host_loop": round(n / t_ref, 2), "outputs_match": bool(same)}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def run_reference_sample(steps, warmup, parity_precision=None):

@@ -219,6 +219,18 @@ OTVM_API int otvm_frame_outputs(const float* raw10, int64_t raw_ld, const float*
                        int32_t pad_top, int32_t pad_left, const float* mean_std, void* mem_in, int64_t mem_ld,
                        int32_t dtype, float* alpha_out, float* trimap_out, void* stream);
 
+/* ---- frame I/O around the loop -----------------------------------------
+ * The reference decodes each frame on the host into fp32 tensors (dataset.py:857-920: cv2.imread, np.float32, / 255,
+ * HWC -> CHW) and reads the matte back as fp32 before converting it (eval.py:209: (alphas * 255).byte()).  Here the
+ * decoded 8-bit images are uploaded as they are and unpacked on the device, and the matte returns as 8 bits.
+ *   fg  : [H*W][fg_channels] u8, BGR(A) as cv2.imread(IMREAD_UNCHANGED) returns it; bg: [H*W][3] u8 BGR
+ *   a   : [H*W] fp32 = A / 255 (1.0 without an alpha channel);  fg_out / bg_out: [3][H*W] fp32 planar BGR in 0..255
+ *         -- exactly the tensors EvalModel.forward takes (eval.py:162-175), bit-identical to the host decode */
+OTVM_API int otvm_unpack_frame_u8(const uint8_t* fg, int32_t fg_channels, const uint8_t* bg, int32_t H, int32_t W,
+                         float* a, float* fg_out, float* bg_out, void* stream);
+/* out[p] = (uint8)(alpha[p] * 255): the PNG eval.py:217 writes, bit-identical to (alphas * 255).byte() */
+OTVM_API int otvm_alpha_to_u8(const float* alpha, int64_t P, uint8_t* out, void* stream);
+
 /* dtype conversion / layout helpers used at the boundary (NCHW fp32 <-> NHWC dtype) */
 OTVM_API int otvm_nchw_to_nhwc(const float* in, int32_t N, int32_t C, int32_t HW, void* out, int64_t out_ld,
                       int32_t dtype, void* stream);

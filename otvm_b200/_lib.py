@@ -76,6 +76,8 @@ SIGNATURES = {
     "otvm_fba_head": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "otvm_frame_outputs": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                                      c_i32, C.POINTER(c_f), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "otvm_unpack_frame_u8": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "otvm_alpha_to_u8": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "otvm_nchw_to_nhwc": (C.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i64, c_i32, c_vp]),
     "otvm_nhwc_to_nchw": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_vp, c_i32, c_vp]),
 }

@@ -330,9 +330,54 @@ __global__ void frame_outputs_kernel(const float* __restrict__ raw10, int64_t ra
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// frame I/O around the loop (reference dataset.py:857-920 decodes on the host into fp32 tensors, eval.py:209 reads
+// the alpha back as fp32 and converts it on the host): here the decoded 8-bit images are uploaded as they are
+// (7 B / pixel instead of 28) and unpacked on the device; the matte goes back as 1 B / pixel.
+// ---------------------------------------------------------------------------------------------------
+__global__ void unpack_frame_u8_kernel(const uint8_t* __restrict__ fg, int fg_c, const uint8_t* __restrict__ bg,
+                                       int64_t P, float* __restrict__ a, float* __restrict__ fg_out,
+                                       float* __restrict__ bg_out) {
+  pdl_sync();                                  // PDL contract (common.cuh)
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* f = fg + p * fg_c;
+    const uint8_t* b = bg + p * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { fg_out[c * P + p] = (float)f[c]; bg_out[c * P + p] = (float)b[c]; }
+    // np.float32(png[..., -1:]) / 255.  (dataset.py:864): IEEE fp32 division; an image without alpha is opaque (:868)
+    a[p] = fg_c == 4 ? __fdiv_rn((float)f[3], 255.f) : 1.f;
+  }
+}
+
+__global__ void alpha_to_u8_kernel(const float* __restrict__ alpha, int64_t P, uint8_t* __restrict__ out) {
+  pdl_sync();                                  // PDL contract (common.cuh)
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    // (alphas * 255).byte()  (eval.py:209): fp32 product, conversion truncates toward zero; alpha is clamped to [0,1]
+    const float v = __fmul_rn(alpha[p], 255.f);
+    out[p] = (uint8_t)(int)fminf(fmaxf(v, 0.f), 255.f);
+  }
+}
+
 }  // namespace otvm
 
 using namespace otvm;
+
+extern "C" int otvm_unpack_frame_u8(const uint8_t* fg, int32_t fg_channels, const uint8_t* bg, int32_t H, int32_t W,
+                                    float* a, float* fg_out, float* bg_out, void* stream) {
+  if (!fg || !bg || !a || !fg_out || !bg_out || (fg_channels != 3 && fg_channels != 4) || H <= 0 || W <= 0) return OTVM_ERR_ARG;
+  const int64_t P = (int64_t)H * W;
+  launch_k(unpack_frame_u8_kernel, grid1d(P, 256), 256, 0, static_cast<cudaStream_t>(stream), fg, (int)fg_channels, bg, P, a,
+           fg_out, bg_out);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_alpha_to_u8(const float* alpha, int64_t P, uint8_t* out, void* stream) {
+  if (!alpha || !out || P <= 0) return OTVM_ERR_ARG;
+  launch_k(alpha_to_u8_kernel, grid1d(P, 256), 256, 0, static_cast<cudaStream_t>(stream), alpha, P, out);
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
 
 #define DISPATCH_DTYPE(dtype, STMT)                                            \
   do {                                                                         \

@@ -323,6 +323,18 @@ def frame_outputs(raw10, raw_ld, fused, hid, extras, Hp, Wp, H, W, pad_top, pad_
                                _dt(hid), _p(alpha_out), _p(trimap_out), _stream()), "otvm_frame_outputs"))
 
 
+def unpack_frame_u8(fg_u8, bg_u8, a, fg, bg):
+    """fg_u8 [H,W,3|4] / bg_u8 [H,W,3] uint8 (cv2.imread layout) -> a [H,W], fg / bg [3,H,W] fp32 (EvalModel inputs)"""
+    H, W, c = fg_u8.shape
+    check(_lib.load().otvm_unpack_frame_u8(_p(fg_u8), c, _p(bg_u8), H, W, _p(a), _p(fg), _p(bg), _stream()),
+          "otvm_unpack_frame_u8")
+
+
+def alpha_to_u8(alpha, out):
+    check(_lib.load().otvm_alpha_to_u8(_p(alpha), alpha.numel(), _p(out), _stream()), "otvm_alpha_to_u8")
+    return out
+
+
 def nchw_to_nhwc(x, out):
     if DRY:
         return out
