@@ -689,7 +689,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
                                                                              const __grid_constant__ CUtensorMap tmB,
                                                                              const __grid_constant__ CUtensorMap tmO,
                                                                              const ConvTcArgs a) {
-  static_assert(GN == GN_NONE || (GN == GN_STATS && BN == 64), "statistics variant: 64 channels = 32 groups of 2");
+  // statistics variant: Cout = 64 = 32 GroupNorm groups of 2 channels (host-checked); a CTA owns BN of them
+  static_assert(GN == GN_NONE || (GN == GN_STATS && BN >= 32), "statistics variant");
+  // Split operands (a.planes > 1): the filter bank holds [chunk][tap][plane] tiles, a patch-ring slot the planes of one
+  // patch, and every tile has a main + a cross-plane accumulator (2 BN columns, see conv_tc_kernel).  Two planes of a
+  // 64-channel layer do not fit one CTA (147 KB of weights alone), so such a layer runs as TWO 32-channel halves:
+  // blockIdx.y picks the half, each half's CTAs walk all tiles.
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -702,7 +707,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
   float* sbias = reinterpret_cast<float*>(tmem_slot + 2);             // [BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr uint32_t TMEM_COLS = 4 * BN;                              // two accumulators per pipeline
+  const int n0 = blockIdx.y * BN;                                     // first output channel of this CTA
+  const uint32_t nplane = (uint32_t)a.planes;
+  const uint32_t ACCW = nplane > 1 ? 2u * BN : (uint32_t)BN;          // columns per tile: main (+ cross-plane) accumulator
+  const uint32_t tmem_cols = 4u * ACCW < 32u ? 32u : 4u * ACCW;       // two tiles in flight per pipeline (power of two)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO);
@@ -711,8 +719,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
-  for (int i = threadIdx.x; i < BN; i += kPersistThreads) sbias[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+  if (warp == 1) tmem_alloc_n(tmem_slot, tmem_cols);
+  for (int i = threadIdx.x; i < BN; i += kPersistThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
@@ -721,10 +729,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     // the filter bank: 9 taps x nchunk boxes [BN x KC] behind one barrier.  Weights are never written inside a frame,
     // so this is issued BEFORE the PDL wait and overlaps the previous kernel's tail.
     if (elect_one()) {
-      mbar_arrive_expect_tx(w_full, (uint32_t)(9 * a.nchunk) * (uint32_t)(BN * a.KC * 2));
+      mbar_arrive_expect_tx(w_full, (uint32_t)(9 * a.nchunk) * (uint32_t)(BN * a.KC * 2) * nplane);
       for (int chunk = 0; chunk < a.nchunk; ++chunk)
         for (int tap = 0; tap < 9; ++tap)
-          tma_load_3d(smem + (size_t)(chunk * 9 + tap) * a.b_bytes, &tmB, w_full, tap * a.Cin + chunk * a.KC, 0, 0);
+          for (int pl = 0; pl < a.planes; ++pl)
+            tma_load_3d(smem + (size_t)(chunk * 9 + tap) * a.b_bytes + (size_t)pl * a.b_plane, &tmB, w_full,
+                        tap * a.Cin + chunk * a.KC, n0, pl);
     }
     __syncwarp();
   }
@@ -738,7 +748,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
   if (warp == 0) {
     // ===== patch producer =====
     int slot = 0; uint32_t ph = 0; int i = 0;
-    const uint32_t p_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes;
+    const uint32_t p_tx = (uint32_t)((a.TW + 2 * d) * (a.TH + 2 * d)) * a.row_bytes * nplane;
+    const uint32_t slot_bytes = nplane * a.patch_bytes;
     for (int t = blockIdx.x; t < a.ntiles; t += gridDim.x, ++i) {
       const int bq = a.tiles_x_magic ? (int)__umulhi((uint32_t)t, a.tiles_x_magic) : t;
       const int tx_i = t - bq * a.tiles_x;
@@ -749,7 +760,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
         mbar_wait(&p_empty[slot], ph ^ 1);
         if (elect_one()) {
           mbar_arrive_expect_tx(&p_full[slot], p_tx);
-          tma_load_5d(smem + a.p_off + (size_t)slot * a.patch_bytes, &tmA, &p_full[slot], chunk * a.KC, cx, cy, n_img, 0);
+          for (int pl = 0; pl < a.planes; ++pl)
+            tma_load_5d(smem + a.p_off + (size_t)slot * slot_bytes + (size_t)pl * a.patch_bytes, &tmA, &p_full[slot],
+                        chunk * a.KC, cx, cy, n_img, pl);
         }
         __syncwarp();
         if (++slot == a.na) { slot = 0; ph ^= 1; }
@@ -760,9 +773,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     // ===== MMA issuers: warp 1 takes the CTA's even tiles (accumulator 0), warp 2 the odd ones (accumulator 1) =====
     const int g = warp - 1;
     constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+    constexpr uint32_t idesc2 = make_idesc_bf16(128, 2 * BN);       // a0 . [b0 | b1] -> [main | cross] in one instruction
+    const uint32_t idesc0 = nplane > 1 ? idesc2 : idesc;
     const uint64_t adesc0 = make_smem_desc(base + a.p_off, (uint32_t)pw * a.row_bytes, a.layout_type);
     const uint64_t bdesc0 = make_smem_desc(base, a.sbo, a.layout_type);
-    const uint32_t b16 = a.b_bytes >> 4, patch16 = a.patch_bytes >> 4;
+    const uint32_t b16 = a.b_bytes >> 4, patch16 = (nplane * a.patch_bytes) >> 4;
+    const uint32_t aplane16 = a.patch_bytes >> 4, bplane16 = a.b_plane >> 4;
     const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
     mbar_wait(w_full, 0);
     // patch-ring position of this pipeline's first tile; every tile consumes nchunk consecutive slots
@@ -774,7 +790,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       const int ab = 2 * g + (j & 1);                              // the pipeline alternates between its two accumulators
       mbar_wait(&acc_empty[ab], (((uint32_t)j >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
       tcgen05_after_sync();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ab * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)ab * ACCW;
       OTVM_PSTAMP(2 * j + g, 1);
       for (int chunk = 0; chunk < a.nchunk; ++chunk) {
         mbar_wait(&p_full[slot], ph);
@@ -791,7 +807,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
               const uint64_t bd = bd0 + (uint64_t)((uint32_t)(ky * 3 + kx) * b16);
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
-                umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (chunk | ky | kx | k) != 0);
+                umma_bf16(d_tmem, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc0, (chunk | ky | kx | k) != 0);
+              // remaining cross-plane products (a1 b0 | a1 b1, a0 b2, a2 b0) into the cross accumulator
+              for (int pr = 2; pr < a.npair; ++pr) {
+                const uint64_t ap = ad + ((kPairA >> (4 * pr)) & 15u) * aplane16, bp = bd + ((kPairB >> (4 * pr)) & 15u) * bplane16;
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_bf16(d_tmem + BN, ap + (uint64_t)(2 * k), bp + (uint64_t)(2 * k), idesc, 1u);
+              }
             }
           }
           umma_commit(&p_empty[slot]);                         // all 9 taps have read this patch
@@ -812,13 +835,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     const bool leader = (warp - 3 - 4 * g) == 0 && lane == 0;   // issues this group's TMA stores
     constexpr int CH = BN >= 32 ? 32 : 16;
     constexpr uint32_t ROWB = BN * 2, MASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
-    constexpr uint32_t STAGE_BYTES = 128u * ROWB;
+    constexpr uint32_t STAGE_BYTES = 128u * ROWB;             // one plane of one output tile
+    constexpr int NG = GN == GN_STATS ? BN / 2 : 1;            // GroupNorm groups (2 channels each) of this CTA
     const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
-    uint8_t* stg = smem + a.stage_off + (size_t)g * STAGE_BYTES;
-    float s1[GN == GN_STATS ? 32 : 1], s2[GN == GN_STATS ? 32 : 1];
+    uint8_t* stg = smem + a.stage_off + (size_t)g * nplane * STAGE_BYTES;
+    float s1[NG], s2[NG];
     if constexpr (GN == GN_STATS) {
 #pragma unroll
-      for (int u = 0; u < 32; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
+      for (int u = 0; u < NG; ++u) { s1[u] = 0.f; s2[u] = 0.f; }
     }
     int j = 0;
     for (int t = blockIdx.x + g * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++j) {
@@ -838,9 +862,16 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
 #pragma unroll
       for (int c = 0; c < BN; c += CH) {
         uint32_t raw[CH];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + c);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)ab * ACCW + (uint32_t)c;
         if constexpr (CH == 32) tmem_ld32(taddr, raw); else tmem_ld16(taddr, raw);
         tmem_wait_ld();
+        if (nplane > 1) {                                      // + cross-plane accumulator
+          uint32_t raw2[CH];
+          if constexpr (CH == 32) tmem_ld32(taddr + BN, raw2); else tmem_ld16(taddr + BN, raw2);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < CH; ++e) raw[e] = __float_as_uint(__uint_as_float(raw[e]) + __uint_as_float(raw2[e]));
+        }
         float v[CH];
 #pragma unroll
         for (int e = 0; e < CH; e += 4) {
@@ -849,11 +880,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
           v[e + 2] = __uint_as_float(raw[e + 2]) + b4.z; v[e + 3] = __uint_as_float(raw[e + 3]) + b4.w;
         }
         if constexpr (GN == GN_STATS) {
-          // statistics of the values GroupNorm will read back (rounded to bf16); rows outside the image count 0
+          // statistics of the values GroupNorm will read back (one plane: rounded to bf16); rows outside the image count 0
 #pragma unroll
           for (int e = 0; e < CH; e += 2) {
-            const float q0 = valid ? __bfloat162float(__float2bfloat16_rn(v[e])) : 0.f;
-            const float q1 = valid ? __bfloat162float(__float2bfloat16_rn(v[e + 1])) : 0.f;
+            const float q0 = !valid ? 0.f : nplane > 1 ? v[e] : __bfloat162float(__float2bfloat16_rn(v[e]));
+            const float q1 = !valid ? 0.f : nplane > 1 ? v[e + 1] : __bfloat162float(__float2bfloat16_rn(v[e + 1]));
             s1[(c + e) >> 1] += q0 + q1;
             s2[(c + e) >> 1] += q0 * q0 + q1 * q1;
           }
@@ -865,13 +896,10 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
           const int cc = c + 8 * e8;
           uint32_t off = (uint32_t)r * ROWB + (uint32_t)cc * 2u;
           off ^= ((off >> 7) & MASK) << 4;
-          uint32_t pk[4];
+          float x8[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * e8 + 2 * e], v[8 * e8 + 2 * e + 1]);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h);
-          }
-          *reinterpret_cast<uint4*>(stg + off) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int e = 0; e < 8; ++e) x8[e] = v[8 * e8 + e];
+          split_store8(stg + off, STAGE_BYTES, a.planes, x8);
         }
       }
       // this warp's share of the accumulator is staged: hand the TMEM buffer back to the pipeline's MMA warp
@@ -882,7 +910,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
       asm volatile("bar.sync %0, 128;" ::"r"(3 + g) : "memory");
       if (leader) {
-        tma_store_5d(&tmO, stg, 0, x0, y0, n_img, 0);         // clips ragged tiles
+        for (uint32_t pl = 0; pl < nplane; ++pl)
+          tma_store_5d(&tmO, stg + pl * STAGE_BYTES, n0, x0, y0, n_img, (int)pl);      // clips ragged tiles
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (q == 3) OTVM_PSTAMP(2 * j + g, 6);
@@ -896,12 +925,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       float* sred = reinterpret_cast<float*>(smem + a.p_off);
       const int row = g * 128 + r;
 #pragma unroll
-      for (int u = 0; u < 32; ++u) { sred[u * kSredPitch2 + row] = s1[u]; sred[(32 + u) * kSredPitch2 + row] = s2[u]; }
+      for (int u = 0; u < NG; ++u) { sred[u * kSredPitch2 + row] = s1[u]; sred[(NG + u) * kSredPitch2 + row] = s2[u]; }
       asm volatile("bar.sync 5, 256;" ::: "memory");
       const int e = threadIdx.x - 96;
-      if (e < 64) {
+      if (e < 2 * NG) {
         // (fp64 adds are ~64x slower than fp32 on this part: 8 independent fp32 chains, fixed order, combined in fp64)
-        const float* rowp = sred + e * kSredPitch2;          // e = which * 32 + group
+        const float* rowp = sred + e * kSredPitch2;          // e = which * NG + group
         float p8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll 4
         for (int k = 0; k < 256; k += 8) {
@@ -911,7 +940,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
         double acc = 0.0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) acc += (double)p8[u];
-        atomicAdd(&a.gn_stats[(e & 31) * 2 + (e >> 5)], acc);
+        atomicAdd(&a.gn_stats[(n0 / 2 + e % NG) * 2 + e / NG], acc);
       }
     }
     tcgen05_before_sync();
@@ -920,7 +949,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
   __syncthreads();
   if (warp == 1) {
     tcgen05_after_sync();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    tmem_dealloc_n(tmem_base, tmem_cols);
   }
 }
 
@@ -1123,7 +1152,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 
 template <int BN, int GN, int KSTEPS>
 static int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvTcArgs& a,
-                               int grid, size_t smem, cudaStream_t s) {
+                               dim3 grid, size_t smem, cudaStream_t s) {
   OTVM_CUDA_CHECK((ensure_dynamic_smem<conv_tc_persist_kernel<BN, GN, KSTEPS>>(220 * 1024)));
   launch_k(conv_tc_persist_kernel<BN, GN, KSTEPS>, grid, kPersistThreads, smem, s, tmA, tmB, tmO, a);
   OTVM_LAUNCH_CHECK();
@@ -1131,7 +1160,7 @@ static int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, c
 }
 template <int BN, int GN>
 static int launch_conv_persist_k(int ksteps, const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
-                                 const ConvTcArgs& a, int grid, size_t smem, cudaStream_t s) {
+                                 const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
   return ksteps == 4 ? launch_conv_persist<BN, GN, 4>(tmA, tmB, tmO, a, grid, smem, s)
                      : launch_conv_persist<BN, GN, 2>(tmA, tmB, tmO, a, grid, smem, s);
 }
@@ -1139,9 +1168,9 @@ static int launch_conv_persist_k(int ksteps, const CUtensorMap& tmA, const CUten
 // Persistent patch-mode variant (conv_tc_persist_kernel) when the layer qualifies; returns 1 when it launched, 0 when the
 // caller should take the one-tile-per-CTA kernel, < 0 on error.
 static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int bn, int epi, int gn,
-                            const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, cudaStream_t s) {
+                            const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmO0, cudaStream_t s) {
   const int mode = conv_persist_mode();
-  if (mode == 0 || !a0.halo || a0.planes != 1 || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
+  if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
   if (gn == GN_STATS && p->Cout != 64) return 0;
   if (a0.KC != 64 && a0.KC != 32) return 0;
   ConvTcArgs a = a0;
@@ -1149,25 +1178,60 @@ static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int
   // auto: only where a CTA gets several tiles (measured: 11.2 vs 16.1 us at 3.5 tiles per SM, 64->64 at 256^2);
   // smaller grids are latency-bound by their single wave and keep the deeper per-tile rings
   if (mode < 0 && a.ntiles < 2 * sm_count()) return 0;
+  // channels per CTA: split operands double the filter bank, so a 64-channel layer runs as two 32-channel halves
+  // (blockIdx.y); each half's CTAs walk every tile and re-read the patches (from L2)
+  const int pbn = (a.planes > 1 && bn == 64) ? 32 : bn;
+  const int ny = bn / pbn;
+  a.b_plane = (uint32_t)pbn * a.KC * 2;
+  if (a.b_plane % 1024u != 0) return 0;
+  a.b_bytes = (uint32_t)a.planes * a.b_plane;
+  const uint32_t slot_bytes = (uint32_t)a.planes * a.patch_bytes;
   const uint32_t w_bytes = (uint32_t)(9 * a.nchunk) * a.b_bytes;
-  const uint32_t stage_bytes = 2u * 128u * (uint32_t)bn * 2u;
+  const uint32_t stage_bytes = 2u * (uint32_t)a.planes * 128u * (uint32_t)pbn * 2u;
   const uint32_t budget = 200u * 1024u;
-  if (w_bytes + stage_bytes + 2 * a.patch_bytes > budget) return 0;
-  int na = (int)((budget - w_bytes - stage_bytes) / a.patch_bytes);
+  if (w_bytes + stage_bytes + 2 * slot_bytes > budget) return 0;
+  if (4u * (uint32_t)pbn * (a.planes > 1 ? 2u : 1u) > 512u) return 0;           // tensor-memory columns
+  int na = (int)((budget - w_bytes - stage_bytes) / slot_bytes);
   if (na > 8) na = 8;
-  // the final GroupNorm reduction parks [64][257] floats in the (then dead) patch ring + staging region
-  if (gn == GN_STATS && (uint32_t)na * a.patch_bytes + stage_bytes < 64u * kSredPitch2 * sizeof(float)) return 0;
+  // Ring depth: the two tile pipelines wait on the SAME ring with phase parities they derive from the tile index.  A
+  // parity wait is only meaningful within one phase of the barrier, i.e. the previous fill of a slot must be complete
+  // whenever a pipeline asks for the next one: its own previous tile guarantees that iff na >= nchunk + 1 (a pipeline
+  // that asked for fill f of a slot before fill f-1 had landed would see "complete" at once and multiply stale data).
+  if (na < a.nchunk + 1) return 0;
+  // the final GroupNorm reduction parks [pbn][257] floats in the (then dead) patch ring + staging region
+  if (gn == GN_STATS && (uint32_t)na * slot_bytes + stage_bytes < (uint32_t)pbn * kSredPitch2 * sizeof(float)) return 0;
   a.na = na;
   a.p_off = w_bytes;                                   // b_bytes and patch_bytes are multiples of 1024
-  a.stage_off = a.p_off + (uint32_t)na * a.patch_bytes;
+  a.stage_off = a.p_off + (uint32_t)na * slot_bytes;
   a.aux_off = a.stage_off + stage_bytes;
   const size_t smem = (size_t)a.aux_off + 1024 + 32 * 8 + 16 + 64 * sizeof(float) + 64;
-  const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+  int gx = sm_count() / ny;
+  if (gx > a.ntiles) gx = a.ntiles;
+  CUtensorMap tmB = tmB0, tmO = tmO0;
+  if (pbn != bn) {                                     // boxes of pbn channels
+    const CUtensorMapSwizzle swz = a.KC == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const uint64_t K = (uint64_t)p->KH * p->KW * p->Cin;
+    uint64_t dims[3] = {K, (uint64_t)p->Cout, (uint64_t)a.planes};
+    uint64_t str[2] = {K * 2, a.planes > 1 ? (uint64_t)p->w_plane_stride * 2 : K * 2 * (uint64_t)p->Cout};
+    uint32_t box[3] = {(uint32_t)a.KC, (uint32_t)pbn, 1};
+    int rc = make_tmap_bf16(&tmB, p->weight, 3, dims, str, box, swz);
+    if (rc) return rc;
+    const CUtensorMapSwizzle oswz = pbn == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : pbn == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    uint64_t odims[5] = {(uint64_t)p->Cout, (uint64_t)a.Wo, (uint64_t)a.Ho, (uint64_t)p->N, (uint64_t)a.planes};
+    uint32_t obox[5] = {(uint32_t)pbn, (uint32_t)a.TW, (uint32_t)a.TH, 1, 1};
+    uint64_t ostr[4] = {(uint64_t)p->out_ps * 2, (uint64_t)a.Wo * p->out_ps * 2, (uint64_t)a.Ho * a.Wo * p->out_ps * 2,
+                        a.planes > 1 ? (uint64_t)a.act_plane * 2 : (uint64_t)p->N * a.Ho * a.Wo * p->out_ps * 2};
+    rc = make_tmap_bf16(&tmO, p->out, 5, odims, ostr, obox, oswz);
+    if (rc) return rc;
+  }
+  const dim3 grid(gx, ny);
   int rc;
   const int ks = a.KC / 16;
-  if (bn == 64) rc = gn == GN_STATS ? launch_conv_persist_k<64, GN_STATS>(ks, tmA, tmB, tmO, a, grid, smem, s)
-                                    : launch_conv_persist_k<64, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
-  else if (bn == 32) rc = launch_conv_persist_k<32, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
+  if (pbn == 64) rc = gn == GN_STATS ? launch_conv_persist_k<64, GN_STATS>(ks, tmA, tmB, tmO, a, grid, smem, s)
+                                     : launch_conv_persist_k<64, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
+  else if (pbn == 32) rc = gn == GN_STATS ? launch_conv_persist_k<32, GN_STATS>(ks, tmA, tmB, tmO, a, grid, smem, s)
+                                          : launch_conv_persist_k<32, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
   else rc = launch_conv_persist_k<16, GN_NONE>(ks, tmA, tmB, tmO, a, grid, smem, s);
   if (rc == OTVM_OK) ++g_conv_persist_launches;
   return rc == OTVM_OK ? 1 : rc;

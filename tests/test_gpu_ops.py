@@ -438,8 +438,9 @@ PERSIST_CASES = [
 ]
 
 
+@pytest.mark.parametrize("dtype", TC_DTYPES)
 @pytest.mark.parametrize("case", PERSIST_CASES)
-def test_conv2d_persistent(case):
+def test_conv2d_persistent(case, dtype):
     """persistent patch-mode tcgen05 kernel (resident filter bank, tile loop, double-buffered TMEM accumulators and
     staging tiles) == fp32 math on the bf16-rounded operands, incl. the GroupNorm statistics of the stored values"""
     import ctypes
@@ -448,7 +449,7 @@ def test_conv2d_persistent(case):
     lib = _lib.load()
     lib.otvm_debug_set_conv_persist.argtypes = [ctypes.c_int]
     lib.otvm_debug_conv_persist_launches.restype = ctypes.c_longlong
-    dtype = torch.bfloat16
+    tol, tol_st = (1e-2, 2e-3) if dtype == torch.bfloat16 else (1e-4, 1e-4)
     Cin, Cout, k, p, d, H, W, gn = case
     g = torch.Generator().manual_seed(sum(case[:7]))
     x = torch.randn(1, Cin, H, W, generator=g)
@@ -468,12 +469,15 @@ def test_conv2d_persistent(case):
             n0 = lib.otvm_debug_conv_persist_launches()
             ops.conv2d(xd, wd, b.to(DEV), out, pad=p, dil=d, gn_stats=stats, act=ops.ACT_NONE if gn else ops.ACT_LEAKY)
             torch.cuda.synchronize()
-            assert lib.otvm_debug_conv_persist_launches() == n0 + 1, "persistent kernel not selected"
-            assert rel_err(nchw(out), want) < 1e-2
+            # (split operands: the filter bank + patch ring of the 3-chunk layers / of three planes exceed one CTA; those
+            # fall back to the one-tile kernel -- results are checked either way)
+            if dtype == torch.bfloat16 or (dtype == X2 and Cin <= 64 and d == 1):
+                assert lib.otvm_debug_conv_persist_launches() == n0 + 1, "persistent kernel not selected"
+            assert rel_err(nchw(out), want) < tol
             if gn:
                 q = rnd(dtype, want).double()[0].reshape(32, -1)
-                assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < 2e-3
-                assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < 2e-3
+                assert rel_err(stats.cpu().view(32, 2)[:, 0], q.sum(1)) < tol_st
+                assert rel_err(stats.cpu().view(32, 2)[:, 1], (q * q).sum(1)) < tol_st
     finally:
         lib.otvm_debug_set_conv_persist(-1)
     # same layer through the one-tile-per-CTA kernel: both kernels round identically (fp32 accumulate, one bf16 rounding)
@@ -483,7 +487,7 @@ def test_conv2d_persistent(case):
         ops.conv2d(xd, wd, b.to(DEV), out0, pad=p, dil=d, act=ops.ACT_NONE if gn else ops.ACT_LEAKY)
     finally:
         lib.otvm_debug_set_conv_persist(-1)
-    assert rel_err(nchw(out0), nchw(out)) < 2e-3
+    assert rel_err(nchw(out0), nchw(out)) < tol_st
 
 
 FUSED_GN_CASES = [
