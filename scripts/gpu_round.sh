@@ -39,19 +39,19 @@ for s in $STEPS; do
       OTVM_OVERLAP=0 timeout 300 python scripts/profile_frame.py bf16 > $OUT/profile_frame.txt 2>&1; head -12 $OUT/profile_frame.txt ;;
     ncu)
       OTVM_OVERLAP=0 OTVM_PDL=0 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
-        --log-file $OUT/launches.csv python scripts/one_frame.py bf16 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+        --log-file $OUT/launches.csv python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
       OTVM_OVERLAP=0 OTVM_PDL=0 timeout 900 ncu --profile-from-start off --clock-control none --csv \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum \
-        --log-file $OUT/launch_metrics.csv python scripts/one_frame.py bf16 1 > $OUT/ncu_metrics.log 2>&1; echo "ncu metrics rc=$?" ;;
+        --log-file $OUT/launch_metrics.csv python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_metrics.log 2>&1; echo "ncu metrics rc=$?" ;;
     ncufull)
       OTVM_OVERLAP=0 OTVM_PDL=0 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
-        -k regex:memory_read_tc -c 1 -f -o $OUT/read_full python scripts/one_frame.py bf16 1 > $OUT/ncu_read.log 2>&1; echo "ncu read rc=$?"
+        -k regex:memory_read_tc -c 1 -f -o $OUT/read_full python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_read.log 2>&1; echo "ncu read rc=$?"
       export_rep $OUT/read_full source
       OTVM_PDL=0 timeout 600 ncu --set full --clock-control none --import-source on \
-        -k regex:conv_tc -c 12 -f -o $OUT/conv_full python scripts/conv_one.py > $OUT/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
+        -k regex:conv_tc -c 12 -f -o $OUT/conv_full python scripts/conv_one.py ${PREC:-bf16x2} > $OUT/ncu_conv.log 2>&1; echo "ncu conv rc=$?"
       export_rep $OUT/conv_full source
       OTVM_PDL=0 timeout 600 ncu --set full --clock-control none \
-        -k regex:gn_apply -c 4 -f -o $OUT/gn_full python scripts/conv_one.py gn > $OUT/ncu_gn.log 2>&1; echo "ncu gn rc=$?"
+        -k regex:gn_apply -c 4 -f -o $OUT/gn_full python scripts/conv_one.py ${PREC:-bf16x2} gn > $OUT/ncu_gn.log 2>&1; echo "ncu gn rc=$?"
       export_rep $OUT/gn_full
       ls -la $OUT; du -sh gpurun_out ;;
   esac

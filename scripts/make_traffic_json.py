@@ -19,7 +19,8 @@ for r in csv.DictReader(lines):
         fam[f]["us"] += v * {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(u, 1)
         if r["ID"] not in seen:
             seen.add(r["ID"]); fam[f]["launches"] += 1
-out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of one eager steady-state 512x512 T=8 frame ({tag}); "
+prec = sys.argv[3] if len(sys.argv) > 3 else "bf16x2"
+out = {"precision": prec, "source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum of one eager steady-state 512x512 T=8 frame ({tag}); "
                  "cold-cache, serialised launches", "per_frame": {k: {kk: round(vv, 1) for kk, vv in v.items()} for k, v in fam.items()}}
 json.dump(out, open("profiles/ncu_traffic.json", "w"), indent=1)
 print(json.dumps(out, indent=1))
