@@ -160,9 +160,28 @@ typedef struct {
   int32_t dtype;
   void* workspace; int64_t workspace_bytes;
   int32_t force_simt;                           /* 1: use the fp32 FFMA kernel even for bf16 inputs (tests) */
+  float* lse;                                   /* optional [HW]: log2-sum-exp of the scaled logits per query    */
+                                                /* (saved for otvm_memory_read_backward), or NULL              */
 } otvm_read_params;
 OTVM_API int64_t otvm_memory_read_workspace(int32_t M, int32_t HW, int32_t De, int32_t Do, int32_t dtype);
 OTVM_API int otvm_memory_read(const otvm_read_params* p, void* stream);
+
+/* Backward of the read (the stage-4 training step differentiates through
+ * Memory.forward, train.py:349-375).  Recomputes 32 x 32 tiles of the affinity from the operands and the saved
+ * log-sum-exp (nothing of size THW x HW is stored), fp32 arithmetic.  Operands as in the forward (dtype OTVM_F32 or
+ * OTVM_BF16); out / dout: forward output and its gradient, fp32 [HW][ld]; gradients fp32:
+ *   dkeys [M][De], dvals [Do][dldv], dquery [HW][De] (all overwritten). */
+typedef struct {
+  const void* keys; const void* vals; int64_t ldv;
+  const void* query; int64_t q_ld;
+  const float* out; int64_t out_ld;
+  const float* dout; int64_t dout_ld;
+  const float* lse;
+  float* dkeys; float* dvals; int64_t dldv; float* dquery;
+  int32_t M, HW, De, Do;
+  int32_t dtype;
+} otvm_read_bwd_params;
+OTVM_API int otvm_memory_read_backward(const otvm_read_bwd_params* p, void* stream);
 
 /* ---- frame glue (EvalModel.forward, models/alpha/model.py:391-512) ----------------------------------
  * preprocess_gt + make_trimap_gt (models/alpha/model.py:342-362,380-389): BGR->RGB flip, 1/255, composite,

@@ -43,6 +43,20 @@ class ReadParams(C.Structure):
         ("dtype", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
         ("force_simt", c_i32),
+        ("lse", c_vp),
+    ]
+
+
+class ReadBwdParams(C.Structure):
+    _fields_ = [
+        ("keys", c_vp), ("vals", c_vp), ("ldv", c_i64),
+        ("query", c_vp), ("q_ld", c_i64),
+        ("out", c_vp), ("out_ld", c_i64),
+        ("dout", c_vp), ("dout_ld", c_i64),
+        ("lse", c_vp),
+        ("dkeys", c_vp), ("dvals", c_vp), ("dldv", c_i64), ("dquery", c_vp),
+        ("M", c_i32), ("HW", c_i32), ("De", c_i32), ("Do", c_i32),
+        ("dtype", c_i32),
     ]
 
 
@@ -68,6 +82,7 @@ SIGNATURES = {
     "otvm_ppm_pool": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp]),
     "otvm_memory_read_workspace": (c_i64, [c_i32, c_i32, c_i32, c_i32, c_i32]),
     "otvm_memory_read": (C.c_int, [C.POINTER(ReadParams), c_vp]),
+    "otvm_memory_read_backward": (C.c_int, [C.POINTER(ReadBwdParams), c_vp]),
     "otvm_preprocess": (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                   C.POINTER(c_f), c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "otvm_trimap_encode": (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, C.POINTER(c_f), c_vp, c_i64,

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) memory_read_simt_kernel(const ReadArgs a)
 template <typename T>
 __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* __restrict__ o_part,
                                                                   const float* __restrict__ ml_part, int nsplit,
-                                                                  int HW, int Do, ptr_t<T> out, int64_t out_ld) {
+                                                                  int HW, int Do, ptr_t<T> out, int64_t out_ld,
+                                                                  float* __restrict__ lse) {
   pdl_sync();                                  // PDL contract (common.cuh)
   const int c4n = Do >> 2;
   const int64_t total = (int64_t)HW * c4n;
@@ -191,6 +192,7 @@ __global__ void __launch_bounds__(256) memory_read_combine_kernel(const float* _
       acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[3] += w * v.w;
     }
     const float inv = 1.f / l;
+    if (lse && c == 0) lse[q] = mstar + log2f(l);        // log2-sum-exp of the scaled logits (for the backward)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] *= inv;
     store4(out + ((int64_t)q * out_ld + c), acc);
@@ -226,7 +228,7 @@ int read_combine(const otvm_read_params* p, int nsplit, cudaStream_t s) {
   int g = ceil_div(total, 256);
   const int64_t ps = dtype_plane_stride(p->dtype);
   switch (dtype_fmt(p->dtype)) {
-#define OTVM_COMBINE(T) launch_k(memory_read_combine_kernel<T>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do, mkptr<T>(p->out, ps), p->out_ld)
+#define OTVM_COMBINE(T) launch_k(memory_read_combine_kernel<T>, g, 256, 0, s, o_part, ml_part, nsplit, p->HW, p->Do, mkptr<T>(p->out, ps), p->out_ld, p->lse)
     case OTVM_F32: OTVM_COMBINE(float); break;
     case OTVM_BF16: OTVM_COMBINE(bf16); break;
     case OTVM_BF16X2: OTVM_COMBINE(bx<2>); break;

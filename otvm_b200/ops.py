@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib, split
-from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, F32, ConvParams, ReadParams, check  # noqa: F401
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, BF16, F32, ConvParams, ReadBwdParams, ReadParams, check  # noqa: F401
 
 
 def _dt(t) -> int:
@@ -246,7 +246,24 @@ def memory_read_workspace(M, HW, De, Do, dtype=None):
     return int(_lib.load().otvm_memory_read_workspace(M, HW, De, Do, BF16))
 
 
-def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
+def memory_read_backward(keys, vals, ldv, query, out, dout, lse, dkeys, dvals, dquery, M):
+    """gradients of :func:`memory_read` (fp32): keys [M,De] / vals [Do,ldv] / query NHWC as in the forward (fp32 or bf16),
+    out / dout [1,h,w,>=Do] fp32 views, lse [HW] from the forward; dkeys [M,De], dvals [Do,*], dquery [HW,De] overwritten"""
+    lib = _lib.load()
+    p = ReadBwdParams()
+    p.keys, p.vals, p.ldv = keys.data_ptr(), vals.data_ptr(), ldv
+    p.query, p.q_ld = query.data_ptr(), _ld(query)
+    p.out, p.out_ld = out.data_ptr(), _ld(out)
+    p.dout, p.dout_ld = dout.data_ptr(), _ld(dout)
+    p.lse = lse.data_ptr()
+    p.dkeys, p.dvals, p.dldv, p.dquery = dkeys.data_ptr(), dvals.data_ptr(), dvals.stride(0), dquery.data_ptr()
+    p.M, p.HW, p.De, p.Do = M, query.shape[1] * query.shape[2], keys.shape[-1], vals.shape[0]
+    p.dtype = _dt(keys)
+    assert out.dtype == dout.dtype == lse.dtype == dkeys.dtype == torch.float32
+    check(lib.otvm_memory_read_backward(C.byref(p), _stream()), "otvm_memory_read_backward")
+
+
+def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False, lse=None):
     """keys [>=M, De] rows; vals [Do, ldv] channel-major; query NHWC view with De channels; out NHWC view with
     Do channels (a slice of the 2*Do decoder input)."""
     if DRY:
@@ -262,6 +279,7 @@ def memory_read(keys, vals, ldv, query, out, M, workspace, *, force_simt=False):
     p.dtype = _dt(keys)
     p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     p.force_simt = int(force_simt)
+    p.lse = lse.data_ptr() if lse is not None else None
     es = keys.element_size() * _planes(keys)
     _timed("memory_read", lambda: check(lib.otvm_memory_read(C.byref(p), _stream()), "otvm_memory_read"),
            2.0 * M * HW * (De + Do), float((De + Do) * M * es + De * HW * es + Do * HW * es))

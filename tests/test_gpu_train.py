@@ -1,0 +1,53 @@
+"""the fused Memory.read under autograd (otvm_b200/train.py) against PyTorch autograd of
+the reference's composite formulation (oracle.memory_read == models/trimap/STM.py:144-163)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from util import ROOT, rel_err
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,T,h,w,scale", [(1, 1, 4, 4, 1.0), (1, 2, 20, 20, 1.0), (2, 3, 7, 9, 2.5), (1, 5, 12, 20, 0.3)])
+def test_fused_read_forward_and_gradients(B, T, h, w, scale):
+    import otvm_oracle as O
+    from otvm_b200.train import memory_read
+    g = torch.Generator().manual_seed(B * 100 + T * 10 + h)
+    mk = lambda *s: torch.randn(*s, generator=g)
+    m_in, m_out = mk(B, 128, T, h, w) * scale, mk(B, 512, T, h, w)
+    q_in, q_out = mk(B, 128, h, w) * scale, mk(B, 512, h, w)
+    gout = mk(B, 1024, h, w)
+    ref_in = [t.clone().requires_grad_(True) for t in (m_in, m_out, q_in, q_out)]
+    want = O.memory_read(*ref_in)
+    want.backward(gout)
+    got_in = [t.clone().cuda().requires_grad_(True) for t in (m_in, m_out, q_in, q_out)]
+    got = memory_read(*got_in)
+    got.backward(gout.cuda())
+    assert rel_err(got.detach().cpu(), want.detach()) < 1e-4
+    for name, a, b in zip(("d_keys", "d_values", "d_query", "d_query_value"), got_in, ref_in):
+        assert rel_err(a.grad.cpu(), b.grad) < 1e-4, name
+
+
+def test_read_block_step_matches_composite():
+    """one fp32 optimisation step of the STM read block with the fused read == the same step with the composite read:
+    same loss, same updated parameters"""
+    import otvm_oracle as O
+    from otvm_b200 import train
+    torch.manual_seed(5)
+    a = train.STMReadBlock().cuda()
+    b = train.STMReadBlock(read_fn=O.memory_read).cuda()
+    b.load_state_dict(a.state_dict())
+    batch = train.synthetic_batch(2, 2, 12, 12, seed=3, device="cuda")
+    oa, ob = torch.optim.SGD(a.parameters(), lr=1e-2), torch.optim.SGD(b.parameters(), lr=1e-2)
+    la = train.train_step(a, oa, batch, None)
+    lb = train.train_step(b, ob, batch, None)
+    assert abs(float(la) - float(lb)) < 1e-5 * max(1.0, abs(float(lb)))
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert rel_err(pa.detach().cpu(), pb.detach().cpu()) < 1e-5, n
+    # bf16 autocast (the reference trains stage 4 in mixed precision): finite loss, gradients flow into every parameter
+    l2 = train.train_step(a, oa, batch, torch.bfloat16)
+    assert torch.isfinite(l2) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in a.parameters())

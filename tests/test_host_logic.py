@@ -139,7 +139,7 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name)
     assert lib.otvm_version() == 4
     assert lib.otvm_strerror(-3).decode().startswith("unsupported")
-    assert ctypes.sizeof(_lib.ConvParams) == 200 and ctypes.sizeof(_lib.ReadParams) == 104   # sizeof() of the C structs
+    assert ctypes.sizeof(_lib.ConvParams) == 200 and ctypes.sizeof(_lib.ReadParams) == 112   # sizeof() of the C structs
 
 
 def test_clip_sharding_two_ranks_gloo():
@@ -242,3 +242,18 @@ print("done | Total time: {}".format(format_time(12.5)))  # eval.py:94
     r = subprocess.run([sys.executable, "-c", script], capture_output=True, text=True, env=env, cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout + r.stderr
     assert "done | Total time:" in r.stdout
+
+
+def test_read_block_ddp_step_two_ranks_gloo():
+    """the DDP plumbing of scripts/train_step_ddp.py on CPU (gloo, world_size 2) with the composite read standing in for
+    the CUDA kernels: gradients are all-reduced (ranks stay in sync), bytes per step = fp32 size of the parameters"""
+    import json
+    env = dict(os.environ, OTVM_TRAIN_CPU="1", STEPS="2", WARMUP="1", FEAT="6", T_MEM="2", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "scripts", "train_step_ddp.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert line, r.stdout + r.stderr
+    d = json.loads(line[-1])
+    assert d["n_ranks"] == 2 and d["backend"] == "gloo" and d["ranks_in_sync"] is True
+    assert d["allreduce_bytes_per_step"] == 4 * d["parameters"] and d["parameters"] > 14_000_000
