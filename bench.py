@@ -445,11 +445,49 @@ def run_reference_sample(steps, warmup, parity_precision=None):
         dt = time.perf_counter() - t0
         if parity_precision is not None and torch.cuda.is_available():
             parity = check_parity(parity_precision, frames[0], bank0, outs[0], seg0, kw)
+    eager = None
+    if parity_precision is not None and torch.cuda.is_available():
+        eager = torch_eager_same_gpu(O, kw)
     cpu = {"value": round(steps / dt, 4), "unit": "frames/s", "cores": cores, "kind": "port",
+           "torch_eager_same_gpu": eager,
            "sample": f"{steps} steady-state {H}x{W} frames at T={T_MEM} (after {warmup} warm-up), oracle port of the "
                      f"reference on {cores} host threads, torch {torch.__version__} CPU fp32",
            "ms_per_step": round(dt / steps * 1e3, 1)}
     return cpu, parity
+
+
+def torch_eager_same_gpu(O, kw, steps=12, warmup=3):
+    """SURVEY.md section 2.3's bar: the reference's OWN GPU path on this very B200 -- the same PyTorch modules in eager
+    mode through cuDNN / cuBLAS (strict fp32, and with TF32 allowed), host distance transform and all
+    (utils/utils.py:12-23).  It is the oracle port with its tensors on the device; reported
+    for context next to the CPU number, measured with the same steady-state protocol (T-frame bank, wall clock with a
+    synchronise per frame as eval.py:195-197 does)."""
+    from otvm_b200.fixtures import make_frame, make_state_dict
+    out = {}
+    for tf32 in (False, True):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.no_grad():
+            om = O.OracleEvalModel(make_state_dict("tempered"), dilate_kernel=RADIUS, device="cuda")
+            fr = [tuple(t.cuda() for t in make_frame(0, i, H, W)) for i in range(4)]
+            om(*fr[0], first_frame=True, last_frame=False, memorize=True, max_memory_num=T_MEM)
+            om.memories = {k: v.repeat(1, 1, 1, T_MEM, 1, 1) for k, v in om.memories.items()}
+            for i in range(warmup):
+                om(*fr[i % 4], **kw)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(steps):
+                om(*fr[i % 4], **kw)
+                torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        out["tf32" if tf32 else "fp32"] = round(steps / dt, 2)
+        del om
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.cuda.empty_cache()
+    return {"unit": "frames/s", "frames_per_s": out, "steps": steps,
+            "what": "oracle port (plain PyTorch eager, cuDNN / cuBLAS, host EDT) with its tensors on this GPU; "
+                    f"{H}x{W}, T={T_MEM}; 'tf32' = torch.backends.*.allow_tf32 on"}
 
 
 def check_parity(precision, frame, bank, ref, ref_seg, kw):

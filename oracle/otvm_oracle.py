@@ -310,6 +310,8 @@ def edt_sq(mask_nonzero: np.ndarray) -> np.ndarray:
 def trimap_transform(trimap2):
     """utils/utils.py:25-39.  trimap2: [N,2,H,W] in {0,1} (bg mask, fg mask) -> [N,6,H,W]."""
     N, _, H, W = trimap2.shape
+    dev = trimap2.device
+    trimap2 = trimap2.cpu()                 # the distance transform runs on the HOST, like utils/utils.py:12-23 (cv2)
     clicks = torch.zeros(N, 6, H, W)
     L = 320
     for n in range(N):
@@ -321,7 +323,7 @@ def trimap_transform(trimap2):
                 dm = -d ** 2
                 for j, s in enumerate((0.02, 0.08, 0.16)):
                     clicks[n, 3 * k + j] = torch.exp(dm / (2 * ((s * L) ** 2)))
-    return clicks
+    return clicks.to(dev)
 
 
 def make_trimap8(tri3):
@@ -353,8 +355,10 @@ class OracleEvalModel:
 
     IMG_SCALE = 1.0 / 255
 
-    def __init__(self, state_dict, dilate_kernel=12):
-        self.sd = {k: v.detach().float() if v.is_floating_point() else v for k, v in state_dict.items()}
+    def __init__(self, state_dict, dilate_kernel=12, device="cpu"):
+        """``device='cuda'`` runs the same PyTorch ops through cuDNN / cuBLAS -- the reference's own GPU path (fp32 eager,
+        host distance transform); used by bench.py as the "PyTorch eager on the same GPU" baseline."""
+        self.sd = {k: (v.detach().float() if v.is_floating_point() else v).to(device) for k, v in state_dict.items()}
         self.radius = dilate_kernel
         self.memories = None
         self.trace = {}

@@ -137,6 +137,9 @@ def test_c_abi_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name)
+    dbg = open(os.path.join(ROOT, "include", "otvm_b200_debug.h")).read()
+    for name in set(re.findall(r"\b(otvm_debug_\w+)\s*\(", dbg)):          # the diagnostic hooks are exported too
+        assert hasattr(lib, name), name
     assert lib.otvm_version() == 4
     assert lib.otvm_strerror(-3).decode().startswith("unsupported")
     assert ctypes.sizeof(_lib.ConvParams) == 200 and ctypes.sizeof(_lib.ReadParams) == 112   # sizeof() of the C structs
