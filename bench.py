@@ -511,7 +511,10 @@ def check_parity(precision, frame, bank, ref, ref_seg, kw):
     def err(got, want):
         return float((got.double().cpu() - want.double()).abs().max() / max(float(want.abs().max()), 1e-12))
     seg = pl.bufs["seg_logits"][0, pl.pad_top:pl.pad_top + H, pl.pad_left:pl.pad_left + W, :3].permute(2, 0, 1)
+    # pixels whose propagated-trimap class differs (near-ties of the oracle's own logits: the class is an argmax)
+    flips = int((seg.float().cpu().argmax(0) != ref_seg[0].argmax(0)).sum())
     return {"precision": precision, "frame": f"steady-state {H}x{W} frame, T={T} bank shared with the oracle",
+            "propagated_class_flips": flips,
             "metric": "max|got-want| / max|want| against the CPU oracle (bit-identical to the reference on tests/golden)",
             "seg_logit": err(seg, ref_seg[0]), "trimap": err(out[1], ref[1]), "alpha": err(out[3], ref[3]),
             "tolerance": {"bf16x2": 1e-2, "fast": 1e-2, "bf16x3": 1e-3, "strict": 1e-3, "fp32": 1e-3}.get(precision)}

@@ -50,7 +50,20 @@ def compare_frame(model, oracle, out, ref, H, W, first, rel_err=rel_err):
     Hp, Wp = pl.Hp, pl.Wp
     e = {}
     if not first:
-        e["seg_logit"] = rel_err(nchw(b["seg_logits"][..., :3]), tr_pad(tr["seg_logit"], Hp, Wp))
+        got_l, want_l = nchw(b["seg_logits"][..., :3]), tr_pad(tr["seg_logit"], Hp, Wp)
+        e["seg_logit"] = rel_err(got_l, want_l)
+        # The propagated trimap is DISCRETISED before it enters the alpha network (argmax -> seed masks -> exact distance
+        # transform, models/alpha/model.py:40-53): a pixel whose two largest logits are closer than the arithmetic noise may
+        # pick the other class, and the distance channels then differ by O(1e-2) around it.  Such flips are legitimate iff
+        # they are near-ties of the ORACLE's own logits; they are counted, checked to be ties, and reported as
+        # e["class_flips"] so that the tests can hold that frame's alpha-network tensors apart (its INPUT differs).
+        flip = got_l.argmax(1) != want_l.argmax(1)
+        e["class_flips"] = int(flip.sum())
+        if e["class_flips"]:
+            top2 = want_l.topk(2, dim=1).values
+            gap = (top2[:, 0] - top2[:, 1])[flip].max()
+            noise = (got_l - want_l).abs().max()
+            assert float(gap) <= 4.0 * float(noise) + 1e-12, ("class flip that is not a near-tie", float(gap), float(noise))
         e["read_mem"] = rel_err(nchw(b["m4in"]), tr["m4"])
         e["q_key"] = rel_err(nchw(b["q_key"]), tr["k4"])
     e["tri8"] = rel_err(nchw(b["x11"][..., 3:11]), tr["tri8"])
@@ -73,6 +86,21 @@ def compare_frame(model, oracle, out, ref, H, W, first, rel_err=rel_err):
     e["scaled_img"] = rel_err(out[0].cpu(), ref[0])
     e["tri_gt"] = rel_err(out[2].cpu(), ref[2])
     return e
+
+
+STM_KEYS = ("seg_logit", "read_mem", "q_key", "scaled_img", "tri_gt")
+
+
+def assert_rows(rows, tol, tag=""):
+    """every traced tensor of every frame within ``tol`` (scale-relative max norm).  A frame with near-tie class flips
+    (see compare_frame) is held to ``tol`` on the propagation path only: the alpha network saw a different discrete input."""
+    for i, e in enumerate(rows):
+        flips = e.get("class_flips", 0)
+        for k, v in e.items():
+            if k == "class_flips" or (flips and k not in STM_KEYS):
+                continue
+            v = v[0] if isinstance(v, tuple) else v
+            assert v < tol, (tag, i, k, v, e)
 
 
 def tr_pad(x, Hp, Wp):
@@ -98,7 +126,8 @@ def run_clip(kind, precision, H, W, n_frames, max_mem=8, teacher=True, memorize=
         torch.cuda.synchronize()
         e = compare_frame(model, oracle, out, ref, H, W, i == 0)
         if with_mean:
-            e = {k: (v, m) for (k, v), m in zip(e.items(), compare_frame(model, oracle, out, ref, H, W, i == 0, rel_err=mean_err).values())}
+            em = compare_frame(model, oracle, out, ref, H, W, i == 0, rel_err=mean_err)
+            e = {k: (v if k == "class_flips" else (v, em[k])) for k, v in e.items()}
         rows.append(e)
         if i == 0 and bank_fill > 1:
             g = torch.Generator().manual_seed(7)

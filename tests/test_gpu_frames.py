@@ -2,7 +2,7 @@
 import pytest
 import torch
 
-from frames_util import run_clip
+from frames_util import assert_rows, run_clip
 from util import golden, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -17,9 +17,7 @@ TC_TOL = {"bf16x2": 1e-2, "bf16x3": 1e-3}
 @pytest.mark.parametrize("kind,H,W", [("tempered", 128, 128), ("default", 128, 128), ("tempered", 120, 152)])
 def test_fp32_frames_teacher_forced(kind, H, W):
     rows = run_clip(kind, "fp32", H, W, 3, max_mem=2 if H == 120 else 8)
-    for i, e in enumerate(rows):
-        for k, v in e.items():
-            assert v < FP32_TOL, (i, k, v, e)
+    assert_rows(rows, FP32_TOL, "fp32")
 
 
 def test_fp32_free_running_matches_reference_golden():
@@ -100,11 +98,8 @@ def test_tensor_core_frames_teacher_forced(kind, H, W, precision):
     fused heads, hid, trimap, alpha -- within the north-star tolerance in the MAX norm: 1e-2 for the default two-plane
     mode, 1e-3 for the strict three-plane mode (measured ~5e-4 / ~1e-5)."""
     rows = run_clip(kind, precision, H, W, 3, max_mem=2 if H == 120 else 8)
-    tol = TC_TOL[precision]
-    for i, e in enumerate(rows):
-        for k, v in e.items():
-            assert v < tol, (precision, i, k, v, e)
-        assert e["scaled_img"] < 1e-6 and e["tri_gt"] == 0
+    assert_rows(rows, TC_TOL[precision], precision)
+    assert all(e["scaled_img"] < 1e-6 and e["tri_gt"] == 0 for e in rows)
 
 
 def test_plain_bf16_frames_document_the_gap():
@@ -173,10 +168,9 @@ def test_frames_512_T8_teacher_forced(precision, frames):
     """BASELINE configs[1] (512x512, bank growing to T=8, the benchmarked workload), every frame against the oracle with
     the oracle's bank: every traced tensor within the mode's tolerance in the max norm"""
     rows = run_clip("tempered", precision, 512, 512, frames, max_mem=8)
-    tol = TC_TOL[precision]
-    for i, e in enumerate(rows):
-        for k, v in e.items():
-            assert v < tol, (precision, i, k, v, e)
+    assert_rows(rows, TC_TOL[precision], precision)
+    # near-tie class flips of the propagated trimap (frames_util.compare_frame) must stay the exception
+    assert sum(1 for e in rows if e.get("class_flips", 0)) <= max(1, frames // 3), [e.get("class_flips", 0) for e in rows]
 
 
 @pytest.mark.parametrize("precision", ["bf16x2", "bf16x3"])
@@ -209,9 +203,7 @@ def test_frames_1024_T16_teacher_forced():
     """BASELINE configs[2]: 1024x1024 with a T=16 bank (HW = 4096, THW = 65536: the un-fused affinity would be 1 GB).
     Frame 0, then the bank is grown to 16 entries and two steady-state frames are compared tensor by tensor."""
     rows = run_clip("tempered", "bf16x2", 1024, 1024, 3, max_mem=16, bank_fill=16)
-    for i, e in enumerate(rows):
-        for k, v in e.items():
-            assert v < TC_TOL["bf16x2"], (i, k, v, e)
+    assert_rows(rows, TC_TOL["bf16x2"], "1024")
     assert "read_mem" in rows[1] and "read_mem" in rows[2]
 
 
@@ -248,7 +240,7 @@ def test_undamped_weights_and_white_noise_frames(precision):
     tol = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16x2": 1e-2}[precision]
     for i, e in enumerate(rows):
         print(precision, i, " ".join(f"{k}={v:.1e}" for k, v in e.items()))
-        assert all(v == v and v < 2.0 for v in e.values()), (precision, i, e)          # finite
+        assert all(v == v and v < 2.0 for k, v in e.items() if k != "class_flips"), (precision, i, e)          # finite
         for k in ("seg_logit", "read_mem", "q_key", "mem_key", "mem_val"):
             if k in e and (i == 0 or not k.startswith("mem_")):                       # frame 1's memorize input is FBA output
                 assert e[k] < tol, (precision, i, k, e[k])
