@@ -1297,13 +1297,15 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.tw_shift = 0; while ((1 << a.tw_shift) < a.TW) ++a.tw_shift;
   auto magic = [](int d) -> uint32_t { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (uint64_t)d - 1) / (uint64_t)d); };
   a.tiles_x_magic = magic(a.tiles_x); a.tiles_y_magic = magic(a.tiles_y);     // exact for n * d < 2^32 (n < 2^16 tiles)
-  // A GroupNorm-fused request whose grid is between one and two CTAs per SM (split operands: the 256 -> 1024 / 512 -> 1024
-  // layers of the FBA encoder at 1/8 resolution, 256 CTAs): the usual 200 KB ring would leave one CTA per SM and no
-  // co-resident wave, i.e. no fusion and a separate gn_apply pass over the whole output.  Half-depth K chunks (32) and a
-  // ~100 KB footprint keep two CTAs per SM, so the grid barrier is legal and the normalisation stays in the epilogue.
+  // Multi-wave grids with split operands: the usual 200 KB ring leaves ONE CTA per SM, so nothing overlaps a CTA's
+  // (long: two accumulators, plane split, two staging tiles) epilogue, and a GroupNorm-fused request with 149..296 CTAs
+  // has no co-resident wave at all (-> a separate gn_apply pass over the whole output).  Half-depth K chunks (32) and a
+  // ~100 KB footprint keep two CTAs per SM.  Measured: 231.6 -> 235.7 frames/s from the fused-GroupNorm layers alone (8
+  // gn_apply passes fewer), -> 239.7 for every multi-wave layer (512 -> 2048 at 64^2: 58 -> 44 us).
+  // OTVM_CONV_SMALL_RING=0 restores the deep ring.
   const int64_t ctas0 = (int64_t)a.tiles_x * a.tiles_y * p->N * ceil_div(p->Cout, bn);
-  const bool small_ring = p->gn_gamma && a.planes > 1 && !a.halo && ctas0 > sm_count() && ctas0 <= 2 * sm_count() &&
-                          a.KC == 64 && getenv("OTVM_CONV_SMALL_RING_OFF") == nullptr;
+  static const int small_ring_on = getenv("OTVM_CONV_SMALL_RING") ? atoi(getenv("OTVM_CONV_SMALL_RING")) : 1;
+  const bool small_ring = small_ring_on && a.planes > 1 && !a.halo && a.KC == 64 && ctas0 > sm_count();
   if (small_ring) { a.KC = 32; a.nchunk = p->Cin / a.KC; a.row_bytes = (uint32_t)a.KC * 2; }
   a.a_plane = a.halo ? 0u : 128u * a.KC * 2;
   a.b_plane = ((uint32_t)bn * a.KC * 2 + 1023u) & ~1023u;
