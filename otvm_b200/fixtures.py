@@ -143,3 +143,18 @@ def user_trimap(kind: str, H: int, W: int):
         return torch.from_numpy(np.eye(3, dtype=np.float32)[cls].transpose(2, 0, 1).copy()).view(1, 1, 3, H, W)
     img = np.round(soft[::-1] * 255.0).astype(np.float32)                  # the model flips channel order (:396)
     return torch.from_numpy(img.copy()).view(1, 1, 3, H, W)
+
+
+def make_train_sample(clip: int, S: int, H: int, W: int):
+    """one stage-4 training sample in the layout ``train.py:349-357`` feeds the model: ``a [1,S,1,H,W]`` in [0,1],
+    ``fg, bg [1,S,3,H,W]`` BGR 0..255, ``tri [1,S,3,H,W]`` one-hot (bg, unknown, fg) derived from the alpha by a
+    5-pixel dilation of its soft band (the role of ``dataset.py:200-229``)."""
+    fr = [make_frame(clip, i, H, W) for i in range(S)]
+    a = torch.cat([f[0] for f in fr], dim=1)
+    fg = torch.cat([f[1] for f in fr], dim=1)
+    bg = torch.cat([f[2] for f in fr], dim=1)
+    unk = ((a > 0) & (a < 1)).float()[0]                               # [S,1,H,W]
+    unk = torch.nn.functional.max_pool2d(unk, kernel_size=11, stride=1, padding=5)
+    cls = torch.where(unk > 0.5, torch.ones_like(unk), 2 * a[0].round()).long()[:, 0]
+    tri = torch.nn.functional.one_hot(cls, 3).permute(0, 3, 1, 2).float().unsqueeze(0)
+    return a, fg, bg, tri

@@ -45,12 +45,24 @@ def main():
     h = w = int(os.environ.get("FEAT", 20))                   # 320x320 crops (config.py:27) at 1/16 resolution
     T = int(os.environ.get("T_MEM", 2))                       # memory frames of a 3-frame sample (config.py:31-32)
     torch.manual_seed(111)
-    model = train.STMReadBlock(read_fn=None if cuda else composite_read).to(dev)
+    full = os.environ.get("MODEL", "read_block") == "stage4"   # the whole stage-4 model (BASELINE configs[4])
+    if full:
+        from otvm_b200 import train_stage4
+        from otvm_b200.fixtures import make_state_dict, make_train_sample
+        model = train_stage4.Stage4Model(read_fn=None if cuda else composite_read)
+        model.load_state_dict(make_state_dict("tempered"))      # strict: the reference's 785 stage-4 keys
+        model = model.to(dev)
+        size, S = int(os.environ.get("SIZE", 320)), int(os.environ.get("FRAMES", 3))    # config.py:27,31-32
+    else:
+        model = train.STMReadBlock(read_fn=None if cuda else composite_read).to(dev)
     ddp = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local] if cuda else None) if world > 1 else model
     opt = torch.optim.RAdam(ddp.parameters(), lr=1e-4)        # train.py:262 uses RAdam
     losses = []
 
     def one(i):
+        if full:
+            sample = [t.to(dev) for t in make_train_sample(1000 * i + rank, S, size, size)]
+            return train_stage4.step(ddp, opt, sample, torch.bfloat16 if cuda else None)[0]
         batch = train.synthetic_batch(1, T, h, w, seed=1000 * i + rank, device=dev)       # a different sample per rank
         return train.train_step(ddp, opt, batch, torch.bfloat16 if cuda else None)
 
@@ -83,9 +95,13 @@ def main():
     else:
         sigs = [sig]
     if rank == 0:
-        print(json.dumps({"what": "STM read block (KeyValue x2, fused Memory.read fwd+bwd, convFM, pred), one sample per rank",
+        what = (f"stage-4 joint step (train.py:349-375): {S} frames of {size}x{size} per rank, FBA + STM networks, four losses, "
+                "fused Memory.read fwd+bwd on the path" if full else
+                "STM read block (KeyValue x2, fused Memory.read fwd+bwd, convFM, pred), one sample per rank")
+        print(json.dumps({"what": what,
                           "n_ranks": world, "backend": ("nccl" if cuda else "gloo") if world > 1 else None,
-                          "autocast": "bf16" if cuda else None, "feature_map": [h, w], "memory_frames": T,
+                          "autocast": "bf16" if cuda else None,
+                          "feature_map": [size // 16, size // 16] if full else [h, w], "memory_frames": S - 1 if full else T,
                           "ms_per_step": round(float(t), 3), "steps": steps,
                           "allreduce_bytes_per_step": train.allreduce_bytes(model) if world > 1 else 0,
                           "parameters": sum(p.numel() for p in model.parameters()),

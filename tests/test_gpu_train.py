@@ -51,3 +51,17 @@ def test_read_block_step_matches_composite():
     # bf16 autocast (the reference trains stage 4 in mixed precision): finite loss, gradients flow into every parameter
     l2 = train.train_step(a, oa, batch, torch.bfloat16)
     assert torch.isfinite(l2) and all(p.grad is not None and torch.isfinite(p.grad).all() for p in a.parameters())
+
+
+def test_stage4_step_matches_reference_golden():
+    """BASELINE configs[4]: one stage-4 training step with the FUSED read (forward + recompute backward) on the path,
+    against the reference's own step: losses, gradient norm, sampled gradients, refined alphas, predicted trimaps"""
+    from test_host_logic import _stage4_against_golden
+    # the golden is an fp32 CPU run: cuDNN / cuBLAS must not drop to TF32 (PyTorch allows it for convolutions by default,
+    # and the random-weight networks amplify 2^-11 roundings to 25 % on the first-layer gradients)
+    tf = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        _stage4_against_golden("cuda", None, 2e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf

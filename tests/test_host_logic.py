@@ -260,3 +260,56 @@ def test_read_block_ddp_step_two_ranks_gloo():
     d = json.loads(line[-1])
     assert d["n_ranks"] == 2 and d["backend"] == "gloo" and d["ranks_in_sync"] is True
     assert d["allreduce_bytes_per_step"] == 4 * d["parameters"] and d["parameters"] > 14_000_000
+
+
+def _stage4_against_golden(device, read_fn, tol):
+    """one stage-4 training step (forward, four losses, backward) of otvm_b200.train_stage4 against the REFERENCE's own
+    step on the same weights / sample (tests/golden/train_step_s4.npz, oracle/make_golden_train.py)"""
+    import numpy as np
+    import torch
+    from otvm_b200 import train_stage4 as S4
+    from otvm_b200.fixtures import make_state_dict, make_train_sample
+    g = np.load(os.path.join(ROOT, "tests", "golden", "train_step_s4.npz"))
+    H, W, S = [int(x) for x in g["meta"]]
+    m = S4.Stage4Model(read_fn=read_fn)
+    m.load_state_dict(make_state_dict("tempered"))                              # strict, 785 keys
+    m = m.to(device)
+    out = m(*[t.to(device) for t in make_train_sample(0, S, H, W)[:3]], ignore_region=None,
+            tri=make_train_sample(0, S, H, W)[3].to(device))
+    losses = [o.mean() for o in out[:4]]
+    sum(losses).backward()
+    for got, want in zip(losses, g["losses"]):
+        assert abs(float(got.detach()) - want) <= tol * max(1.0, abs(want)), (float(got.detach()), want)
+    named = dict(m.named_parameters())
+    gsq = sum(float(v.grad.double().pow(2).sum()) for v in named.values() if v.grad is not None)
+    assert abs(gsq ** 0.5 - float(g["grad_norm"])) <= tol * float(g["grad_norm"])
+    for k in g.files:
+        if k.startswith("g:"):
+            gr = named[k[2:]].grad.flatten().cpu()
+            gr = gr[:: max(1, gr.numel() // 256)][:256].numpy()
+            assert np.abs(gr - g[k]).max() <= tol * max(np.abs(g[k]).max(), 1e-3), k
+    assert np.abs(out[4][0, :, 0].detach().cpu().numpy()[:, ::2, ::2] - g["alphas"]).max() < tol
+    assert np.abs(out[5][0].detach().cpu().numpy()[:, :, ::4, ::4] - g["preds_trimap"]).max() < tol
+
+
+def test_stage4_step_matches_reference_golden_cpu():
+    """host logic of the stage-4 step (graph, losses, parameter names) with the composite read standing in for the CUDA
+    kernels; the GPU test of the same name in test_gpu_train.py runs it with the fused read"""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from train_step_ddp import composite_read
+    _stage4_against_golden("cpu", composite_read, 2e-3)
+
+
+def test_stage4_ddp_step_two_ranks_gloo():
+    """BASELINE configs[4] plumbing on CPU: the whole stage-4 model under DDP (gloo, world_size 2), 295.5 MB of fp32
+    gradients all-reduced per step (SURVEY 8(d) cfg 5), ranks in sync afterwards"""
+    import json
+    env = dict(os.environ, OTVM_TRAIN_CPU="1", MODEL="stage4", SIZE="64", STEPS="1", WARMUP="0", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29619", os.path.join(ROOT, "scripts", "train_step_ddp.py")],
+                       env=env, capture_output=True, text=True, timeout=900)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert line, r.stdout + r.stderr
+    d = json.loads(line[-1])
+    assert d["n_ranks"] == 2 and d["ranks_in_sync"] is True
+    assert d["parameters"] == 73_887_684 and d["allreduce_bytes_per_step"] == 295_550_736
