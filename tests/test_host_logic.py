@@ -262,7 +262,7 @@ def test_read_block_ddp_step_two_ranks_gloo():
     assert d["allreduce_bytes_per_step"] == 4 * d["parameters"] and d["parameters"] > 14_000_000
 
 
-def _stage4_against_golden(device, read_fn, tol):
+def _stage4_against_golden(device, read_fn, tol, tol_grad=None):
     """one stage-4 training step (forward, four losses, backward) of otvm_b200.train_stage4 against the REFERENCE's own
     step on the same weights / sample (tests/golden/train_step_s4.npz, oracle/make_golden_train.py)"""
     import numpy as np
@@ -283,11 +283,12 @@ def _stage4_against_golden(device, read_fn, tol):
     named = dict(m.named_parameters())
     gsq = sum(float(v.grad.double().pow(2).sum()) for v in named.values() if v.grad is not None)
     assert abs(gsq ** 0.5 - float(g["grad_norm"])) <= tol * float(g["grad_norm"])
+    tol_grad = tol_grad or tol
     for k in g.files:
         if k.startswith("g:"):
             gr = named[k[2:]].grad.flatten().cpu()
             gr = gr[:: max(1, gr.numel() // 256)][:256].numpy()
-            assert np.abs(gr - g[k]).max() <= tol * max(np.abs(g[k]).max(), 1e-3), k
+            assert np.abs(gr - g[k]).max() <= tol_grad * max(np.abs(g[k]).max(), 1e-3), k
     assert np.abs(out[4][0, :, 0].detach().cpu().numpy()[:, ::2, ::2] - g["alphas"]).max() < tol
     assert np.abs(out[5][0].detach().cpu().numpy()[:, :, ::4, ::4] - g["preds_trimap"]).max() < tol
 
