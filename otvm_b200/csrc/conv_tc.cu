@@ -71,7 +71,8 @@ struct ConvTcArgs {
   uint32_t p_off, stage_off;   // byte offsets of the patch ring and of the two epilogue staging tiles (weights sit at 0)
 };
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;       // TMA + MMA warps + ONE group of four epilogue warps
+constexpr int kConvThreadsMax = 320;    // ... + a second epilogue group (BN >= 64): the groups split the tile's columns
 
 // per-chunk GroupNorm partial sums: CGC consecutive channels form one slot.  Every thread (= tile row) parks its
 // partial (sum, sum of squares) per slot in shared memory, sred[which][slot][129]; after the chunk loop one thread
@@ -110,22 +111,57 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
 constexpr uint32_t kPairA = 0x201100u, kPairB = 0x021010u;
 
 // 8 fp32 values -> `planes` bf16 planes, 16 bytes each at base + plane * stride (x is consumed)
-__device__ __forceinline__ void split_store8(uint8_t* base, uint32_t stride, int planes, float (&x)[8]) {
-#pragma unroll 1
-  for (int pl = 0; pl < planes; ++pl) {
-    uint32_t pk[4];
+__device__ __forceinline__ uint4 pack8_and_subtract(float (&x)[8], bool subtract) {
+  uint32_t pk[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
-      pk[e] = *reinterpret_cast<const uint32_t*>(&h);
-      x[2 * e] -= __low2float(h); x[2 * e + 1] -= __high2float(h);
-    }
-    *reinterpret_cast<uint4*>(base + (size_t)pl * stride) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  for (int e = 0; e < 4; ++e) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x[2 * e], x[2 * e + 1]);
+    pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+    if (subtract) { x[2 * e] -= __low2float(h); x[2 * e + 1] -= __high2float(h); }
+  }
+  return make_uint4(pk[0], pk[1], pk[2], pk[3]);
+}
+__device__ __forceinline__ void split_store8(uint8_t* base, uint32_t stride, int planes, float (&x)[8]) {
+  // (straight-line per plane count: the remainder is not computed behind the last plane)
+  if (planes == 1) {
+    *reinterpret_cast<uint4*>(base) = pack8_and_subtract(x, false);
+  } else if (planes == 2) {
+    *reinterpret_cast<uint4*>(base) = pack8_and_subtract(x, true);
+    *reinterpret_cast<uint4*>(base + stride) = pack8_and_subtract(x, false);
+  } else {
+    *reinterpret_cast<uint4*>(base) = pack8_and_subtract(x, true);
+    *reinterpret_cast<uint4*>(base + stride) = pack8_and_subtract(x, true);
+    *reinterpret_cast<uint4*>(base + 2 * (size_t)stride) = pack8_and_subtract(x, false);
   }
 }
 
+__device__ __forceinline__ void bar_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Sum of the 128 row partials of every (statistic, slot) column of `sred` -> one fp64 atomic per column.  `nthr` epilogue
+// threads (e = 0 .. nthr-1, whole warps) share the 2 * nslot columns: `per` = 1, 2 or 4 threads per column, each adds
+// 128 / per rows in an order that keeps the 32 lanes of a warp on 32 different banks (column pitch 129), then a shuffle
+// tree.  (One thread per column walking 128 rows was ~600 cycles of the GroupNorm-fused epilogue's critical path.)
+__device__ __forceinline__ void gn_reduce_columns(const float* sred, int e, int nthr, int nslot, int cgc, int cg, int n0, int Cout,
+                                                  double* gn_stats) {
+  const int ncol = 2 * nslot;
+  const int per = nthr >= 4 * ncol ? 4 : nthr >= 2 * ncol ? 2 : 1;
+  const int col = e / per, sub = e - col * per;
+  const int rows = 128 / per, rot = (32 / per) * sub;
+  const int which = col / nslot, slot = col - which * nslot;
+  const bool live = col < ncol && n0 + slot * cgc < Cout;
+  float acc = 0.f;
+  if (live) {
+    const float* colp = sred + (which * 32 + slot) * kSredPitch + rows * sub;
+#pragma unroll 8
+    for (int j = 0; j < rows; ++j) acc += colp[(j + rot) & (rows - 1)];
+  }
+  if (per >= 2) acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (per >= 4) acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (live && sub == 0) atomicAdd(&gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
+}
+
 template <int BN, int GN, int EPI, bool HALO>
-__global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
                                                                const __grid_constant__ CUtensorMap tmR,
@@ -171,8 +207,8 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_n(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 2 * 128; i += kConvThreads) sstat[i] = 0.f;
-  for (int i = threadIdx.x; i < BN; i += kConvThreads) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+  // (the bias is fetched by the epilogue warps behind this barrier: a global load in front of it put ~700 cycles of
+  // memory latency into every CTA's prologue)
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
@@ -403,25 +439,88 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
   }
 }
   if (warp >= 2) {
-    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    // ===== epilogue: warps 2..5 (and 6..9 when the block has a second group) own TMEM lanes 32*(warp%4) .. +31 =====
     // Compile-time variants (EPI) keep the per-element instruction count low: the three store paths and the
     // residual paths would otherwise all be issued as predicated-off instructions (measured: 1800 SASS
     // instructions per 32-column chunk, which made the epilogue issue-bound at ~2000 cycles per chunk).
+    //
+    // Short-K layers are bound by THIS code, not by the MMAs (scripts/conv_ts4.py, 64 -> 256 1x1 at 128^2, two planes:
+    // accumulator ready after 2.1 us, epilogue 4.3 us plain / 7.6 us with a residual / 15 us GroupNorm-fused).  Hence:
+    //   * two groups of four warps split the tile's columns (the chain tcgen05.ld -> bias -> residual -> activation ->
+    //     plane split -> st.shared is latency-bound at one warp per scheduler),
+    //   * the residual of a chunk is requested before the accumulator wait / while the previous chunk is processed,
+    //   * each 64-column sub-tile is handed to the TMA store as soon as it is staged, so the store overlaps the rest.
     constexpr bool kRes = (EPI & EPI_RES) != 0, kRelu2 = (EPI & EPI_RELU2) != 0, kDirect = (EPI & EPI_DIRECT) != 0;
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;                         // epilogue group 0 / 1
     const int r = q * 32 + lane;                             // tile row = pixel
     const int ty = r >> a.tw_shift, tx = r - (ty << a.tw_shift);
     const int oy = y0 + ty, ox = x0 + tx;
     const bool valid = oy < a.Ho && ox < a.Wo;
     const int64_t pix = ((int64_t)n_img * a.Ho + oy) * a.Wo + ox;
-    constexpr int CH = BN >= 32 ? 32 : 16;                   // columns per TMEM load
+    // columns per TMEM load: 32; 16 with a residual (two prefetched residual planes + main / cross accumulator chunks must
+    // fit the 96 registers that keep two 320-thread CTAs on an SM)
+    constexpr int CH = (BN >= 32 && !kRes) ? 32 : 16;
+    constexpr int NCHUNK = BN / CH;
+    // column range of this group: BN = 128 -> one 64-column sub-tile per group, BN = 64 -> one 32-column chunk per group
+    const int ngrp = (NCHUNK >= 2 && blockDim.x > kConvThreads) ? 2 : 1;
+    const int nthr = 128 * ngrp;                             // epilogue threads (GroupNorm barriers / reductions)
+    const int c_lo = grp * (BN / ngrp), c_hi = c_lo + BN / ngrp;
+    const bool idle = grp >= ngrp;                           // (a second group on a tile with a single chunk)
     const int cg = GN != GN_NONE ? a.Cout / 32 : 0;          // channels per GroupNorm group
     const int cgc = cg < CH ? cg : CH;
     constexpr uint32_t TILE = 128u * BN * 2u;                  // one bf16 staging tile (one plane of the output tile)
     const uint32_t nplane = (uint32_t)a.planes;
     float* sred = reinterpret_cast<float*>(smem + nplane * TILE);     // behind the staging tiles, inside the drained stages
-    // act(v) = max(v,0) + slope*min(v,0): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
+    // act(v) = max(v, slope * v): none -> 1, ReLU -> 0, LeakyReLU -> 0.01
     const float slope = a.act == OTVM_ACT_NONE ? 1.f : a.act == OTVM_ACT_RELU ? 0.f : 0.01f;
+    const int e = threadIdx.x - 64;                          // 0 .. nthr-1
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+
+    // residual planes 0 / 1 of one chunk (a third plane is fetched where it is added)
+    uint4 rr[2][CH / 8];
+    auto load_res = [&](int cbase) {
+      if constexpr (kRes) {
+#pragma unroll
+        for (int pl = 0; pl < 2; ++pl) {
+          if ((uint32_t)pl < nplane) {
+            const uint4* rp = reinterpret_cast<const uint4*>(a.res + (int64_t)pl * a.act_plane + pix * a.res_ld + cbase);
+#pragma unroll
+            for (int j = 0; j < CH / 8; ++j) rr[pl][j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
+    };
+    // accumulator chunk (main + cross-plane columns) -> raw[]
+    auto load_acc = [&](int c, uint32_t (&raw)[CH]) {
+      uint32_t raw2[CH];
+      if constexpr (CH == 32) tmem_ld32(trow + (uint32_t)c, raw); else tmem_ld16(trow + (uint32_t)c, raw);
+      if (nplane > 1) {
+        if constexpr (CH == 32) tmem_ld32(trow + ACC_COLS + (uint32_t)c, raw2); else tmem_ld16(trow + ACC_COLS + (uint32_t)c, raw2);
+      }
+      tmem_wait_ld();
+      if (nplane > 1) {
+#pragma unroll
+        for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
+      }
+    };
+    auto stats_chunk = [&](const float (&qv)[CH], int c) {
+      const int slot0 = c / cgc;
+      switch (cgc) {
+        case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
+        case 2: gn_chunk<CH, 2>(qv, r, sred, slot0); break;
+        case 4: gn_chunk<CH, 4>(qv, r, sred, slot0); break;
+        case 8: gn_chunk<CH, 8>(qv, r, sred, slot0); break;
+        case 16: gn_chunk<CH, 16>(qv, r, sred, slot0); break;
+        default: gn_chunk<CH, CH>(qv, r, sred, slot0); break;
+      }
+    };
+
+    if (!idle) {                                             // (whole warps: a second group on a single-chunk tile does nothing)
+    // bias (a constant: no PDL dependency, and warp 2 -- weight / patch producer first -- has waited anyway)
+    for (int i = e; i < BN; i += nthr) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+    if (n0 + c_lo < a.Cout) load_res(n0 + c_lo);             // in flight while the last MMAs finish
+    bar_sync_n(1, nthr);                                     // bias visible to every epilogue thread
     mbar_wait(accum_bar, 0);
     tcgen05_after_sync();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
@@ -430,54 +529,24 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       // stays in TMEM), a grid-wide barrier makes every CTA's contribution visible, pass 2 (the loop below)
       // normalises.  The host only selects this variant when the whole grid is co-resident (one wave).
 #pragma unroll 1
-      for (int c = 0; c < BN; c += CH) {
+      for (int c = c_lo; c < c_hi; c += CH) {
         if (n0 + c >= a.Cout) break;
         uint32_t raw[CH];
-        if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-        else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-        tmem_wait_ld();
-        if (nplane > 1) {                                    // + cross-plane accumulator
-          uint32_t raw2[CH];
-          if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
-          else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-        }
+        load_acc(c, raw);
         float qv[CH];
 #pragma unroll
         for (int j = 0; j < CH; ++j) qv[j] = valid ? __uint_as_float(raw[j]) + sbias[c + j] : 0.f;
-        const int slot0 = c / cgc;
-        switch (cgc) {
-          case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
-          case 2: gn_chunk<CH, 2>(qv, r, sred, slot0); break;
-          case 4: gn_chunk<CH, 4>(qv, r, sred, slot0); break;
-          case 8: gn_chunk<CH, 8>(qv, r, sred, slot0); break;
-          case 16: gn_chunk<CH, 16>(qv, r, sred, slot0); break;
-          default: gn_chunk<CH, CH>(qv, r, sred, slot0); break;
-        }
+        stats_chunk(qv, c);
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int e = threadIdx.x - 64;
-      {
-        const int nslot = BN / cgc;
-        if (e < 2 * nslot) {
-          const int which = e / nslot, slot = e - which * nslot;
-          if (n0 + slot * cgc < a.Cout) {
-            const float* row = sred + (which * 32 + slot) * kSredPitch;
-            float acc = 0.f;
-#pragma unroll 8
-            for (int i = 0; i < 128; ++i) acc += row[i];
-            atomicAdd(&a.gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // this CTA's atomics are issued
+      bar_sync_n(1, nthr);
+      gn_reduce_columns(sred, e, nthr, BN / cgc, cgc, cg, n0, a.Cout, a.gn_stats);
+      bar_sync_n(1, nthr);                                    // this CTA's atomics are issued
       if (e == 0) {
         unsigned int* ctr = reinterpret_cast<unsigned int*>(a.gn_stats + 64);     // zeroed with the statistics arena
         const unsigned int total = gridDim.x * gridDim.y;
-        __threadfence();
-        atomicAdd(ctr, 1u);
+        // release at gpu scope: the CTA's statistics atomics (ordered before this by the barrier) are visible to whoever
+        // acquires the incremented counter
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
         // Bounded wait.  The host only selects this variant for grids it computed to be co-resident, but it cannot see
         // what else shares the device (other streams / processes, MPS, a debugger): if a CTA is still missing after
         // ~1 s the kernel gives up WITHOUT trapping (a trap would poison the whole CUDA context, graph replays included):
@@ -485,12 +554,11 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         // statistics have arrived, so this launch's output is wrong but the process and the stream stay usable.
         uint32_t spins = 0;
         while (ld_acquire_gpu(ctr) < total) {
-          __nanosleep(64);
-          if (++spins > (1u << 23)) { atomicOr(&g_device_error_flags, 1u); break; }
+          __nanosleep(20);
+          if (++spins > (1u << 24)) { atomicOr(&g_device_error_flags, 1u); break; }
         }
-        __threadfence();
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bar_sync_n(1, nthr);
       if (e < BN && n0 + e < a.Cout) {
         const int ch = n0 + e, g = ch / cg;
         // (fp64 only for the cancelling subtraction; fp64 division / square root run at 1/64 rate on this part)
@@ -501,32 +569,36 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
         sstat[e] = sc;
         sstat[128 + e] = a.gn_beta[ch] - (float)mean * sc;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      bar_sync_n(1, nthr);
     }
+    // sub-tile hand-over to the TMA store: the threads that staged a 64-column sub-tile meet on a named barrier and one
+    // of them issues its stores; BN = 128 with two groups: each group owns one sub-tile (barriers 2 / 3, 128 threads)
+    const bool own_sub = ngrp == 2 && BN == 128;
+    const int store_bar = own_sub ? 2 + grp : 2, store_thr = own_sub ? 128 : nthr;
+    const bool storer = own_sub ? (threadIdx.x == 64 + 128 * grp) : threadIdx.x == 64;
+    auto store_sub = [&](int sub) {
+      if constexpr (!kDirect) {
+        fence_proxy_async_smem();                             // generic-proxy smem writes -> visible to the TMA engine
+        bar_sync_n(store_bar, store_thr);
+        if (storer && n0 + sub * 64 < a.Cout) {
+          constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += CH) {
+          for (uint32_t pl = 0; pl < nplane; ++pl) {
+            tma_store_5d(&tmO, smem + pl * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
+            if constexpr (kRelu2)
+              tma_store_5d(&tmR, smem + (nplane + pl) * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+    };
+    int pending_sub = -1;                                    // staged sub-tile not yet handed to the TMA store
+#pragma unroll 1
+    for (int c = c_lo; c < c_hi; c += CH) {
       const int cbase = n0 + c;
-      if (cbase >= a.Cout) break;                            // warp-uniform
+      if (cbase >= a.Cout) break;                            // uniform over the threads that share a sub-tile
       uint32_t raw[CH];
-      if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-      else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
-      // residual for this chunk is fetched while the TMEM load is in flight (host guarantees 16-byte alignment
-      // and Cout % CH == 0 whenever EPI_RES is selected)
-      uint4 rr[CH / 8];
-      if constexpr (kRes) {
-        const uint4* rp = reinterpret_cast<const uint4*>(a.res + pix * a.res_ld + cbase);
-#pragma unroll
-        for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
-      }
-      tmem_wait_ld();
-      if (nplane > 1) {                                      // + cross-plane accumulator
-        uint32_t raw2[CH];
-        if constexpr (CH == 32) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
-        else tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + ACC_COLS + (uint32_t)c, raw2);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
-      }
+      load_acc(c, raw);
       if (dbg && threadIdx.x == 64 && c == 0) dbg[8] = clock64();
       float v[CH];
 #pragma unroll
@@ -550,34 +622,34 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < CH; ++j) qv[j] = valid ? v[j] : 0.f;
         }
-        const int slot0 = c / cgc;
-        switch (cgc) {
-          case 1: gn_chunk<CH, 1>(qv, r, sred, slot0); break;
-          case 2: gn_chunk<CH, 2>(qv, r, sred, slot0); break;
-          case 4: gn_chunk<CH, 4>(qv, r, sred, slot0); break;
-          case 8: gn_chunk<CH, 8>(qv, r, sred, slot0); break;
-          case 16: gn_chunk<CH, 16>(qv, r, sred, slot0); break;
-          default: gn_chunk<CH, CH>(qv, r, sred, slot0); break;
-        }
+        stats_chunk(qv, c);
       }
       if constexpr (kRes) {
-#pragma unroll 1
-        for (uint32_t pl = 0; pl < nplane; ++pl) {
-          if (pl != 0) {                                       // further planes of a split residual
-            const uint4* rp = reinterpret_cast<const uint4*>(a.res + (int64_t)pl * a.act_plane + pix * a.res_ld + cbase);
 #pragma unroll
-            for (int j = 0; j < CH / 8; ++j) rr[j] = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
-          }
+        for (int pl = 0; pl < 2; ++pl) {
+          if ((uint32_t)pl < nplane) {
 #pragma unroll
-          for (int j = 0; j < CH / 8; ++j) {
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+            for (int j = 0; j < CH / 8; ++j) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&rr[pl][j]);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) { v[8 * j + 2 * e] += __low2float(h[e]); v[8 * j + 2 * e + 1] += __high2float(h[e]); }
+              for (int k = 0; k < 4; ++k) { v[8 * j + 2 * k] += __low2float(h[k]); v[8 * j + 2 * k + 1] += __high2float(h[k]); }
+            }
           }
         }
+        if (nplane > 2) {                                      // third plane of a split residual
+          const uint4* rp = reinterpret_cast<const uint4*>(a.res + 2 * a.act_plane + pix * a.res_ld + cbase);
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) {
+            const uint4 t = valid ? __ldg(rp + j) : make_uint4(0, 0, 0, 0);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[8 * j + 2 * k] += __low2float(h[k]); v[8 * j + 2 * k + 1] += __high2float(h[k]); }
+          }
+        }
+        if (c + CH < c_hi && cbase + CH < a.Cout) load_res(cbase + CH);     // next chunk's residual: in flight during the split
       }
 #pragma unroll
-      for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], 0.f) + slope * fminf(v[j], 0.f);
+      for (int j = 0; j < CH; ++j) v[j] = fmaxf(v[j], slope * v[j]);
       if constexpr (!kDirect) {
         // swizzled staging tile(s): [BN/64][128 rows][min(BN,64) ch]; 16-byte chunk j of row r lands at the address the
         // TMA swizzle expects, so 8 consecutive rows cover all 32 banks (conflict-free 16 B stores).  Rows outside
@@ -591,13 +663,17 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
           float x8[8];
           if constexpr (kRelu2) {                              // second output = ReLU(out): tiles nplane .. 2 nplane - 1
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x8[e] = fmaxf(v[8 * j + e], 0.f);
+            for (int k = 0; k < 8; ++k) x8[k] = fmaxf(v[8 * j + k], 0.f);
             split_store8(smem + nplane * TILE + off, TILE, a.planes, x8);
           }
 #pragma unroll
-          for (int e = 0; e < 8; ++e) x8[e] = v[8 * j + e];
+          for (int k = 0; k < 8; ++k) x8[k] = v[8 * j + k];
           split_store8(smem + off, TILE, a.planes, x8);
         }
+        // a 64-column sub-tile is complete after its last chunk (BN = 128); with one group the remaining chunks overlap
+        // the store of the first sub-tile
+        pending_sub = c >> 6;
+        if constexpr (BN == 128) { if ((c & 63) == 64 - CH) { store_sub(pending_sub); pending_sub = -1; } }
       } else if (valid) {
         // direct stores: fp32 heads ([P][8] / [P][12]) and the channel-major value bank (lanes = consecutive pixels)
         if (a.out_f32) {
@@ -619,41 +695,18 @@ __global__ void __launch_bounds__(kConvThreads) conv_tc_kernel(const __grid_cons
       }
     }
     if (dbg && threadIdx.x == 64) dbg[9] = clock64();
-    if (!kDirect) {
-      fence_proxy_async_smem();                               // generic-proxy smem writes -> visible to the TMA engine
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (threadIdx.x == 64) {
-        constexpr int NSUB = BN > 64 ? BN / 64 : 1;
-        constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2;
-#pragma unroll 1
-        for (uint32_t pl = 0; pl < nplane; ++pl) {
-#pragma unroll
-          for (int sub = 0; sub < NSUB; ++sub) {
-            if (n0 + sub * 64 >= a.Cout) break;
-            tma_store_5d(&tmO, smem + pl * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
-            if constexpr (kRelu2)
-              tma_store_5d(&tmR, smem + (nplane + pl) * TILE + (size_t)sub * 128 * ROWB, n0 + sub * 64, x0, y0, n_img, (int)pl);
-          }
-        }
-        tma_store_commit_and_wait();
-      }
+    if constexpr (!kDirect) {
+      // BN = 128: a sub-tile whose second chunk lies beyond Cout is still pending; BN <= 64: ONE sub-tile, staged by every
+      // epilogue thread (a group whose columns lie beyond Cout staged nothing but takes part in the hand-over barrier)
+      if constexpr (BN == 128) { if (pending_sub >= 0) store_sub(pending_sub); } else store_sub(0);
+      if (storer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging tiles read before the CTA exits
     }
     if constexpr (GN == GN_STATS) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-      const int e = threadIdx.x - 64;                         // 0..127: (which, slot) = (e / 32.., e % nslot)
-      const int nslot = BN / cgc;                             // <= 32 (host-checked)
-      if (e < 2 * nslot) {
-        const int which = e / nslot, slot = e - which * nslot;
-        if (n0 + slot * cgc < a.Cout) {
-          const float* row = sred + (which * 32 + slot) * kSredPitch;
-          float acc = 0.f;
-#pragma unroll 8
-          for (int i = 0; i < 128; ++i) acc += row[i];
-          atomicAdd(&a.gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
-        }
-      }
+      bar_sync_n(1, nthr);                                    // the epilogue warps only
+      gn_reduce_columns(sred, e, nthr, BN / cgc, cgc, cg, n0, a.Cout, a.gn_stats);
     }
     if (dbg && threadIdx.x == 64) dbg[6] = clock64();
+    }
     tcgen05_before_sync();
   }
   __syncthreads();
@@ -1120,6 +1173,14 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   return dev >= 0 && otvm_device_is_sm100(dev) == 1;
 }
 
+// block size: tiles of >= 64 channels (two or four 32-column chunks) get a second group of four epilogue warps
+// (OTVM_CONV_EPI_GROUPS=1 keeps one)
+template <int BN>
+static int conv_threads() {
+  static const int groups = getenv("OTVM_CONV_EPI_GROUPS") ? atoi(getenv("OTVM_CONV_EPI_GROUPS")) : 2;
+  return (BN >= 64 && groups >= 2) ? kConvThreadsMax : kConvThreads;
+}
+
 template <int BN, int GN, int EPI, bool HALO>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s, bool dry_run) {
@@ -1135,7 +1196,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
       regs = fa.numRegs > 0 ? fa.numRegs : 255;
     }
     const int regs_per_warp = ((regs * 32 + 255) / 256) * 256;
-    const int by_regs = 65536 / (regs_per_warp * (kConvThreads / 32));
+    const int by_regs = 65536 / (regs_per_warp * (conv_threads<BN>() / 32));
     const int by_smem = (int)((227u * 1024u) / (smem + 1024));
     const int tmem_cols = (BN < 32 ? 32 : BN) * (a.planes > 1 ? 2 : 1);
     int occ = by_regs < by_smem ? by_regs : by_smem;
@@ -1145,7 +1206,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     if ((int64_t)grid.x * grid.y * grid.z > (int64_t)occ * sm_count()) return OTVM_ERR_UNSUPPORTED;
   }
   if (dry_run) return OTVM_OK;
-  launch_k(conv_tc_kernel<BN, GN, EPI, HALO>, grid, kConvThreads, smem, s, tmA, tmB, tmO, tmR, a);
+  launch_k(conv_tc_kernel<BN, GN, EPI, HALO>, grid, conv_threads<BN>(), smem, s, tmA, tmB, tmO, tmR, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
