@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define OTVM_ABI_VERSION 4
+#define OTVM_ABI_VERSION 5
 #if defined(__GNUC__)
 #define OTVM_API __attribute__((visibility("default")))
 #else
@@ -107,6 +107,13 @@ typedef struct {
    * OTVM_ERR_UNSUPPORTED otherwise and launches nothing). */
   const float* gn_gamma; const float* gn_beta;
   int64_t w_plane_stride;                         /* split formats: elements between the planes of `weight`  */
+  /* Channels per GroupNorm group; 0 = Cout / 32 (GroupNorm(32, Cout) over this call's channels).  A caller can run
+   * a wide layer as channel SLICES -- one call per slice with the slice's weights / gamma / beta / out / res views,
+   * gn_group_ch = full Cout / 32 and its own statistics slot: the slice then holds Cout / gn_group_ch whole groups
+   * (statistics [Cout / gn_group_ch][2]).  Groups never straddle slices, so the result is that of the unsliced
+   * layer, and a slice whose grid is one co-resident wave can take the fused path (gn_gamma) where the whole layer
+   * could not (FBA layer4: 512 -> 2048 at 1/8 resolution).  tcgen05 path only. */
+  int32_t gn_group_ch;
 } otvm_conv_params;
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d can run this problem with the GroupNorm fused into the convolution kernel (see gn_gamma) */

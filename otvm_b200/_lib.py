@@ -31,6 +31,7 @@ class ConvParams(C.Structure):
         ("gn_stats_zeroed", c_i32), ("gn_eps", c_f),
         ("gn_gamma", c_vp), ("gn_beta", c_vp),
         ("w_plane_stride", c_i64),
+        ("gn_group_ch", c_i32),
     ]
 
 
@@ -116,7 +117,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the export is missing
         fn.restype, fn.argtypes = res, args
-    if lib.otvm_version() != 4:
+    if lib.otvm_version() != 5:
         raise OtvmError("ABI version mismatch")
     _lib = lib
     return lib

@@ -278,6 +278,7 @@ int conv2d_simt(const otvm_conv_params* p, cudaStream_t s) {
   if (a.M <= 0 || a.Cout <= 0) return OTVM_OK;
   if (p->gn_stats) {
     if (p->N != 1 || p->Cout % 32 != 0) return OTVM_ERR_UNSUPPORTED;
+    if (p->gn_group_ch > 0 && p->gn_group_ch != p->Cout / 32) return OTVM_ERR_UNSUPPORTED;   // channel slices: tcgen05 path only
     if (!p->gn_stats_zeroed) OTVM_CUDA_CHECK(cudaMemsetAsync(p->gn_stats, 0, sizeof(double) * 64, s));
   }
   // (out_f32 with bf16 / split inputs: the kernel's T covers in / weight / res, `out` is written as float)

@@ -65,6 +65,7 @@ struct ConvTcArgs {
   double* gn_stats;
   const float* gn_gamma; const float* gn_beta; float gn_eps;   // GN == 2: normalise in this kernel (grid barrier)
   double gn_inv_cnt;           // 1 / elements per GroupNorm group
+  int gn_cg;                   // channels per GroupNorm group (Cout / 32 unless the caller runs a channel slice)
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
   // persistent patch-mode kernel (conv_tc_persist_kernel): tiles walked per CTA, smem carve-up
   int ntiles;                  // tiles_x * tiles_y * N
@@ -467,7 +468,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     const int nthr = 128 * ngrp;                             // epilogue threads (GroupNorm barriers / reductions)
     const int c_lo = grp * (BN / ngrp), c_hi = c_lo + BN / ngrp;
     const bool idle = grp >= ngrp;                           // (a second group on a tile with a single chunk)
-    const int cg = GN != GN_NONE ? a.Cout / 32 : 0;          // channels per GroupNorm group
+    const int cg = GN != GN_NONE ? a.gn_cg : 0;              // channels per GroupNorm group
     const int cgc = cg < CH ? cg : CH;
     constexpr uint32_t TILE = 128u * BN * 2u;                  // one bf16 staging tile (one plane of the output tile)
     const uint32_t nplane = (uint32_t)a.planes;
@@ -752,8 +753,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* w_full = reinterpret_cast<uint64_t*>(smem + a.aux_off);
-  uint64_t* p_full = w_full + 1;                                      // [8] patch ring
-  uint64_t* p_empty = p_full + 8;                                     // [8]
+  uint64_t* p_full = w_full + 1;                                      // [2][8] patch ring: one "full" barrier per pipeline and slot
+  uint64_t* p_empty = p_full + 16;                                    // [8]
   uint64_t* acc_full = p_empty + 8;                                   // [4] accumulator 2g+b ready for epilogue group g
   uint64_t* acc_empty = acc_full + 4;                                 // [4] accumulator 2g+b drained (4 warp arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
@@ -768,7 +769,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmO);
     mbar_init(w_full, 1);
-    for (int i = 0; i < 8; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < 16; ++i) mbar_init(&p_full[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&p_empty[i], 1);
     for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     fence_barrier_init();
   }
@@ -812,9 +814,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       for (int chunk = 0; chunk < a.nchunk; ++chunk) {
         mbar_wait(&p_empty[slot], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&p_full[slot], p_tx);
+          // the patch completes on the barrier of the pipeline that consumes this tile (i even / odd): each pipeline's
+          // barrier of a slot then counts only its OWN fills, and the parity it waits for is exact at any ring depth
+          uint64_t* fb = &p_full[(i & 1) * 8 + slot];
+          mbar_arrive_expect_tx(fb, p_tx);
           for (int pl = 0; pl < a.planes; ++pl)
-            tma_load_5d(smem + a.p_off + (size_t)slot * slot_bytes + (size_t)pl * a.patch_bytes, &tmA, &p_full[slot],
+            tma_load_5d(smem + a.p_off + (size_t)slot * slot_bytes + (size_t)pl * a.patch_bytes, &tmA, fb,
                         chunk * a.KC, cx, cy, n_img, pl);
         }
         __syncwarp();
@@ -835,8 +840,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
     const uint32_t kx16 = ((uint32_t)d * a.row_bytes) >> 4, ky16 = ((uint32_t)(d * pw) * a.row_bytes) >> 4;
     mbar_wait(w_full, 0);
     // patch-ring position of this pipeline's first tile; every tile consumes nchunk consecutive slots
-    int slot = 0; uint32_t ph = 0;
-    auto skip = [&](int n) { slot += n; while (slot >= a.na) { slot -= a.na; ph ^= 1; } };
+    int slot = 0; uint32_t fills = 0;
+    auto skip = [&](int n) { slot += n; while (slot >= a.na) slot -= a.na; };
     if (g) skip(a.nchunk);
     int j = 0;                                                   // tiles done by this pipeline
     for (int t = blockIdx.x + g * gridDim.x; t < a.ntiles; t += 2 * gridDim.x, ++j) {
@@ -846,7 +851,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
       const uint32_t d_tmem = tmem_base + (uint32_t)ab * ACCW;
       OTVM_PSTAMP(2 * j + g, 1);
       for (int chunk = 0; chunk < a.nchunk; ++chunk) {
-        mbar_wait(&p_full[slot], ph);
+        // own "full" barrier of this slot, parity of the number of own fills so far (bit `slot` of fills)
+        mbar_wait(&p_full[g * 8 + slot], (fills >> slot) & 1u);
+        fills ^= 1u << slot;
         tcgen05_after_sync();
         if (chunk == a.nchunk - 1) OTVM_PSTAMP(2 * j + g, 2);
         if (elect_one()) {
@@ -874,7 +881,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) conv_tc_persist_kernel(con
           if (chunk == a.nchunk - 1) umma_commit(&acc_full[ab]);
         }
         __syncwarp();
-        if (++slot == a.na) { slot = 0; ph ^= 1; }
+        if (++slot == a.na) slot = 0;
       }
       OTVM_PSTAMP(2 * j + g, 3);
       skip(a.nchunk);                                            // the other pipeline's tile
@@ -1013,14 +1020,19 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
                                                             const float* __restrict__ bias, cptr_t<T> res,
                                                             int64_t res_ld, int act, void* __restrict__ out, int64_t out_ps,
                                                             int64_t out_cs, int out_f32, ptr_t<T> out_relu,
-                                                            int64_t out_relu_ld, double* __restrict__ gn_stats, int64_t ps) {
+                                                            int64_t out_relu_ld, double* __restrict__ gn_stats, int64_t ps,
+                                                            int gn_cg) {
   pdl_sync();                                  // PDL contract (common.cuh)
-  __shared__ double sstat[32][2];      // fp64 partials: (near-)exact sums, so the atomic order does not change the result
+  // fp64 partials: (near-)exact sums, so the atomic order does not change the result.  One copy per warp: shared-memory
+  // fp64 atomics are compare-and-swap loops, and eight warps retrying on the same 64 words made this kernel 3x slower
+  // than its memory traffic (21.7 us for 12 MB behind the 3072 -> 256 convolution)
+  __shared__ double sstat_w[8][32][2];
+  double (*sstat)[2] = sstat_w[threadIdx.x >> 5];
   const int c4n = Cout >> 2;
   const int64_t total = M * c4n;
-  const int cg = gn_stats ? Cout / 32 : 1;
+  const int cg = gn_stats ? gn_cg : 1;
   if (gn_stats) {
-    if (threadIdx.x < 32) { sstat[threadIdx.x][0] = 0.0; sstat[threadIdx.x][1] = 0.0; }
+    sstat[threadIdx.x & 31][0] = 0.0; sstat[threadIdx.x & 31][1] = 0.0;
     __syncthreads();
   }
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -1071,9 +1083,12 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
   }
   if (gn_stats) {
     __syncthreads();
-    if (threadIdx.x < 32) {
-      atomicAdd(&gn_stats[threadIdx.x * 2 + 0], sstat[threadIdx.x][0]);
-      atomicAdd(&gn_stats[threadIdx.x * 2 + 1], sstat[threadIdx.x][1]);
+    if (threadIdx.x < 64) {
+      const int g = threadIdx.x >> 1, which = threadIdx.x & 1;
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sstat_w[w][g][which];
+      atomicAdd(&gn_stats[g * 2 + which], t);
     }
   }
 }
@@ -1159,11 +1174,12 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   const int Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
   if (Wo < 8 || Ho < 1) return false;
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
-  if (p->gn_stats && (p->N != 1 || p->Cout % 32 != 0)) return false;
+  const int gcg = p->gn_group_ch > 0 ? p->gn_group_ch : p->Cout / 32;      // channels per GroupNorm group
+  if (p->gn_stats && (p->N != 1 || gcg < 1 || p->Cout % gcg != 0 || p->Cout / gcg > 32)) return false;
   const int bn = pick_bn(p);
   if (conv_tc_epi(p, bn) < 0) return false;
   if (p->gn_stats) {            // a GroupNorm group must not straddle tiles / 16-column chunks irregularly
-    const int cg = p->Cout / 32;
+    const int cg = gcg;
     if (bn < 32) return false;
     if (cg > 32 && (cg % 32 != 0 || bn % cg != 0)) return false;
     if (cg <= 32 && 32 % cg != 0) return false;
@@ -1214,7 +1230,7 @@ static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
 template <int BN, int GN, int KSTEPS>
 static int launch_conv_persist(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvTcArgs& a,
                                dim3 grid, size_t smem, cudaStream_t s) {
-  OTVM_CUDA_CHECK((ensure_dynamic_smem<conv_tc_persist_kernel<BN, GN, KSTEPS>>(220 * 1024)));
+  OTVM_CUDA_CHECK((ensure_dynamic_smem<conv_tc_persist_kernel<BN, GN, KSTEPS>>(226 * 1024)));
   launch_k(conv_tc_persist_kernel<BN, GN, KSTEPS>, grid, kPersistThreads, smem, s, tmA, tmB, tmO, a);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
@@ -1232,7 +1248,7 @@ static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int
                             const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmO0, cudaStream_t s) {
   const int mode = conv_persist_mode();
   if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
-  if (gn == GN_STATS && p->Cout != 64) return 0;
+  if (gn == GN_STATS && (p->Cout != 64 || (p->gn_group_ch > 0 && p->gn_group_ch != 2))) return 0;
   if (a0.KC != 64 && a0.KC != 32) return 0;
   ConvTcArgs a = a0;
   a.ntiles = a.tiles_x * a.tiles_y * p->N;
@@ -1249,23 +1265,27 @@ static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int
   const uint32_t slot_bytes = (uint32_t)a.planes * a.patch_bytes;
   const uint32_t w_bytes = (uint32_t)(9 * a.nchunk) * a.b_bytes;
   const uint32_t stage_bytes = 2u * (uint32_t)a.planes * 128u * (uint32_t)pbn * 2u;
-  const uint32_t budget = 200u * 1024u;
+  // 200 KB; up to 220 KB when that buys the ring a slot per K-chunk of a tile (96 -> 64 / 32 with two planes: 108 KB of
+  // filters + 32 KB of staging leave 2 slots of 24 KB in 200 KB, 3 in 220 KB)
+  uint32_t budget = 200u * 1024u;
   if (w_bytes + stage_bytes + 2 * slot_bytes > budget) return 0;
   if (4u * (uint32_t)pbn * (a.planes > 1 ? 2u : 1u) > 512u) return 0;           // tensor-memory columns
+  if ((int)((budget - w_bytes - stage_bytes) / slot_bytes) < a.nchunk && w_bytes + stage_bytes + (uint32_t)a.nchunk * slot_bytes <= 220u * 1024u)
+    budget = 220u * 1024u;
   int na = (int)((budget - w_bytes - stage_bytes) / slot_bytes);
   if (na > 8) na = 8;
-  // Ring depth: the two tile pipelines wait on the SAME ring with phase parities they derive from the tile index.  A
-  // parity wait is only meaningful within one phase of the barrier, i.e. the previous fill of a slot must be complete
-  // whenever a pipeline asks for the next one: its own previous tile guarantees that iff na >= nchunk + 1 (a pipeline
-  // that asked for fill f of a slot before fill f-1 had landed would see "complete" at once and multiply stale data).
-  if (na < a.nchunk + 1) return 0;
+  // Ring depth: each pipeline has its own "full" barrier per slot (the producer completes a patch on the barrier of the
+  // pipeline that consumes the tile), so the parity a pipeline waits for counts only its own fills and is exact at any
+  // depth >= 2.  (Round 2 first shared one barrier per slot, which needed na >= nchunk + 1 and sent the 3-chunk 96 -> 64 /
+  // 96 -> 32 layers to the one-tile kernel: 155 + 96 us per frame.)
+  if (na < 2) return 0;
   // the final GroupNorm reduction parks [pbn][257] floats in the (then dead) patch ring + staging region
   if (gn == GN_STATS && (uint32_t)na * slot_bytes + stage_bytes < (uint32_t)pbn * kSredPitch2 * sizeof(float)) return 0;
   a.na = na;
   a.p_off = w_bytes;                                   // b_bytes and patch_bytes are multiples of 1024
   a.stage_off = a.p_off + (uint32_t)na * slot_bytes;
   a.aux_off = a.stage_off + stage_bytes;
-  const size_t smem = (size_t)a.aux_off + 1024 + 32 * 8 + 16 + 64 * sizeof(float) + 64;
+  const size_t smem = (size_t)a.aux_off + 1024 + 40 * 8 + 16 + 64 * sizeof(float) + 64;
   int gx = sm_count() / ny;
   if (gx > a.ntiles) gx = a.ntiles;
   CUtensorMap tmB = tmB0, tmO = tmO0;
@@ -1442,7 +1462,8 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
   a.gn_gamma = p->gn_gamma; a.gn_beta = p->gn_beta; a.gn_eps = p->gn_eps;
-  a.gn_inv_cnt = 1.0 / ((double)a.Ho * a.Wo * (double)(p->Cout >= 32 ? p->Cout / 32 : 1));
+  a.gn_cg = p->gn_group_ch > 0 ? p->gn_group_ch : (p->Cout >= 32 ? p->Cout / 32 : 1);
+  a.gn_inv_cnt = 1.0 / ((double)a.Ho * a.Wo * (double)a.gn_cg);
   a.dbg = g_conv_dbg;
   const bool fuse_gn = p->gn_gamma != nullptr;
   if (fuse_gn) {
@@ -1518,7 +1539,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
 #define OTVM_FINISH(T)                                                                                              \
     launch_k(splitk_finish_kernel<T>, g, 256, 0, s, static_cast<const float*>(p->workspace), nsplit, Mtot, p->Cout,  \
              p->bias, mkcptr<T>(p->res, ps), p->res_ld, p->act, p->out, p->out_ps, p->out_cs, p->out_f32,            \
-             mkptr<T>(p->out_relu, ps), p->out_relu_ld, p->gn_stats, ps)
+             mkptr<T>(p->out_relu, ps), p->out_relu_ld, p->gn_stats, ps, a.gn_cg)
     if (a.planes == 1) OTVM_FINISH(bf16); else if (a.planes == 2) OTVM_FINISH(bx<2>); else OTVM_FINISH(bx<3>);
 #undef OTVM_FINISH
     OTVM_LAUNCH_CHECK();

@@ -254,14 +254,18 @@ __global__ void __launch_bounds__(256) upsample8_kernel(cptr_t<T> in, int64_t in
                                                         ptr_t<T> out, int64_t out_ld,
                                                         ptr_t<T> out_relu, int64_t out_relu_ld, int N) {
   pdl_sync();                                  // PDL contract (common.cuh)
-  const int c8n = C >> 3;
-  const int64_t total = (int64_t)N * Ho * Wo * c8n;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
-    int64_t pix = idx / c8n; int c = (int)(idx - pix * c8n) * 8;
-    int n = (int)(pix / ((int64_t)Ho * Wo));
-    int r = (int)(pix - (int64_t)n * Ho * Wo);
-    int oy = r / Wo, ox = r - oy * Wo;
+  // (32-bit index arithmetic: the host takes this kernel only for < 2^31 channel octets; three 64-bit divisions per
+  // element made it issue-bound at 2.3 TB/s)
+  const uint32_t c8n = (uint32_t)C >> 3;
+  const uint32_t total = (uint32_t)N * (uint32_t)Ho * (uint32_t)Wo * c8n;
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  const uint32_t hw = (uint32_t)Ho * (uint32_t)Wo;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const uint32_t pix32 = idx / c8n; const int c = (int)(idx - pix32 * c8n) * 8;
+    const int64_t pix = pix32;
+    const int n = (int)(pix32 / hw);
+    const int r = (int)(pix32 - (uint32_t)n * hw);
+    const int oy = r / Wo, ox = r - oy * Wo;
     int y0, y1, x0, x1; float ly, lx;
     src_index(sy, oy, Hi, y0, y1, ly);
     src_index(sx, ox, Wi, x0, x1, lx);
@@ -355,35 +359,72 @@ __device__ __forceinline__ int bin_end(int b, int s, int L) { return ((b + 1) * 
 template <typename T>
 __global__ void __launch_bounds__(128) ppm_rows_kernel(cptr_t<T> in, int64_t in_ld, int H, int W, int C,
                                                        float* __restrict__ rows) {
+  // One block = one row y x 128 channels: lane = channel quad, warp w = quarter w of the row (its <= 16 pixels are
+  // requested in one batch).  The four quarters' bin sums meet in shared memory and are added in quarter order
+  // (deterministic).  The first version walked a whole row per thread with one load in flight: 32 K threads, 42-47 us
+  // for the 33 MB layer-4 map.
   pdl_sync();                                  // PDL contract (common.cuh)
+  __shared__ float part[4][12][32][4];
   const int y = blockIdx.x, n = blockIdx.z;
-  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 4;
-  if (c >= C) return;
-  float acc[12][4];
-#pragma unroll
-  for (int b = 0; b < 12; ++b)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
-  cptr_t<T> row = in + (((int64_t)(n * H + y) * W) * in_ld + c);
-  for (int x = 0; x < W; ++x) {
-    float v[4];
-    load4(row + (int64_t)x * in_ld, v);
+  const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
+  const int c = (blockIdx.y * 32 + lane) * 4;
+  const bool live = c < C;
+  int lo[12], hi[12];
+  {
     int bi = 0;
 #pragma unroll
     for (int si = 0; si < 4; ++si) {
       const int s = si == 0 ? 1 : si == 1 ? 2 : si == 2 ? 3 : 6;
 #pragma unroll
-      for (int b = 0; b < s; ++b, ++bi) {
-        if (x >= bin_start(b, s, W) && x < bin_end(b, s, W)) {
+      for (int b = 0; b < s; ++b, ++bi) { lo[bi] = bin_start(b, s, W); hi[bi] = bin_end(b, s, W); }
+    }
+  }
+  float acc[12][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[bi][j] += v[j];
+  for (int b = 0; b < 12; ++b)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
+  const int seg = (W + 3) >> 2, xa = wq * seg, xb = min(W, xa + seg);
+  if (live) {
+    cptr_t<T> row = in + (((int64_t)(n * H + y) * W) * in_ld + c);
+    for (int x0 = xa; x0 < xb; x0 += 16) {
+      float v[16][4];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (x0 + u < xb) load4(row + (int64_t)(x0 + u) * in_ld, v[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int x = x0 + u;
+        if (x < xb) {
+#pragma unroll
+          for (int bi = 0; bi < 12; ++bi) {
+            if (x >= lo[bi] && x < hi[bi]) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) acc[bi][j] += v[u][j];
+            }
+          }
         }
       }
     }
   }
+#pragma unroll
+  for (int b = 0; b < 12; ++b)
+    *reinterpret_cast<float4*>(part[wq][b][lane]) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+  __syncthreads();
+  if (!live) return;
   float* o = rows + (((int64_t)n * H + y) * 12) * C + c;
 #pragma unroll
-  for (int b = 0; b < 12; ++b) *reinterpret_cast<float4*>(o + (int64_t)b * C) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+  for (int k = 0; k < 3; ++k) {                   // warp wq finishes bins 3 wq .. 3 wq + 2
+    const int b = wq * 3 + k;
+    float4 t = *reinterpret_cast<const float4*>(part[0][b][lane]);
+#pragma unroll
+    for (int q = 1; q < 4; ++q) {
+      const float4 u = *reinterpret_cast<const float4*>(part[q][b][lane]);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    *reinterpret_cast<float4*>(o + (int64_t)b * C) = t;
+  }
 }
 
 template <typename T>
@@ -490,7 +531,7 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
                       (!out_relu || out_relu_ld % 8 == 0) &&
                       !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add) |
                          reinterpret_cast<uintptr_t>(out_relu)) & 15);
-    if (wide) {
+    if (wide && (int64_t)N * Ho * Wo * (C / 8) < (int64_t)0x7fffffff) {
       int64_t total8 = (int64_t)N * Ho * Wo * (C / 8);
       launch_k(upsample8_kernel<T>, grid_for(total8, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, Hi, Wi, C, Ho, Wo,
                                                                 sy, sx, mkcptr<T>(add, ps), add_ld,
@@ -540,7 +581,7 @@ extern "C" int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32
 template <typename T>
 static int ppm_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, float* scratch,
                  int64_t ps, cudaStream_t s) {
-  dim3 g1(H, ceil_div(C / 4, 128), N), g2(50, ceil_div(C / 4, 128), N);
+  dim3 g1(H, ceil_div(C / 4, 32), N), g2(50, ceil_div(C / 4, 128), N);
   launch_k(ppm_rows_kernel<T>, g1, 128, 0, s, mkcptr<T>(in, ps), in_ld, H, W, C, scratch);
   OTVM_LAUNCH_CHECK();
   launch_k(ppm_cells_kernel<T>, g2, 128, 0, s, scratch, H, W, C, mkptr<T>(out, ps));

@@ -301,6 +301,7 @@ class Engine:
         self.streams: Dict[str, "torch.cuda.Stream"] = {}
         self._ws_tag = "main"
         self._open_forks = 0                       # branches issued and not yet joined
+        self._gn_slices: Dict[tuple, int] = {}     # (conv, input shape) -> channel slices of _ws_gn_sliced (0: none)
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
         self.warm, self.seen = set(), set()
         self.graph_launches: Dict[tuple, int] = {}
@@ -429,12 +430,50 @@ class Engine:
         # Only while nothing else is in flight on another stream: two grid-synchronising kernels sharing the SMs
         # could each hold slots the other needs to become fully resident.
         alone = self._ws_tag == "main" and self._open_forks == 0
+        if alone and cout >= 1024 and not ops.DRY and self._ws_gn_sliced(pl, conv, g, b, x, dst, raw, act, res, stride, pad, dil):
+            return dst
         if alone and self._conv(pl, conv, x, out=dst, stride=stride, pad=pad, dil=dil, gn_stats=stats,
                                 gn_stats_zeroed=True, gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res):
             return dst
         if not alone:
             self._conv(pl, conv, x, out=raw, stride=stride, pad=pad, dil=dil, gn_stats=stats, gn_stats_zeroed=True)
         return self._gn(pl, norm, raw, act=act, res=res, out=out, stats=stats)
+
+    def _ws_gn_sliced(self, pl, conv, g, b, x, dst, raw, act, res, stride, pad, dil) -> bool:
+        """A wide normalised layer whose grid is more than one co-resident wave (FBA layer4: 512 / 1024 -> 2048 at 1/8
+        resolution, 512 CTAs) as 2 or 4 channel slices, each a launch of its own with its own statistics slot and grid
+        barrier: GroupNorm groups are 64 consecutive channels, so slices hold whole groups and every slice takes the
+        in-kernel GroupNorm path (no raw tensor round trip, no gn_apply pass).  False: not applicable, nothing launched."""
+        w, bias = self.w.conv[conv]
+        if w.dim() != 5 or os.environ.get("OTVM_GN_SLICES", "1") == "0":
+            return False
+        cout = w.shape[1]
+        ws = self.workspace(pl)
+
+        def run(a, c, i, query=False):
+            return ops.conv2d(x, w[:, a:c], bias[a:c] if bias is not None else None, dst[..., a:c], stride=stride, pad=pad,
+                              dil=dil, workspace=ws, gn_stats=pl.gn_slot(f"{conv}#slice{i}"), gn_stats_zeroed=True,
+                              gn_fuse=(g[a:c], b[a:c], 1e-5), gn_raw_out=raw[..., a:c], act=act,
+                              res=res[..., a:c] if res is not None else None, gn_group_ch=cout // 32, query_fuse=query)
+
+        key = (conv, tuple(x.shape))
+        ns = self._gn_slices.get(key)
+        if ns is None:
+            ns = 0
+            if not ops.conv2d(x, w, bias, dst, stride=stride, pad=pad, dil=dil, workspace=ws, gn_stats=pl.gn_slot(conv),
+                              gn_stats_zeroed=True, gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res, query_fuse=True):
+                for n in (2, 4):
+                    if (cout // n) % (cout // 32) == 0 and run(0, cout // n, 0, query=True):
+                        ns = n
+                        break
+            self._gn_slices[key] = ns
+        if ns < 2:
+            return False
+        step = cout // ns
+        for i in range(ns):
+            ok = run(i * step, (i + 1) * step, i)
+            assert ok, "a channel slice lost the fused GroupNorm path it was planned with"
+        return True
 
     def _gn_bottleneck(self, pl, p, x, stride, dil, out=None):
         # (no parallel downsample branch here: the GroupNorm-fused kernels synchronise their whole grid and must never

@@ -98,7 +98,8 @@ def _p(t):
 
 
 def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=False, res=None, out_relu=None,
-           gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None, gn_fuse=None, gn_raw_out=None):
+           gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None, gn_fuse=None, gn_raw_out=None,
+           gn_group_ch=0, query_fuse=False):
     """x [N,H,W,Cin(view)], w [Cout,KH,KW,Cin] packed, out NHWC view (or any buffer with ``out_strides`` =
     (pixel_stride, channel_stride) in elements, used for the channel-major value bank).
 
@@ -106,14 +107,18 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     library can (one co-resident wave, see include/otvm_b200.h); the call then returns ``True``.  When it cannot,
     nothing of the normalisation is done, the raw convolution (+ statistics) is written to ``gn_raw_out`` and
     ``False`` is returned (the caller follows with :func:`gn_apply`).  Without ``gn_fuse`` the function returns
-    ``out``."""
+    ``out``.
+
+    Channel slices of a wide normalised layer: pass the ``[a:b]`` views of the packed weights (dim 1 of split weights),
+    gamma / beta / out / res, ``gn_group_ch`` = full Cout / 32 and a statistics slot of its own per slice
+    (``otvm_conv_params.gn_group_ch``).  ``query_fuse=True`` only answers whether the fused path would be taken."""
     if DRY:
         return out if gn_fuse is None else True
     lib = _lib.load()
     N, H, W, Cx = x.shape
-    wplanes = 1
-    if w.dim() == 5:                       # split weights [planes][Cout][KH][KW][Cin]
-        wplanes, w = w.shape[0], w[0]
+    wplanes, w_plane_stride = 1, 0
+    if w.dim() == 5:                       # split weights [planes][Cout][KH][KW][Cin] (or a [:, a:b] channel slice)
+        wplanes, w_plane_stride, w = w.shape[0], w.stride(0), w[0]
     Cout, KH, KW, Cin = w.shape
     assert (cin or Cx) == Cin, (x.shape, w.shape)
     p = ConvParams()
@@ -129,7 +134,8 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     p.res, p.res_ld = (res.data_ptr(), _ld(res)) if res is not None else (None, 0)
     p.out_relu, p.out_relu_ld = (out_relu.data_ptr(), _ld(out_relu)) if out_relu is not None else (None, 0)
     p.act, p.relu_in, p.dtype = act, int(relu_in), _dt(x)
-    p.w_plane_stride = w.numel()
+    p.w_plane_stride = w_plane_stride or w.numel()
+    p.gn_group_ch = gn_group_ch
     assert wplanes == max(1, p.dtype & 0xff), "weights and activations must have the same number of planes"
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None
@@ -141,6 +147,8 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
         if workspace is not None:
             p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
         fused = GN_FUSE and bool(lib.otvm_conv2d_can_fuse_gn(C.byref(p)))
+        if query_fuse:
+            return fused
         if not fused:                     # plain convolution + statistics; residual / activation belong to gn_apply
             p.gn_gamma = p.gn_beta = None
             p.res, p.res_ld, p.act = None, 0, ACT_NONE

@@ -140,9 +140,9 @@ def test_c_abi_exports_every_declared_symbol():
     dbg = open(os.path.join(ROOT, "include", "otvm_b200_debug.h")).read()
     for name in set(re.findall(r"\b(otvm_debug_\w+)\s*\(", dbg)):          # the diagnostic hooks are exported too
         assert hasattr(lib, name), name
-    assert lib.otvm_version() == 4
+    assert lib.otvm_version() == 5
     assert lib.otvm_strerror(-3).decode().startswith("unsupported")
-    assert ctypes.sizeof(_lib.ConvParams) == 200 and ctypes.sizeof(_lib.ReadParams) == 112   # sizeof() of the C structs
+    assert ctypes.sizeof(_lib.ConvParams) == 208 and ctypes.sizeof(_lib.ReadParams) == 112   # sizeof() of the C structs
 
 
 def test_clip_sharding_two_ranks_gloo():
