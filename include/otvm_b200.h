@@ -114,6 +114,12 @@ typedef struct {
    * layer, and a slice whose grid is one co-resident wave can take the fused path (gn_gamma) where the whole layer
    * could not (FBA layer4: 512 -> 2048 at 1/8 resolution).  tcgen05 path only. */
   int32_t gn_group_ch;
+  /* Weight groups; 0 / 1 = one filter bank.  groups = G > 1: `weight` holds G banks [G][Cout][KH][KW][Cin] (per plane)
+   * and `bias` [G][Cout]; image n of the batch (N == G) is convolved with bank n.  One launch then runs G layers of
+   * identical shape on G inputs -- the two STM encoders (Encoder_Q on the current frame, Encoder_M on the previous
+   * one, STM.py:33-102: same ResNet-50 stages, different weights) share every launch instead of competing on two
+   * streams.  tcgen05 path only; no GroupNorm, no split-K. */
+  int32_t groups;
 } otvm_conv_params;
 OTVM_API int otvm_conv2d(const otvm_conv_params* p, void* stream);
 /* 1 when otvm_conv2d can run this problem with the GroupNorm fused into the convolution kernel (see gn_gamma) */

@@ -31,7 +31,7 @@ class ConvParams(C.Structure):
         ("gn_stats_zeroed", c_i32), ("gn_eps", c_f),
         ("gn_gamma", c_vp), ("gn_beta", c_vp),
         ("w_plane_stride", c_i64),
-        ("gn_group_ch", c_i32),
+        ("gn_group_ch", c_i32), ("groups", c_i32),
     ]
 
 

@@ -263,6 +263,7 @@ static int launch_conv_simt(const ConvArgs& a, cudaStream_t s) {
 }
 
 int conv2d_simt(const otvm_conv_params* p, cudaStream_t s) {
+  if (p->groups > 1) return OTVM_ERR_UNSUPPORTED;               // grouped convolutions: tcgen05 path only
   ConvArgs a;
   a.in = p->in; a.in_ld = p->in_ld; a.N = p->N; a.H = p->H; a.W = p->W; a.Cin = p->Cin;
   a.Ho = (p->H + 2 * p->pad - p->dil * (p->KH - 1) - 1) / p->stride + 1;

@@ -66,6 +66,7 @@ struct ConvTcArgs {
   const float* gn_gamma; const float* gn_beta; float gn_eps;   // GN == 2: normalise in this kernel (grid barrier)
   double gn_inv_cnt;           // 1 / elements per GroupNorm group
   int gn_cg;                   // channels per GroupNorm group (Cout / 32 unless the caller runs a channel slice)
+  int w_group_rows;            // grouped convolution (otvm_conv_params.groups): image n reads filter rows n * Cout + ..; else 0
   long long* dbg;              // dev: per-CTA clock64 timestamps [grid][8] (NULL in production)
   // persistent patch-mode kernel (conv_tc_persist_kernel): tiles walked per CTA, smem carve-up
   int ntiles;                  // tiles_x * tiles_y * N
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
   const int ty_i = bq - n_img * a.tiles_y;
   const int x0 = tx_i * a.TW, y0 = ty_i * a.TH;
   const int n0 = blockIdx.y * BN;
+  const int wrow = n_img * a.w_group_rows + n0;               // first filter row (grouped: the bank of this image)
   const int num_k_all = a.KH * a.KW * a.nchunk;
   const int it0 = blockIdx.z * a.k_per_split;
   const int num_k = min(a.k_per_split, num_k_all - it0);      // this CTA's K range is [it0, it0 + num_k)
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
           mbar_arrive_expect_tx(&full_bar[s], b_tx);
           for (int pl = 0; pl < a.planes; ++pl)
             tma_load_3d(smem + a.b_off + (size_t)s * a.b_bytes + (size_t)pl * a.b_plane, &tmB, &full_bar[s],
-                        tap * a.Cin + chunk * a.KC, n0, pl);
+                        tap * a.Cin + chunk * a.KC, wrow, pl);
         }
         __syncwarp();
         if (++s == a.nstage) { s = 0; ph ^= 1; }
@@ -373,8 +375,8 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         mbar_wait_a(ea, ph);
       }
       if (elect_one()) {
-        for (int pl = 0; pl < a.planes; ++pl) tma_load_3d_a(sb + (uint32_t)pl * a.b_plane, &tmB, fa, k0, n0, pl);
-        if (two) tma_load_3d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, n0, 0);
+        for (int pl = 0; pl < a.planes; ++pl) tma_load_3d_a(sb + (uint32_t)pl * a.b_plane, &tmB, fa, k0, wrow, pl);
+        if (two) tma_load_3d_a(sb + stage_bytes, &tmB, fa, k0 + a.KC, wrow, 0);
       }
       __syncwarp();
       it += two ? 2 : 1;
@@ -519,7 +521,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
 
     if (!idle) {                                             // (whole warps: a second group on a single-chunk tile does nothing)
     // bias (a constant: no PDL dependency, and warp 2 -- weight / patch producer first -- has waited anyway)
-    for (int i = e; i < BN; i += nthr) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[n0 + i] : 0.f;
+    for (int i = e; i < BN; i += nthr) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[wrow + i] : 0.f;
     if (n0 + c_lo < a.Cout) load_res(n0 + c_lo);             // in flight while the last MMAs finish
     bar_sync_n(1, nthr);                                     // bias visible to every epilogue thread
     mbar_wait(accum_bar, 0);
@@ -1174,6 +1176,7 @@ bool conv2d_tc_supported(const otvm_conv_params* p) {
   const int Wo = (p->W + 2 * p->pad - p->dil * (p->KW - 1) - 1) / p->stride + 1;
   if (Wo < 8 || Ho < 1) return false;
   if (((int64_t)p->KH * p->KW * p->Cin * 2) % 16 != 0) return false;
+  if (p->groups > 1 && (p->N != p->groups || p->gn_stats)) return false;    // grouped: one image per filter bank, no GroupNorm
   const int gcg = p->gn_group_ch > 0 ? p->gn_group_ch : p->Cout / 32;      // channels per GroupNorm group
   if (p->gn_stats && (p->N != 1 || gcg < 1 || p->Cout % gcg != 0 || p->Cout / gcg > 32)) return false;
   const int bn = pick_bn(p);
@@ -1247,7 +1250,7 @@ static int launch_conv_persist_k(int ksteps, const CUtensorMap& tmA, const CUten
 static int try_conv_persist(const otvm_conv_params* p, const ConvTcArgs& a0, int bn, int epi, int gn,
                             const CUtensorMap& tmA, const CUtensorMap& tmB0, const CUtensorMap& tmO0, cudaStream_t s) {
   const int mode = conv_persist_mode();
-  if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED) return 0;
+  if (mode == 0 || !a0.halo || p->Cout != bn || bn > 64 || epi != 0 || gn == GN_FUSED || p->groups > 1) return 0;
   if (gn == GN_STATS && (p->Cout != 64 || (p->gn_group_ch > 0 && p->gn_group_ch != 2))) return 0;
   if (a0.KC != 64 && a0.KC != 32) return 0;
   ConvTcArgs a = a0;
@@ -1437,7 +1440,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   // 16-36 iteration layers SLOWER, 206 vs 224 frames/s -- they are bound by their fixed costs, not by the K walk, and the
   // workspace round trip + finish kernel add to those)
   const int num_kp = num_k;
-  if (p->workspace && ctas * 2 <= sm_count() && num_kp >= 48 && p->Cout % 4 == 0 &&
+  if (p->workspace && p->groups <= 1 && ctas * 2 <= sm_count() && num_kp >= 48 && p->Cout % 4 == 0 &&
       (!p->res || p->res_ld % 4 == 0) && (!p->out_relu || p->out_relu_ld % 4 == 0)) {
     nsplit = (int)(sm_count() / ctas);
     if (nsplit > num_kp / 12) nsplit = num_kp / 12;        // >= 12 K iterations' worth per slice: the extra pass must pay off
@@ -1462,6 +1465,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   a.out_relu = static_cast<bf16*>(p->out_relu); a.out_relu_ld = p->out_relu_ld;
   a.act = p->act; a.out_f32 = p->out_f32; a.gn_stats = p->gn_stats;
   a.gn_gamma = p->gn_gamma; a.gn_beta = p->gn_beta; a.gn_eps = p->gn_eps;
+  a.w_group_rows = p->groups > 1 ? p->Cout : 0;
   a.gn_cg = p->gn_group_ch > 0 ? p->gn_group_ch : (p->Cout >= 32 ? p->Cout / 32 : 1);
   a.gn_inv_cnt = 1.0 / ((double)a.Ho * a.Wo * (double)a.gn_cg);
   a.dbg = g_conv_dbg;
@@ -1490,8 +1494,9 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   }
   {
     const uint64_t K = (uint64_t)p->KH * p->KW * p->Cin;
-    uint64_t dims[3] = {K, (uint64_t)p->Cout, (uint64_t)a.planes};
-    uint64_t str[2] = {K * 2, a.planes > 1 ? (uint64_t)p->w_plane_stride * 2 : K * 2 * (uint64_t)p->Cout};
+    const uint64_t wrows = (uint64_t)p->Cout * (uint64_t)(p->groups > 1 ? p->groups : 1);
+    uint64_t dims[3] = {K, wrows, (uint64_t)a.planes};
+    uint64_t str[2] = {K * 2, a.planes > 1 ? (uint64_t)p->w_plane_stride * 2 : K * 2 * wrows};
     uint32_t box[3] = {(uint32_t)a.KC, (uint32_t)bn, 1};
     int rc = make_tmap_bf16(&tmB, p->weight, 3, dims, str, box, swz);
     if (rc) return rc;

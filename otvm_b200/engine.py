@@ -89,6 +89,24 @@ class PackedWeights:
                         put(f"{p}.conv{c}", *bn_fold(f(f"{p}.conv{c}.weight"), f"{p}.bn{c}"))
                     if b == 0:
                         put(p + ".downsample", *bn_fold(f(p + ".downsample.0.weight"), p + ".downsample.1"))
+        # The two encoders have the same stages with different weights: store every res2..res4 layer as ONE pair tensor
+        # (bank 0 = Encoder_Q, bank 1 = Encoder_M) for the grouped launches of Engine._tv_encoder; the per-encoder
+        # entries become views of it (no copy).
+        self.pair: Dict[str, tuple] = {}
+        if bf:
+            q, m = "trimap.model.Encoder_Q", "trimap.model.Encoder_M"
+            for name in [n for n in self.conv if n.startswith(q + ".res")]:
+                sfx = name[len(q):]
+                (wq, bq), (wm, bm) = self.conv[q + sfx], self.conv[m + sfx]
+                bp = torch.stack([bq, bm])
+                if planes > 1:
+                    wp = torch.stack([wq, wm], dim=1)                     # [planes][2][Cout][KH][KW][Cin]
+                    self.conv[q + sfx], self.conv[m + sfx] = (wp[:, 0], bp[0]), (wp[:, 1], bp[1])
+                    self.pair[sfx] = (wp.view(planes, 2 * wq.shape[1], *wq.shape[2:]), bp.view(-1))
+                else:
+                    wp = torch.stack([wq, wm], dim=0)                     # [2][Cout][KH][KW][Cin]
+                    self.conv[q + sfx], self.conv[m + sfx] = (wp[0], bp[0]), (wp[1], bp[1])
+                    self.pair[sfx] = (wp.view(2 * wq.shape[0], *wq.shape[1:]), bp.view(-1))
         for kv in ("trimap.model.KV_M_r4", "trimap.model.KV_Q_r4"):
             put(kv + ".Key", f(kv + ".Key.weight"), f(kv + ".Key.bias"))
             put(kv + ".Value", f(kv + ".Value.weight"), f(kv + ".Value.bias"))
@@ -301,6 +319,7 @@ class Engine:
         self.streams: Dict[str, "torch.cuda.Stream"] = {}
         self._ws_tag = "main"
         self._open_forks = 0                       # branches issued and not yet joined
+        self.tv_pair = os.environ.get("OTVM_TV_PAIR", "1") != "0"   # grouped Encoder_Q + Encoder_M launches (_tv_encoder)
         self._gn_slices: Dict[tuple, int] = {}     # (conv, input shape) -> channel slices of _ws_gn_sliced (0: none)
         self.graphs: Dict[tuple, "torch.cuda.CUDAGraph"] = {}
         self.warm, self.seen = set(), set()
@@ -384,26 +403,65 @@ class Engine:
         ws = self.workspace(pl)
         return ops.conv2d(x, w, b, out, stride=stride, pad=pad, dil=dil, workspace=ws, **kw)
 
-    def _tv_bottleneck(self, pl, p, x, stride, out=None):
+    # ---- STM encoders (torchvision ResNet-50 stem..layer3, BN folded) -------------------------------------
+    # Encoder_Q (current frame) and Encoder_M (previous frame + its trimap / alpha / hidden maps) are the same stages with
+    # different weights.  Every activation is ONE [2, H, W, C] buffer (image 0 = Q, image 1 = M): an encoder running
+    # alone works on its image (``idx`` 0 / 1), and when both are due -- every steady-state frame, because frame t-1's
+    # memorize pass is deferred to the start of frame t -- each layer is ONE grouped launch over both images
+    # (``idx`` None, otvm_conv_params.groups = 2) instead of two small-grid launches competing on two streams.
+    _TV = ("trimap.model.Encoder_Q", "trimap.model.Encoder_M")
+
+    def _tv_buf(self, pl, key, shape, idx):
+        t = pl.buf("tv." + key, (2,) + tuple(shape[1:]))
+        return t if idx is None else t[idx:idx + 1]
+
+    def _tv_conv(self, pl, idx, sfx, x, *, stride=1, pad=0, act=ACT_NONE, res=None):
+        if idx is None:
+            (w, b), groups = self.w.pair[sfx], 2
+        else:
+            (w, b), groups = self.w.conv[self._TV[idx] + sfx], 1
+        N, H, W, _ = x.shape
+        kh, cout = w.shape[-3], w.shape[-4] // groups
+        Ho = (H + 2 * pad - (kh - 1) - 1) // stride + 1
+        Wo = (W + 2 * pad - (kh - 1) - 1) // stride + 1
+        out = self._tv_buf(pl, sfx, (1, Ho, Wo, cout), idx)
+        return ops.conv2d(x, w, b, out, stride=stride, pad=pad, act=act, res=res, workspace=self.workspace(pl), groups=groups)
+
+    def _tv_bottleneck(self, pl, idx, p, x, stride):
         """torchvision Bottleneck with BN folded; ReLUs and the residual add live in the conv epilogues."""
         idn, f = x, None
-        if (p + ".downsample") in self.w.conv:
+        if (self._TV[0] + p + ".downsample") in self.w.conv:
             with self.fork("ds") as f:
-                idn = self._conv(pl, p + ".downsample", x, stride=stride)
-        t1 = self._conv(pl, p + ".conv1", x, act=ACT_RELU)
-        t2 = self._conv(pl, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU)
+                idn = self._tv_conv(pl, idx, p + ".downsample", x, stride=stride)
+        t1 = self._tv_conv(pl, idx, p + ".conv1", x, act=ACT_RELU)
+        t2 = self._tv_conv(pl, idx, p + ".conv2", t1, stride=stride, pad=1, act=ACT_RELU)
         if f is not None:
             f.join()
-        return self._conv(pl, p + ".conv3", t2, out=out, res=idn, act=ACT_RELU)
+        return self._tv_conv(pl, idx, p + ".conv3", t2, res=idn, act=ACT_RELU)
 
-    def _tv_encoder(self, pl, enc, x):
-        c1 = self._conv(pl, enc + ".stem", x, stride=2, pad=3, act=ACT_RELU)
+    def _tv_encoder(self, pl, idx, x_q=None, x_m=None):
+        """``idx`` 0: Encoder_Q on ``x_q``; 1: Encoder_M on ``x_m``; None: both (grouped).  Returns r2, r3, r4 with the
+        batch dimension of the mode ([1, ...] or [2, ...])."""
+        xs = (x_q, x_m)
+        N, H, W, _ = (x_q if x_q is not None else x_m).shape
+        c1 = self._tv_buf(pl, "stem", (1, (H + 1) // 2, (W + 1) // 2, 64), None)
+        f = None
+        for i in ((0, 1) if idx is None else (idx,)):
+            w, b = self.w.conv[self._TV[i] + ".stem"]
+            if idx is None and i == 1:                     # the second stem beside the first
+                with self.fork("stem") as f:
+                    ops.conv2d(xs[i], w, b, c1[i:i + 1], stride=2, pad=3, act=ACT_RELU, workspace=self.workspace(pl))
+            else:
+                ops.conv2d(xs[i], w, b, c1[i:i + 1], stride=2, pad=3, act=ACT_RELU, workspace=self.workspace(pl))
+        if f is not None:
+            f.join()
+        c1 = c1 if idx is None else c1[idx:idx + 1]
         N, H, W, C = c1.shape
-        x = ops.maxpool3x3s2(c1, pl.buf(enc + ".pool", (N, (H + 1) // 2, (W + 1) // 2, C)))
+        x = ops.maxpool3x3s2(c1, self._tv_buf(pl, "pool", (1, (H + 1) // 2, (W + 1) // 2, C), idx))
         feats = []
         for lname, blocks, stride in (("res2", 3, 1), ("res3", 4, 2), ("res4", 6, 2)):
             for b in range(blocks):
-                x = self._tv_bottleneck(pl, f"{enc}.{lname}.{b}", x, stride if b == 0 else 1)
+                x = self._tv_bottleneck(pl, idx, f".{lname}.{b}", x, stride if b == 0 else 1)
             feats.append(x)
         return feats       # r2, r3, r4
 
@@ -497,10 +555,11 @@ class Engine:
         return y, yr
 
     # ---- STM ---------------------------------------------------------------------------------------
-    def segment(self, pl: FramePlan, bank: MemoryBank, join=None):
-        """Propagated trimap logits [Hp*Wp][4] fp32 for the current frame (imgn must be ready)."""
+    def segment(self, pl: FramePlan, bank: MemoryBank, join=None, feats=None):
+        """Propagated trimap logits [Hp*Wp][4] fp32 for the current frame (imgn must be ready).  ``feats``: r2, r3, r4 of
+        Encoder_Q when the caller ran the grouped encoder pass."""
         imgn = pl.bufs["imgn"]                      # [1,Hp,Wp,cin_img]: 3 normalised channels + zeros
-        r2, r3, r4 = self._tv_encoder(pl, "trimap.model.Encoder_Q", imgn)
+        r2, r3, r4 = feats if feats is not None else self._tv_encoder(pl, 0, x_q=imgn)
         N, h, w, _ = r4.shape
         m4in = pl.buf("m4in", (1, h, w, 2 * DO))
         # parallel branches: the skip-connection halves of the decoder (STM.py:113-114 only need r3 / r2) and the
@@ -554,10 +613,12 @@ class Engine:
         ops.upsample(p2[..., :3], logits[..., :3])                                    # STM.py:136
         return logits
 
-    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int):
-        """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``."""
+    def memorize(self, pl: FramePlan, bank: MemoryBank, slot: int, r4=None):
+        """Encode (frame, trimap, alpha, hidden) and write key/value straight into bank slot ``slot``.  ``r4``: Encoder_M's
+        last feature map when the caller ran the grouped encoder pass."""
         mem_in = pl.bufs["mem_in"]                  # [1,Hp,Wp,cin_mem]: 22 channels + zeros
-        _, _, r4 = self._tv_encoder(pl, "trimap.model.Encoder_M", mem_in)
+        if r4 is None:
+            _, _, r4 = self._tv_encoder(pl, 1, x_m=mem_in)
         N, h, w, _ = r4.shape
         kdst = bank.key_slot(slot).view(1, h, w, DE)
         vdst = bank.vals[:, slot * bank.hw:]
@@ -749,7 +810,9 @@ class Engine:
         H, W, Hp, Wp, P = pl.H, pl.W, pl.Hp, pl.Wp, pl.Hp * pl.Wp
         f32 = torch.float32
         join = None
-        if pending is not None:
+        # both encoders are due (steady state): one grouped pass after the preprocessing below instead of two streams
+        pair = pending is not None and not first_frame and self.tv_pair and bool(self.w.pair)
+        if pending is not None and not pair:
             if ops.PROFILER is None and not ops.DRY:
                 if "memorize" not in self.streams:
                     self.streams["memorize"] = torch.cuda.Stream(device=self.device)
@@ -785,7 +848,24 @@ class Engine:
                 tri_first[pl.pad_top:pl.pad_top + H, pl.pad_left:pl.pad_left + W, :3] = user_tri.permute(1, 2, 0)
             ops.trimap_encode(tri_first, 4, False, *enc_args)                   # preds_trimap = tri_ (:429)
         else:
-            logits = self.segment(pl, bank, join)
+            feats = None
+            if pair:
+                r2, r3, r4 = self._tv_encoder(pl, None, x_q=pl.bufs["imgn"], x_m=pl.bufs["mem_in"])
+                feats = (r2[0:1], r3[0:1], r4[0:1])
+                if ops.PROFILER is None and not ops.DRY:     # KV_M projections beside the query path, joined before the read
+                    if "memorize" not in self.streams:
+                        self.streams["memorize"] = torch.cuda.Stream(device=self.device)
+                    join = self.streams["memorize"]
+                    join.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(join):
+                        self._ws_tag = "memorize"
+                        try:
+                            self.memorize(pl, bank, pending, r4=r4[1:2])
+                        finally:
+                            self._ws_tag = "main"
+                else:
+                    self.memorize(pl, bank, pending, r4=r4[1:2])
+            logits = self.segment(pl, bank, join, feats=feats)
             join = None
             ops.trimap_encode(logits, 4, True, *enc_args)                       # softmax + make_trimap (:440-442)
         net = self.matting(pl)

@@ -99,7 +99,7 @@ def _p(t):
 
 def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=False, res=None, out_relu=None,
            gn_stats=None, gn_stats_zeroed=False, out_strides=None, cin=None, workspace=None, gn_fuse=None, gn_raw_out=None,
-           gn_group_ch=0, query_fuse=False):
+           gn_group_ch=0, query_fuse=False, groups=1):
     """x [N,H,W,Cin(view)], w [Cout,KH,KW,Cin] packed, out NHWC view (or any buffer with ``out_strides`` =
     (pixel_stride, channel_stride) in elements, used for the channel-major value bank).
 
@@ -111,7 +111,10 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
 
     Channel slices of a wide normalised layer: pass the ``[a:b]`` views of the packed weights (dim 1 of split weights),
     gamma / beta / out / res, ``gn_group_ch`` = full Cout / 32 and a statistics slot of its own per slice
-    (``otvm_conv_params.gn_group_ch``).  ``query_fuse=True`` only answers whether the fused path would be taken."""
+    (``otvm_conv_params.gn_group_ch``).  ``query_fuse=True`` only answers whether the fused path would be taken.
+
+    ``groups=G``: ``w`` stacks G filter banks along its Cout axis ([G*Cout][KH][KW][Cin]), ``bias`` is [G*Cout], and image
+    n of the batch (N == G) uses bank n (``otvm_conv_params.groups``)."""
     if DRY:
         return out if gn_fuse is None else True
     lib = _lib.load()
@@ -120,6 +123,8 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     if w.dim() == 5:                       # split weights [planes][Cout][KH][KW][Cin] (or a [:, a:b] channel slice)
         wplanes, w_plane_stride, w = w.shape[0], w.stride(0), w[0]
     Cout, KH, KW, Cin = w.shape
+    assert Cout % groups == 0 and (groups == 1 or N == groups), (groups, N, w.shape)
+    Cout //= groups
     assert (cin or Cx) == Cin, (x.shape, w.shape)
     p = ConvParams()
     p.inp, p.in_ld = x.data_ptr(), _ld(x)
@@ -136,6 +141,7 @@ def conv2d(x, w, bias, out, *, stride=1, pad=0, dil=1, act=ACT_NONE, relu_in=Fal
     p.act, p.relu_in, p.dtype = act, int(relu_in), _dt(x)
     p.w_plane_stride = w_plane_stride or w.numel()
     p.gn_group_ch = gn_group_ch
+    p.groups = groups
     assert wplanes == max(1, p.dtype & 0xff), "weights and activations must have the same number of planes"
     p.out_f32 = int(out.dtype == torch.float32 and x.dtype != torch.float32)
     p.gn_stats = gn_stats.data_ptr() if gn_stats is not None else None

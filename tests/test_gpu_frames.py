@@ -90,6 +90,36 @@ def test_overlap_and_pdl_do_not_change_results(precision):
         assert rel_err(a1.cpu(), a0.cpu()) < tol and rel_err(t1.cpu(), t0.cpu()) < tol
 
 
+@pytest.mark.parametrize("precision", ["bf16x2", "bf16"])
+def test_grouped_encoder_pass_does_not_change_results(precision):
+    """Encoder_Q (frame t) + Encoder_M (frame t-1) as ONE grouped launch per layer (Engine._tv_encoder, otvm_conv_params
+    .groups) against the two-stream schedule: the same kernels compute the same tiles, so outputs agree to rounding of the
+    tile-shape heuristics (a doubled grid may pick another tile width)"""
+    import os
+    from frames_util import build_model
+    from otvm_b200 import ops
+    from otvm_b200.fixtures import make_frame
+    outs, launches = {}, {}
+    for mode in ("0", "1"):
+        os.environ["OTVM_TV_PAIR"] = mode
+        try:
+            model, _ = build_model("tempered", precision)
+            assert model.engine.tv_pair == (mode == "1")       # (the engine is built on first use and reads the switch then)
+        finally:
+            os.environ["OTVM_TV_PAIR"] = "1"
+        res, n0 = [], ops.launch_count()
+        for i in range(8):
+            a, fg, bg = make_frame(0, i, 128, 160)
+            out = model(a.cuda(), fg.cuda(), bg.cuda(), first_frame=(i == 0), last_frame=(i == 7), memorize=(i % 3 != 2),
+                        max_memory_num=4)
+            res.append((out[3].clone(), out[1].clone()))
+        outs[mode], launches[mode] = res, ops.launch_count() - n0 + model.engine.replayed_launches
+    assert launches["1"] < launches["0"], launches             # ~44 launches fewer per steady-state frame
+    tol = 1e-2 if precision == "bf16" else 1e-3
+    for (a0, t0), (a1, t1) in zip(outs["0"], outs["1"]):
+        assert rel_err(a1.cpu(), a0.cpu()) < tol and rel_err(t1.cpu(), t0.cpu()) < tol
+
+
 @pytest.mark.parametrize("precision", ["bf16x2", "bf16x3"])
 @pytest.mark.parametrize("kind,H,W", [("tempered", 256, 256), ("default", 128, 128), ("tempered", 120, 152)])
 def test_tensor_core_frames_teacher_forced(kind, H, W, precision):

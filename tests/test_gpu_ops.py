@@ -532,6 +532,50 @@ def test_conv2d_fused_groupnorm(case, dtype):
         assert rel_err(nchw(out), y) < (1e-2 if dtype == torch.bfloat16 else 1e-4)
 
 
+GROUPED_CASES = [
+    # Cin, Cout, k, stride, H, W, with_res      (STM encoder layers at 128 x 160 and 512 x 512 frames)
+    (64, 64, 1, 1, 32, 40, False), (64, 64, 3, 1, 32, 40, False), (64, 256, 1, 1, 32, 40, True), (256, 128, 1, 1, 32, 40, False),
+    (128, 128, 3, 2, 32, 40, False), (256, 512, 1, 2, 32, 40, False), (1024, 256, 1, 1, 8, 10, False),
+    (256, 256, 3, 1, 32, 32, False), (256, 1024, 1, 1, 32, 32, True), (64, 64, 3, 1, 128, 128, False),
+]
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("case", GROUPED_CASES)
+def test_conv2d_grouped_pair(case, dtype):
+    """otvm_conv_params.groups = 2: image n of a batch of two is convolved with filter bank n (+ its bias, its residual)
+    in ONE launch == two separate convolutions (the layers of Encoder_Q / Encoder_M, STM.py:33-102)"""
+    ops = _ops()
+    Cin, Cout, k, stride, H, W, with_res = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(2, Cin, H, W, generator=g)
+    w = torch.randn(2, Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(2, Cout, generator=g)
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn(2, Cout, Ho, Wo, generator=g)
+    want = torch.cat([F.conv2d(rnd(dtype, x[i:i + 1]), rnd(dtype, w[i]), b[i], stride, pad) for i in range(2)])
+    if with_res:
+        want = want + rnd(dtype, res)
+    want = F.relu(want)
+    wd = [wpack(w[i], dtype) for i in range(2)]
+    wpair = torch.cat(wd, dim=1 if wd[0].dim() == 5 else 0).contiguous()            # banks stacked along Cout
+    xd = nhwc(x, dtype)
+    out = zeros((2, Ho, Wo, Cout), dtype)
+    ops.conv2d(xd, wpair, b.reshape(-1).to(DEV), out, stride=stride, pad=pad, act=ops.ACT_RELU,
+               res=nhwc(res, dtype) if with_res else None, groups=2)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    # and bit-identical to the two single launches when the tile shape is the same (it is for these grids' second image)
+    single = zeros((2, Ho, Wo, Cout), dtype)
+    rd = nhwc(res, dtype) if with_res else None
+    for i in range(2):
+        ops.conv2d(xd[i:i + 1], wd[i], b[i].to(DEV), single[i:i + 1], stride=stride, pad=pad, act=ops.ACT_RELU,
+                   res=rd[i:i + 1] if with_res else None)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(out), nchw(single)) < (4e-3 if dtype == torch.bfloat16 else 1e-5)
+
+
 @pytest.mark.parametrize("dtype", TC_DTYPES)
 @pytest.mark.parametrize("nslice", [2, 4])
 def test_conv2d_fused_groupnorm_channel_slices(nslice, dtype):
