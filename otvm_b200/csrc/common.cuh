@@ -124,6 +124,54 @@ template <int P> __device__ __forceinline__ void st1(BxPtr<P> q, int64_t i, floa
     v -= __bfloat162float(h);
   }
 }
+// 8 consecutive elements <-> float[8] (one 16-byte bf16 access or two 16-byte fp32 accesses)
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
+  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
+  uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+
+template <int P> __device__ __forceinline__ void load8(BxPtr<P> q, float (&v)[8]) {
+  load8(q.p, v);
+#pragma unroll
+  for (int k = 1; k < P; ++k) {
+    float t[8];
+    load8(q.p + k * q.ps, t);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += t[j];
+  }
+}
+template <int P> __device__ __forceinline__ void store8(BxPtr<P> q, const float (&v)[8]) {
+  float r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = v[j];
+#pragma unroll
+  for (int k = 0; k < P; ++k) {
+    uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
+      r[2 * i] -= __low2float(h[i]); r[2 * i + 1] -= __high2float(h[i]);
+    }
+    *reinterpret_cast<uint4*>(q.p + k * q.ps) = t;
+  }
+}
+
 // the value a consumer reads back after a store of `v` (GroupNorm statistics are those of the STORED tensor):
 // exact for fp32, bf16 rounding for one plane, identity (to ~2^-17) for split elements
 template <typename T> __device__ __forceinline__ float stored(float v) { return v; }

@@ -13,54 +13,6 @@ static inline int grid_for(int64_t work_items, int block) {
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
 
-// 8 consecutive elements <-> float[8] (one 16-byte bf16 access or two 16-byte fp32 accesses)
-__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
-  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-}
-__device__ __forceinline__ void load8(const bf16* p, float (&v)[8]) {
-  uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
-}
-__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void store8(bf16* p, const float (&v)[8]) {
-  uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-  *reinterpret_cast<uint4*>(p) = t;
-}
-
-template <int P> __device__ __forceinline__ void load8(BxPtr<P> q, float (&v)[8]) {
-  load8(q.p, v);
-#pragma unroll
-  for (int k = 1; k < P; ++k) {
-    float t[8];
-    load8(q.p + k * q.ps, t);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] += t[j];
-  }
-}
-template <int P> __device__ __forceinline__ void store8(BxPtr<P> q, const float (&v)[8]) {
-  float r[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) r[j] = v[j];
-#pragma unroll
-  for (int k = 0; k < P; ++k) {
-    uint4 t; __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      h[i] = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);
-      r[2 * i] -= __low2float(h[i]); r[2 * i + 1] -= __high2float(h[i]);
-    }
-    *reinterpret_cast<uint4*>(q.p + k * q.ps) = t;
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // GroupNorm statistics: per (n, group) sum and sum of squares in fp64 (fp32 partials per thread/block).
 // ------------------------------------------------------------------------------------------------------
@@ -359,58 +311,53 @@ __device__ __forceinline__ int bin_end(int b, int s, int L) { return ((b + 1) * 
 template <typename T>
 __global__ void __launch_bounds__(128) ppm_rows_kernel(cptr_t<T> in, int64_t in_ld, int H, int W, int C,
                                                        float* __restrict__ rows) {
-  // One block = one row y x 128 channels: lane = channel quad, warp w = quarter w of the row (its <= 16 pixels are
-  // requested in one batch).  The four quarters' bin sums meet in shared memory and are added in quarter order
-  // (deterministic).  The first version walked a whole row per thread with one load in flight: 32 K threads, 42-47 us
-  // for the 33 MB layer-4 map.
+  // One block = one row y x 128 channels: lane = channel quad, warp w = quarter w of the row.  A warp first parks its
+  // (<= 32) pixels in shared memory -- every load of the quarter in flight at once -- then walks the 12 bins with
+  // warp-uniform pixel ranges (static accumulators, no predicated adds); the four quarters' bin sums meet in shared
+  // memory and are added in quarter order (deterministic).  The first version walked a whole row per thread with one
+  // load in flight: 32 K threads, 42-47 us for the 33 MB layer-4 map.
   pdl_sync();                                  // PDL contract (common.cuh)
-  __shared__ float part[4][12][32][4];
-  const int y = blockIdx.x, n = blockIdx.z;
+  constexpr int NB = 16;                         // pixels per batch
+  __shared__ float4 px[4][NB][32];               // 32 KB; reused for the quarters' bin sums afterwards
+  float (*part)[12][32][4] = reinterpret_cast<float (*)[12][32][4]>(&px[0][0][0]);      // [4][12][32][4] floats = 24 KB
+  const int y = blockIdx.y, n = blockIdx.z;
   const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-  const int c = (blockIdx.y * 32 + lane) * 4;
+  const int c = (blockIdx.x * 32 + lane) * 4;
   const bool live = c < C;
-  int lo[12], hi[12];
-  {
+  const int seg = (W + 3) >> 2, xa = wq * seg, xb = min(W, xa + seg);
+  float4 acc[12];
+#pragma unroll
+  for (int bi = 0; bi < 12; ++bi) acc[bi] = make_float4(0.f, 0.f, 0.f, 0.f);
+  cptr_t<T> row = in + (((int64_t)(n * H + y) * W) * in_ld + (live ? c : 0));
+  for (int x0 = xa; x0 < xb; x0 += NB) {
+    const int x1 = min(xb, x0 + NB);
+    if (live) {
+#pragma unroll 8
+      for (int x = x0; x < x1; ++x) {
+        float v[4];
+        load4(row + (int64_t)x * in_ld, v);
+        px[wq][x - x0][lane] = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    __syncwarp();
     int bi = 0;
 #pragma unroll
     for (int si = 0; si < 4; ++si) {
       const int s = si == 0 ? 1 : si == 1 ? 2 : si == 2 ? 3 : 6;
 #pragma unroll
-      for (int b = 0; b < s; ++b, ++bi) { lo[bi] = bin_start(b, s, W); hi[bi] = bin_end(b, s, W); }
-    }
-  }
-  float acc[12][4];
-#pragma unroll
-  for (int b = 0; b < 12; ++b)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[b][j] = 0.f;
-  const int seg = (W + 3) >> 2, xa = wq * seg, xb = min(W, xa + seg);
-  if (live) {
-    cptr_t<T> row = in + (((int64_t)(n * H + y) * W) * in_ld + c);
-    for (int x0 = xa; x0 < xb; x0 += 16) {
-      float v[16][4];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (x0 + u < xb) load4(row + (int64_t)(x0 + u) * in_ld, v[u]);
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int x = x0 + u;
-        if (x < xb) {
-#pragma unroll
-          for (int bi = 0; bi < 12; ++bi) {
-            if (x >= lo[bi] && x < hi[bi]) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) acc[bi][j] += v[u][j];
-            }
-          }
+      for (int b = 0; b < s; ++b, ++bi) {
+        const int lo = max(bin_start(b, s, W), x0), hi = min(bin_end(b, s, W), x1);     // warp-uniform
+        for (int x = lo; x < hi; ++x) {
+          const float4 t = px[wq][x - x0][lane];
+          acc[bi].x += t.x; acc[bi].y += t.y; acc[bi].z += t.z; acc[bi].w += t.w;
         }
       }
     }
+    __syncwarp();
   }
+  __syncthreads();                               // every warp is done with its pixels: the buffer becomes `part`
 #pragma unroll
-  for (int b = 0; b < 12; ++b)
-    *reinterpret_cast<float4*>(part[wq][b][lane]) = make_float4(acc[b][0], acc[b][1], acc[b][2], acc[b][3]);
+  for (int bi = 0; bi < 12; ++bi) *reinterpret_cast<float4*>(part[wq][bi][lane]) = acc[bi];
   __syncthreads();
   if (!live) return;
   float* o = rows + (((int64_t)n * H + y) * 12) * C + c;
@@ -442,9 +389,14 @@ __global__ void __launch_bounds__(128) ppm_cells_kernel(const float* __restrict_
   const int by = local / s, bx = local - by * s;
   const int y0 = bin_start(by, s, H), y1 = bin_end(by, s, H);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int y = y0; y < y1; ++y) {
-    float4 v = *reinterpret_cast<const float4*>(rows + (((int64_t)n * H + y) * 12 + xoff + bx) * C + c);
-    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  for (int yb = y0; yb < y1; yb += 8) {            // 8 row sums in flight, added in row order
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (yb + u < y1) v[u] = __ldg(reinterpret_cast<const float4*>(rows + (((int64_t)n * H + yb + u) * 12 + xoff + bx) * C + c));
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (yb + u < y1) { acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w; }
   }
   const float inv = 1.f / (float)((y1 - y0) * (bin_end(bx, s, W) - bin_start(bx, s, W)));
 #pragma unroll
@@ -581,7 +533,7 @@ extern "C" int otvm_maxpool3x3s2(const void* in, int64_t in_ld, int32_t N, int32
 template <typename T>
 static int ppm_t(const void* in, int64_t in_ld, int N, int H, int W, int C, void* out, float* scratch,
                  int64_t ps, cudaStream_t s) {
-  dim3 g1(H, ceil_div(C / 4, 32), N), g2(50, ceil_div(C / 4, 128), N);
+  dim3 g1(ceil_div(C / 4, 32), H, N), g2(50, ceil_div(C / 4, 128), N);
   launch_k(ppm_rows_kernel<T>, g1, 128, 0, s, mkcptr<T>(in, ps), in_ld, H, W, C, scratch);
   OTVM_LAUNCH_CHECK();
   launch_k(ppm_cells_kernel<T>, g2, 128, 0, s, scratch, H, W, C, mkptr<T>(out, ps));

@@ -38,13 +38,13 @@ for s in $STEPS; do
       timeout 300 python scripts/bench_conv.py > $OUT/bench_conv.txt 2>&1
       OTVM_OVERLAP=0 timeout 300 python scripts/profile_frame.py bf16 > $OUT/profile_frame.txt 2>&1; head -12 $OUT/profile_frame.txt ;;
     ncu)
-      OTVM_OVERLAP=0 OTVM_PDL=0 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+      OTVM_PDL=0 timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
         --log-file $OUT/launches.csv python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
-      OTVM_OVERLAP=0 OTVM_PDL=0 timeout 900 ncu --profile-from-start off --clock-control none --csv \
+      OTVM_PDL=0 timeout 900 ncu --profile-from-start off --clock-control none --csv \
         --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__throughput.avg.pct_of_peak_sustained_elapsed,lts__t_bytes.sum \
         --log-file $OUT/launch_metrics.csv python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_metrics.log 2>&1; echo "ncu metrics rc=$?" ;;
     ncufull)
-      OTVM_OVERLAP=0 OTVM_PDL=0 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
+      OTVM_PDL=0 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on \
         -k regex:memory_read_tc -c 1 -f -o $OUT/read_full python scripts/one_frame.py ${PREC:-bf16x2} 1 > $OUT/ncu_read.log 2>&1; echo "ncu read rc=$?"
       export_rep $OUT/read_full source
       OTVM_PDL=0 timeout 600 ncu --set full --clock-control none --import-source on \
