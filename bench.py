@@ -288,6 +288,8 @@ def run_b200(args):
                 continue
             c = Clip(prec, H, T_MEM, rank, 3)
             ms, _ = timed(c.step, 48, reduce=False)
+            for i in range(3):
+                c.e2e_step(i)                              # (staging buffers / copy stream are created on first use)
             ms2, _ = timed(c.e2e_step, 48, reduce=False)
             modes[prec] = {"value": round(48 / (ms * 1e-3), 2), "e2e": round(48 / (ms2 * 1e-3), 2), "unit": "frames/s",
                            "note": {"bf16x3": "strict mode: three planes, <= 1e-3 of the reference (tests/test_gpu_frames.py)",
@@ -298,6 +300,8 @@ def run_b200(args):
         if H == 512:
             c = Clip(model.precision, 1024, 16, rank, 3)
             ms, _ = timed(c.step, 24, reduce=False)
+            for i in range(3):
+                c.e2e_step(i)
             ms2, _ = timed(c.e2e_step, 24, reduce=False)
             line["cfg3"] = {"workload": workload(1024, 16), "value": round(24 / (ms * 1e-3), 2), "unit": "frames/s",
                             "ms_per_step": round(ms / 24, 3), "e2e": round(24 / (ms2 * 1e-3), 2), "steps": 24,

@@ -681,8 +681,21 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         // direct stores: fp32 heads ([P][8] / [P][12]) and the channel-major value bank (lanes = consecutive pixels)
         if (a.out_f32) {
           float* op = static_cast<float*>(a.out) + (int64_t)blockIdx.z * a.split_stride + pix * a.out_ps + (int64_t)cbase * a.out_cs;
+          if (a.out_cs == 1 && (reinterpret_cast<uintptr_t>(op) & 15) == 0) {
+            // channel-contiguous rows (the fp32 heads, split-K partial tiles): 16-byte stores for whole quads inside Cout
+            // (scalar stores at a 32 / 48-byte row pitch touched every sector four times)
 #pragma unroll
-          for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
+            for (int j = 0; j < CH; j += 4) {
+              if (cbase + j + 3 < a.Cout) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (cbase + j + k < a.Cout) op[j + k] = v[j + k];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (cbase + j < a.Cout) op[(int64_t)j * a.out_cs] = v[j];
+          }
         } else {
           bf16* op = static_cast<bf16*>(a.out) + pix * a.out_ps + (int64_t)cbase * a.out_cs;
 #pragma unroll 1
