@@ -269,34 +269,39 @@ __global__ void __launch_bounds__(256) upsample_scalar_kernel(cptr_t<T> in, int6
 // ------------------------------------------------------------------------------------------------------
 // MaxPool2d(3, 2, 1)
 // ------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int V>                     // V channels per thread: 8 (16-byte accesses) when C % 8 == 0, else 4
 __global__ void __launch_bounds__(256) maxpool_kernel(cptr_t<T> in, int64_t in_ld, int N, int H, int W,
                                                       int C, int Ho, int Wo, ptr_t<T> out, int64_t out_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
-  const int c4n = C >> 2;
-  const int64_t total = (int64_t)N * Ho * Wo * c4n;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
-    int64_t pix = idx / c4n; int c = (int)(idx - pix * c4n) * 4;
-    int n = (int)(pix / ((int64_t)Ho * Wo));
-    int r = (int)(pix - (int64_t)n * Ho * Wo);
-    int oy = r / Wo, ox = r - oy * Wo;
-    float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  const uint32_t cvn = (uint32_t)C / V;
+  const uint32_t hw = (uint32_t)Ho * (uint32_t)Wo;
+  const uint32_t total = (uint32_t)N * hw * cvn;                    // (host: < 2^31)
+  const uint32_t nthreads = gridDim.x * blockDim.x;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const uint32_t pix = idx / cvn; const int c = (int)(idx - pix * cvn) * V;
+    const int n = (int)(pix / hw);
+    const int r = (int)(pix - (uint32_t)n * hw);
+    const int oy = r / Wo, ox = r - oy * Wo;
+    float m[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) m[j] = -INFINITY;
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
-      int iy = oy * 2 - 1 + dy;
+      const int iy = oy * 2 - 1 + dy;
       if (iy < 0 || iy >= H) continue;
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        int ix = ox * 2 - 1 + dx;
+        const int ix = ox * 2 - 1 + dx;
         if (ix < 0 || ix >= W) continue;
-        float v[4];
-        load4(in + (((int64_t)(n * H + iy) * W + ix) * in_ld + c), v);
+        float v[V];
+        if constexpr (V == 8) load8(in + (((int64_t)(n * H + iy) * W + ix) * in_ld + c), v);
+        else load4(in + (((int64_t)(n * H + iy) * W + ix) * in_ld + c), v);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) m[j] = fmaxf(m[j], v[j]);
+        for (int j = 0; j < V; ++j) m[j] = fmaxf(m[j], v[j]);
       }
     }
-    store4(out + (pix * out_ld + c), m);
+    if constexpr (V == 8) store8(out + ((int64_t)pix * out_ld + c), m);
+    else store4(out + ((int64_t)pix * out_ld + c), m);
   }
 }
 
@@ -517,8 +522,15 @@ static int maxpool_t(const void* in, int64_t in_ld, int N, int H, int W, int C, 
                      int64_t ps, cudaStream_t s) {
   int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int64_t total = (int64_t)N * Ho * Wo * (C / 4);
-  launch_k(maxpool_kernel<T>, grid_for(total, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, N, H, W, C, Ho, Wo,
-                                                        mkptr<T>(out, ps), out_ld);
+  if (total >= (int64_t)0x7fffffff) return OTVM_ERR_UNSUPPORTED;
+  const bool wide = C % 8 == 0 && in_ld % 8 == 0 && out_ld % 8 == 0 &&
+                    !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15);
+  if (wide)
+    launch_k(maxpool_kernel<T, 8>, grid_for(total / 2, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, N, H, W, C, Ho, Wo,
+                                                             mkptr<T>(out, ps), out_ld);
+  else
+    launch_k(maxpool_kernel<T, 4>, grid_for(total, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, N, H, W, C, Ho, Wo,
+                                                          mkptr<T>(out, ps), out_ld);
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }
