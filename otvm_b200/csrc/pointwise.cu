@@ -243,6 +243,64 @@ __global__ void __launch_bounds__(256) upsample8_kernel(cptr_t<T> in, int64_t in
   }
 }
 
+// Exact x2 variant (Ho = 2 Hi, Wo = 2 Wi: every big resize of the frame): a thread owns one INPUT pixel and 8 channels,
+// loads its 3 x 3 neighbourhood once and writes the 2 x 2 output block that lies inside it -- 9 loads per 4 outputs
+// instead of 16.  Output (2m + a, 2k + b) interpolates rows {m - 1 + a, m + a} and columns {k - 1 + b, k + b} of the
+// neighbourhood with the weights of src_index; where src_index clamps (image border) its weight on the clamped
+// neighbour is exactly 0, so the statically chosen (clamped) neighbour contributes 0 as well: same arithmetic.
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x8_kernel(cptr_t<T> in, int64_t in_ld, int Hi, int Wi, int C,
+                                                          cptr_t<T> add, int64_t add_ld, ptr_t<T> out, int64_t out_ld,
+                                                          ptr_t<T> out_relu, int64_t out_relu_ld, int N) {
+  pdl_sync();                                  // PDL contract (common.cuh)
+  const uint32_t c8n = (uint32_t)C >> 3, hw = (uint32_t)Hi * (uint32_t)Wi;
+  const uint32_t total = (uint32_t)N * hw * c8n, nthreads = gridDim.x * blockDim.x;
+  const int Ho = 2 * Hi, Wo = 2 * Wi;
+  for (uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += nthreads) {
+    const uint32_t pix = idx / c8n; const int c = (int)(idx - pix * c8n) * 8;
+    const int n = (int)(pix / hw);
+    const int r = (int)(pix - (uint32_t)n * hw);
+    const int m = r / Wi, k = r - m * Wi;
+    cptr_t<T> b = in + ((int64_t)n * Hi * Wi * in_ld + c);
+    float v[3][3][8];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int y = min(max(m - 1 + dy, 0), Hi - 1);
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int x = min(max(k - 1 + dx, 0), Wi - 1);
+        load8(b + ((int64_t)y * Wi + x) * in_ld, v[dy][dx]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      int y0, y1; float ly;
+      src_index(0.5f, 2 * m + a, Hi, y0, y1, ly);
+      const float hy = 1.f - ly;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        int x0, x1; float lx;
+        src_index(0.5f, 2 * k + bb, Wi, x0, x1, lx);
+        const float hx = 1.f - lx;
+        const int64_t opix = ((int64_t)n * Ho + (2 * m + a)) * Wo + (2 * k + bb);
+        float o[8], a8[8];
+        if (add) load8(add + (opix * add_ld + c), a8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          o[j] = hy * (hx * v[a][bb][j] + lx * v[a][bb + 1][j]) + ly * (hx * v[a + 1][bb][j] + lx * v[a + 1][bb + 1][j]);
+          if (add) o[j] = a8[j] + o[j];
+        }
+        store8(out + (opix * out_ld + c), o);
+        if (out_relu) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaxf(o[j], 0.f);
+          store8(out_relu + (opix * out_relu_ld + c), o);
+        }
+      }
+    }
+  }
+}
+
 // scalar-channel variant writing fp32 (NHWC with out_ld, or NCHW planes): the 3-channel STM logits (STM.py:136)
 template <typename T>
 __global__ void __launch_bounds__(256) upsample_scalar_kernel(cptr_t<T> in, int64_t in_ld, int Hi,
@@ -488,6 +546,12 @@ static int upsample_t(const void* in, int64_t in_ld, int N, int Hi, int Wi, int 
                       (!out_relu || out_relu_ld % 8 == 0) &&
                       !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(add) |
                          reinterpret_cast<uintptr_t>(out_relu)) & 15);
+    if (wide && Ho == 2 * Hi && Wo == 2 * Wi && (int64_t)N * Ho * Wo * (C / 8) < (int64_t)0x7fffffff) {
+      launch_k(upsample2x8_kernel<T>, grid_for((int64_t)N * Hi * Wi * (C / 8), 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, Hi, Wi, C,
+               mkcptr<T>(add, ps), add_ld, mkptr<T>(out, ps), out_ld, mkptr<T>(out_relu, ps), out_relu_ld, N);
+      OTVM_LAUNCH_CHECK();
+      return OTVM_OK;
+    }
     if (wide && (int64_t)N * Ho * Wo * (C / 8) < (int64_t)0x7fffffff) {
       int64_t total8 = (int64_t)N * Ho * Wo * (C / 8);
       launch_k(upsample8_kernel<T>, grid_for(total8, 256), 256, 0, s, mkcptr<T>(in, ps), in_ld, Hi, Wi, C, Ho, Wo,
