@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
   uint64_t* accum_bar = empty_bar + a.nstage;
   uint64_t* a_empty = accum_bar + 1;                                  // [4] patch ring (halo mode)
   uint64_t* a_full = a_empty + 4;                                     // [4]
+  uint64_t* res_bar = a_full + 3;                                     // residual tile landed (GroupNorm-fused + residual); the
+                                                                      // patch ring never has more than two slots
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 4);
   float* sstat = reinterpret_cast<float*>(tmem_slot + 2);            // [<=128] GroupNorm partials (sum, sumsq per slot)
   float* sbias = sstat + 256;                                        // [BN] bias of this tile's channels
@@ -463,7 +465,14 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     const int64_t pix = ((int64_t)n_img * a.Ho + oy) * a.Wo + ox;
     // columns per TMEM load: 32; 16 with a residual (two prefetched residual planes + main / cross accumulator chunks must
     // fit the 96 registers that keep two 320-thread CTAs on an SM)
-    constexpr int CH = (BN >= 32 && !kRes) ? 32 : 16;
+    // Residual: the residual TILE is fetched by TMA into the staging tiles as soon as the pipeline stages are dead (all
+    // MMAs complete), read back from shared memory and the result written in its place: no global loads and no residual
+    // registers in the epilogue.  GroupNorm-fused layers hide the fetch behind their statistics pass + grid barrier; the
+    // others wait ~1 us once instead of two exposed global-load latencies per 16-column chunk (64 -> 256 1x1 at 128^2:
+    // 3.2 us of a 5 us epilogue).  tmR is the residual's tensor map; the variants with a second (ReLU) output use tmR for
+    // that output and keep the register path (kResTma false).
+    constexpr bool kResTma = kRes && !kRelu2;
+    constexpr int CH = (BN >= 32 && (!kRes || kResTma)) ? 32 : 16;
     constexpr int NCHUNK = BN / CH;
     // column range of this group: BN = 128 -> one 64-column sub-tile per group, BN = 64 -> one 32-column chunk per group
     const int ngrp = (NCHUNK >= 2 && blockDim.x > kConvThreads) ? 2 : 1;
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     // residual planes 0 / 1 of one chunk (a third plane is fetched where it is added)
     uint4 rr[2][CH / 8];
     auto load_res = [&](int cbase) {
-      if constexpr (kRes) {
+      if constexpr (kRes && !kResTma) {
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
           if ((uint32_t)pl < nplane) {
@@ -527,6 +536,19 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     mbar_wait(accum_bar, 0);
     tcgen05_after_sync();
     if (dbg && threadIdx.x == 64) dbg[5] = clock64();
+    if constexpr (kResTma) {
+      // every MMA has completed: the pipeline stages are dead, the staging tiles may be filled
+      if (threadIdx.x == 64) {
+        constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2;
+        constexpr int NSUB = BN > 64 ? BN / 64 : 1;
+        int nsub = 0;
+        for (int sub = 0; sub < NSUB; ++sub) nsub += (n0 + sub * 64 < a.Cout) ? 1 : 0;
+        mbar_arrive_expect_tx(res_bar, (uint32_t)nsub * nplane * 128u * ROWB);
+        for (uint32_t pl = 0; pl < nplane; ++pl)
+          for (int sub = 0; sub < nsub; ++sub)
+            tma_load_5d(smem + pl * TILE + (size_t)sub * 128 * ROWB, &tmR, res_bar, n0 + sub * 64, x0, y0, n_img, (int)pl);
+      }
+    }
     if constexpr (GN == GN_FUSED) {
       // ---- fused GroupNorm: pass 1 accumulates the statistics of the fp32 convolution output (the accumulator
       // stays in TMEM), a grid-wide barrier makes every CTA's contribution visible, pass 2 (the loop below)
@@ -595,6 +617,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         }
       }
     };
+    if constexpr (kResTma) mbar_wait(res_bar, 0);
     int pending_sub = -1;                                    // staged sub-tile not yet handed to the TMA store
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += CH) {
@@ -627,7 +650,22 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         }
         stats_chunk(qv, c);
       }
-      if constexpr (kRes) {
+      if constexpr (kResTma) {
+        constexpr uint32_t ROWB = (BN < 64 ? BN : 64) * 2, MASK = ROWB == 128 ? 7u : ROWB == 64 ? 3u : 1u;
+#pragma unroll
+        for (int j = 0; j < CH / 8; ++j) {
+          const int cc = c + 8 * j;
+          uint32_t off = (uint32_t)(cc >> 6) * (128u * ROWB) + (uint32_t)r * ROWB + (uint32_t)(cc & 63) * 2u;
+          off ^= ((off >> 7) & MASK) << 4;
+#pragma unroll 1
+          for (uint32_t pl = 0; pl < nplane; ++pl) {
+            const uint4 t = *reinterpret_cast<const uint4*>(smem + pl * TILE + off);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { v[8 * j + 2 * k] += __low2float(h[k]); v[8 * j + 2 * k + 1] += __high2float(h[k]); }
+          }
+        }
+      } else if constexpr (kRes) {
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
           if ((uint32_t)pl < nplane) {
@@ -1527,6 +1565,12 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
                        a.planes > 1 ? (uint64_t)a.act_plane * 2 : (uint64_t)p->N * a.Ho * a.Wo * p->out_ps * 2};
     int rc = make_tmap_bf16(&tmO, p->out, 5, dims, str, box, oswz);
     if (rc) return rc;
+    if (p->res && !p->out_relu) {            // the residual tile arrives by TMA (kResTma)
+      uint64_t str2[4] = {(uint64_t)p->res_ld * 2, (uint64_t)a.Wo * p->res_ld * 2, (uint64_t)a.Ho * a.Wo * p->res_ld * 2,
+                          a.planes > 1 ? (uint64_t)a.act_plane * 2 : (uint64_t)p->N * a.Ho * a.Wo * p->res_ld * 2};
+      rc = make_tmap_bf16(&tmR, p->res, 5, dims, str2, box, oswz);
+      if (rc) return rc;
+    }
     if (p->out_relu) {
       uint64_t str2[4] = {(uint64_t)p->out_relu_ld * 2, (uint64_t)a.Wo * p->out_relu_ld * 2,
                           (uint64_t)a.Ho * a.Wo * p->out_relu_ld * 2,
