@@ -563,15 +563,18 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         for (int j = 0; j < CH; ++j) qv[j] = valid ? __uint_as_float(raw[j]) + sbias[c + j] : 0.f;
         stats_chunk(qv, c);
       }
+      if (dbg && e == 0) dbg[13] = clock64();                 // statistics pass done (this thread)
       bar_sync_n(1, nthr);
       gn_reduce_columns(sred, e, nthr, BN / cgc, cgc, cg, n0, a.Cout, a.gn_stats);
       bar_sync_n(1, nthr);                                    // this CTA's atomics are issued
+      if (dbg && e == 0) dbg[14] = clock64();                 // column sums + atomics issued
       if (e == 0) {
         unsigned int* ctr = reinterpret_cast<unsigned int*>(a.gn_stats + 64);     // zeroed with the statistics arena
         const unsigned int total = gridDim.x * gridDim.y;
         // release at gpu scope: the CTA's statistics atomics (ordered before this by the barrier) are visible to whoever
         // acquires the incremented counter
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        if (dbg) dbg[15] = clock64();                         // release-increment issued
         // Bounded wait.  The host only selects this variant for grids it computed to be co-resident, but it cannot see
         // what else shares the device (other streams / processes, MPS, a debugger): if a CTA is still missing after
         // ~1 s the kernel gives up WITHOUT trapping (a trap would poison the whole CUDA context, graph replays included):
@@ -582,6 +585,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
           __nanosleep(20);
           if (++spins > (1u << 24)) { atomicOr(&g_device_error_flags, 1u); break; }
         }
+        if (dbg) { dbg[16] = clock64(); dbg[18] = spins; }    // barrier passed; polls that saw it closed
       }
       bar_sync_n(1, nthr);
       if (e < BN && n0 + e < a.Cout) {
@@ -595,6 +599,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
         sstat[128 + e] = a.gn_beta[ch] - (float)mean * sc;
       }
       bar_sync_n(1, nthr);
+      if (dbg && e == 0) dbg[17] = clock64();                 // scale / shift of this tile's channels ready
     }
     // sub-tile hand-over to the TMA store: the threads that staged a 64-column sub-tile meet on a named barrier and one
     // of them issues its stores; BN = 128 with two groups: each group owns one sub-tile (barriers 2 / 3, 128 threads)

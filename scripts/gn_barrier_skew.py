@@ -29,5 +29,12 @@ for Cin, Cout, k, d, H, W in [(64, 256, 1, 1, 128, 128), (256, 1024, 1, 1, 64, 6
     c0 = start + (t[:, 8] - t[:, 0]) / 1965.0                       # first chunk of pass 2
     end = (t[:, 12] - t0) / 1e3
     q = lambda v: f"min {v.min():5.1f} med {v.median():5.1f} max {v.max():5.1f}"
+    last = int(torch.argmax(acc))                                   # the CTA whose accumulator was ready last
+    rel = lambda i: (t[last, i] - t[last, 5]) / 1965.0
+    print(f"   last CTA, us after its accumulator: statistics pass {rel(13):.2f}, column sums + atomics {rel(14):.2f}, release-increment issued "
+          f"{rel(15):.2f}, barrier passed {rel(16):.2f} ({int(t[last, 18])} closed polls), scale/shift ready {rel(17):.2f}, first chunk {rel(8):.2f}")
+    med = lambda i: ((t[:, i] - t[:, 5]) / 1965.0).median()
+    print(f"   median CTA: statistics pass {med(13):.2f}, atomics {med(14):.2f}, increment {med(15):.2f}, barrier passed {med(16):.2f}, "
+          f"scale/shift {med(17):.2f}, first chunk {med(8):.2f}")
     print(f"Cin={Cin} Cout={Cout} k={k} {H}x{W} ctas={len(t)}: CTA start {q(start)} | accumulator ready {q(acc)} | pass-2 chunk 0 {q(c0)} | "
           f"end {q(end)}  => barrier released {c0.min() - acc.max():.1f} us after the LAST accumulator")
