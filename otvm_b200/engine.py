@@ -169,7 +169,7 @@ class FramePlan:
         self.bufs: Dict[str, torch.Tensor] = {}
         # GroupNorm statistics arena: one [32][2] fp64 slot per normalised convolution, zeroed ONCE per frame
         # (one memset node instead of one in front of each of the 66 convolutions)
-        self.gn_arena = torch.zeros(128, 72, dtype=torch.float64, device=device)   # [32][2] sums + barrier counter + pad
+        self.gn_arena = torch.zeros(320, 72, dtype=torch.float64, device=device)   # [32][2] sums + barrier counter + pad
         self.gn_slots: Dict[str, int] = {}
         self.pending: Optional[int] = None          # bank slot whose memorize pass is deferred to the next frame
 
@@ -488,7 +488,7 @@ class Engine:
         # Only while nothing else is in flight on another stream: two grid-synchronising kernels sharing the SMs
         # could each hold slots the other needs to become fully resident.
         alone = self._ws_tag == "main" and self._open_forks == 0
-        if alone and cout >= 1024 and not ops.DRY and self._ws_gn_sliced(pl, conv, g, b, x, dst, raw, act, res, stride, pad, dil):
+        if alone and cout >= 128 and not ops.DRY and self._ws_gn_sliced(pl, conv, g, b, x, dst, raw, act, res, stride, pad, dil):
             return dst
         if alone and self._conv(pl, conv, x, out=dst, stride=stride, pad=pad, dil=dil, gn_stats=stats,
                                 gn_stats_zeroed=True, gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res):
@@ -520,8 +520,8 @@ class Engine:
             ns = 0
             if not ops.conv2d(x, w, bias, dst, stride=stride, pad=pad, dil=dil, workspace=ws, gn_stats=pl.gn_slot(conv),
                               gn_stats_zeroed=True, gn_fuse=(g, b, 1e-5), gn_raw_out=raw, act=act, res=res, query_fuse=True):
-                for n in (2, 4):
-                    if (cout // n) % (cout // 32) == 0 and run(0, cout // n, 0, query=True):
+                for n in (2, 4, 8):
+                    if cout % n == 0 and (cout // n) % max(cout // 32, 8) == 0 and run(0, cout // n, 0, query=True):
                         ns = n
                         break
             self._gn_slices[key] = ns
