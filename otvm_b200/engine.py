@@ -884,7 +884,7 @@ class Engine:
         buffers: scaled_img [3,H,W], trimap [3,H,W], tri3 [Hp*Wp,4] one-hot (padded), alpha [H,W].
 
         Steady-state frames are replayed from a CUDA graph keyed by (bank size, destination slot): the frame is
-        ~270 kernel launches whose host-side issue cost would otherwise bound the frame rate."""
+        ~180 kernel launches whose host-side issue cost would otherwise bound the frame rate."""
         H, W = a.shape[-2:]
         pl = self.plan(H, W)
         bank = self.bank(pl)
