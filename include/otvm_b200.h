@@ -239,6 +239,15 @@ OTVM_API int otvm_edt_sq(const uint8_t* seed, int32_t H, int32_t W, int32_t* d2,
 OTVM_API int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int32_t raw_f32, const float* extras,
                   int64_t P, float* out7, void* alpha_dst, int64_t alpha_ld, void* stream);
 
+/* The 1x1 head convolution on a 16-channel activation + otvm_fba_head in ONE pointwise pass: replaces
+ * nn.Conv2d(16, 7, 1) `conv_up4.4` (FBA/models.py:347) / nn.Conv2d(16, 10, 1) `pred.4` (:415) and the fusion behind them.
+ *   x   : [P][x_ld] dtype, 16 channels;   w: [Cout][16] fp32, bias: [Cout] fp32 or NULL, 7 <= Cout <= 12
+ *   raw : [P][raw_ld] fp32 (raw_ld = 8 or 12): raw[p][co] = bias[co] + sum_c w[co][c] x[p][c], columns >= Cout zero
+ *   extras / out7 / alpha_dst / alpha_ld as in otvm_fba_head (the fusion reads raw[p][0..6]) */
+OTVM_API int otvm_head_conv_fba(const void* x, int64_t x_ld, int32_t dtype, const float* w, const float* bias, int32_t Cout,
+                       float* raw, int64_t raw_ld, const float* extras, int64_t P, float* out7, void* alpha_dst,
+                       int64_t alpha_ld, void* stream);
+
 /* softmax of the refined trimap logits (models/alpha/model.py:460), the 20-channel memorize input
  * cat(tri3, alpha, hid16) + frame (models/trimap/model.py:231, STM.py:56-67: 22 = 3 normalised RGB + unknown
  * + fg + alpha + 16 hidden, padded to mem_ld), and the cropped planar outputs eval.py reads (:495-508).

@@ -90,6 +90,7 @@ SIGNATURES = {
                                      c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "otvm_edt_sq": (C.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "otvm_fba_head": (C.c_int, [c_vp, c_i64, c_i32, c_i32, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "otvm_head_conv_fba": (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
     "otvm_frame_outputs": (C.c_int, [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32,
                                      c_i32, C.POINTER(c_f), c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "otvm_unpack_frame_u8": (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),

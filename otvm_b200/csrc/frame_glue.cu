@@ -265,33 +265,90 @@ __global__ void trimap_pack_kernel(const float* __restrict__ extras, const int* 
 // ---------------------------------------------------------------------------------------------------
 // clamp / sigmoid / fba_fusion (FBA/models.py:279-288)
 // ---------------------------------------------------------------------------------------------------
+// clamp / sigmoid / fba_fusion of one pixel (FBA/models.py:279-288, 383-390): raw = (alpha, F rgb, B rgb), img rgb
+__device__ __forceinline__ void fba_fuse(const float (&raw)[7], const float (&img)[3], float& a2, float (&Fo)[3], float (&Bo)[3]) {
+  const float al = fminf(fmaxf(raw[0], 0.f), 1.f);
+  float F[3], B[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    F[c] = 1.f / (1.f + expf(-raw[1 + c]));
+    B[c] = 1.f / (1.f + expf(-raw[4 + c]));
+  }
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float f = al * img[c] + (1.f - al * al) * F[c] - al * (1.f - al) * B[c];
+    float b = (1.f - al) * img[c] + (2.f * al - al * al) * B[c] - al * (1.f - al) * f;   // uses updated F (:281)
+    f = fminf(fmaxf(f, 0.f), 1.f);
+    b = fminf(fmaxf(b, 0.f), 1.f);
+    Fo[c] = f; Bo[c] = b;
+    num += (img[c] - b) * (f - b);
+    den += (f - b) * (f - b);
+  }
+  a2 = (al * 0.1f + num) / (den + 0.1f);
+  a2 = fminf(fmaxf(a2, 0.f), 1.f);
+}
+
 template <typename TR, typename TA>
 __global__ void fba_head_kernel(cptr_t<TR> raw, int64_t raw_ld, const float* __restrict__ extras,
                                 int64_t P, float* __restrict__ out7, ptr_t<TA> alpha_dst, int64_t alpha_ld) {
   pdl_sync();                                  // PDL contract (common.cuh)
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
     cptr_t<TR> r = raw + p * raw_ld;
-    float al = fminf(fmaxf(ld1(r, 0), 0.f), 1.f);
-    float F[3], B[3], img[3];
+    float rv[7], img[3], a2, Fo[3], Bo[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      F[c] = 1.f / (1.f + expf(-ld1(r, 1 + c)));
-      B[c] = 1.f / (1.f + expf(-ld1(r, 4 + c)));
-      img[c] = extras[p * 8 + c];
-    }
-    float num = 0.f, den = 0.f, Fo[3], Bo[3];
+    for (int c = 0; c < 7; ++c) rv[c] = ld1(r, c);
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      float f = al * img[c] + (1.f - al * al) * F[c] - al * (1.f - al) * B[c];
-      float b = (1.f - al) * img[c] + (2.f * al - al * al) * B[c] - al * (1.f - al) * f;   // uses updated F (:281)
-      f = fminf(fmaxf(f, 0.f), 1.f);
-      b = fminf(fmaxf(b, 0.f), 1.f);
-      Fo[c] = f; Bo[c] = b;
-      num += (img[c] - b) * (f - b);
-      den += (f - b) * (f - b);
+    for (int c = 0; c < 3; ++c) img[c] = extras[p * 8 + c];
+    fba_fuse(rv, img, a2, Fo, Bo);
+    float* o = out7 + p * 8;
+    *reinterpret_cast<float4*>(o) = make_float4(a2, Fo[0], Fo[1], Fo[2]);
+    *reinterpret_cast<float4*>(o + 4) = make_float4(Bo[0], Bo[1], Bo[2], 0.f);
+    if (alpha_dst) st1(alpha_dst, p * alpha_ld, a2);
+  }
+}
+
+// The 1x1 head convolution (16 -> 7 / 10 channels, FBA/models.py:347 `conv_up4.4`, :415 `pred.4`) + the fusion above in ONE
+// pointwise pass: 160 multiply-adds per pixel are no tensor-core work -- as a tcgen05 layer it was 2048 one-tile CTAs and
+// 19-22 us, followed by a second kernel that re-read its fp32 output.  fp32 weights and accumulation on the stored
+// (split) activations; raw (the head's output, kept: the refined-trimap logits 7..9 are read by otvm_frame_outputs) is
+// written as whole 16-byte quads, columns >= Cout as zeros.
+template <typename T>
+__global__ void __launch_bounds__(256) head_conv_fba_kernel(cptr_t<T> x, int64_t x_ld, const float* __restrict__ w,
+                                                            const float* __restrict__ bias, int Cout, float* __restrict__ raw,
+                                                            int64_t raw_ld, const float* __restrict__ extras, int64_t P,
+                                                            float* __restrict__ out7, ptr_t<T> alpha_dst, int64_t alpha_ld) {
+  __shared__ float sw[12][16];
+  __shared__ float sb[12];
+  for (int i = threadIdx.x; i < 12 * 16; i += blockDim.x) sw[i >> 4][i & 15] = (i >> 4) < Cout ? w[i] : 0.f;   // constants
+  if (threadIdx.x < 12) sb[threadIdx.x] = (threadIdx.x < Cout && bias) ? bias[threadIdx.x] : 0.f;
+  pdl_sync();                                  // PDL contract (common.cuh)
+  __syncthreads();
+  const int nq = (int)(raw_ld >> 2);             // 16-byte quads per raw row (2 or 3)
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+    float v[16];
+    {
+      float v0[8], v1[8];
+      load8(x + p * x_ld, v0); load8(x + (p * x_ld + 8), v1);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) { v[c] = v0[c]; v[8 + c] = v1[c]; }
     }
-    float a2 = (al * 0.1f + num) / (den + 0.1f);
-    a2 = fminf(fmaxf(a2, 0.f), 1.f);
+    float r[12];
+#pragma unroll
+    for (int co = 0; co < 12; ++co) {
+      float acc = sb[co];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc = fmaf(sw[co][c], v[c], acc);
+      r[co] = acc;
+    }
+    float* rp = raw + p * raw_ld;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (q < nq) *reinterpret_cast<float4*>(rp + 4 * q) = make_float4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+    float rv[7] = {r[0], r[1], r[2], r[3], r[4], r[5], r[6]}, img[3], a2, Fo[3], Bo[3];
+    const float4 e0 = *reinterpret_cast<const float4*>(extras + p * 8);
+    img[0] = e0.x; img[1] = e0.y; img[2] = e0.z;
+    fba_fuse(rv, img, a2, Fo, Bo);
     float* o = out7 + p * 8;
     *reinterpret_cast<float4*>(o) = make_float4(a2, Fo[0], Fo[1], Fo[2]);
     *reinterpret_cast<float4*>(o + 4) = make_float4(Bo[0], Bo[1], Bo[2], 0.f);
@@ -481,6 +538,22 @@ extern "C" int otvm_fba_head(const void* raw, int64_t raw_ld, int32_t dtype, int
   else
     DISPATCH_DTYPE(dtype, (launch_k(fba_head_kernel<T, T>, g, 256, 0, s, mkcptr<T>(raw, ps), raw_ld, extras, P, out7,
                                     mkptr<T>(alpha_dst, ps), alpha_ld)));
+  OTVM_LAUNCH_CHECK();
+  return OTVM_OK;
+}
+
+extern "C" int otvm_head_conv_fba(const void* x, int64_t x_ld, int32_t dtype, const float* w, const float* bias, int32_t Cout,
+                                  float* raw, int64_t raw_ld, const float* extras, int64_t P, float* out7, void* alpha_dst,
+                                  int64_t alpha_ld, void* stream) {
+  if (!x || !w || !raw || !extras || !out7 || Cout < 7 || Cout > 12 || raw_ld < Cout || raw_ld % 4 || raw_ld > 12 || x_ld % 8)
+    return OTVM_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(raw) | reinterpret_cast<uintptr_t>(extras) |
+       reinterpret_cast<uintptr_t>(out7)) & 15)
+    return OTVM_ERR_ARG;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int g = grid1d(P, 256);
+  DISPATCH_DTYPE(dtype, launch_k(head_conv_fba_kernel<T>, g, 256, 0, s, mkcptr<T>(x, ps), x_ld, w, bias, Cout, raw, raw_ld, extras, P,
+                                 out7, mkptr<T>(alpha_dst, ps), alpha_ld));
   OTVM_LAUNCH_CHECK();
   return OTVM_OK;
 }

@@ -119,6 +119,13 @@ class PackedWeights:
                       "NET.refine.pred.4"]
         for name in plain:
             put(name, f(name + ".weight"), f(name + ".bias"))
+        # the two 1x1 heads run in a pointwise kernel with fp32 weights (ops.head_conv_fba)
+        self.head: Dict[str, tuple] = {}
+        if fba:
+            for name in ("NET.decoder.conv_up4.4", "NET.refine.pred.4"):
+                w = f(name + ".weight")
+                self.head[name] = (w.reshape(w.shape[0], w.shape[1]).contiguous().to(device),
+                                   f(name + ".bias").contiguous().to(device))
         ms = lambda m, s: [float(v) for v in f(m).flatten()] + [float(v) for v in f(s).flatten()]
         self.ms_q = ms("trimap.model.Encoder_Q.mean", "trimap.model.Encoder_Q.std")
         self.ms_m = ms("trimap.model.Encoder_M.mean", "trimap.model.Encoder_M.std")
@@ -784,11 +791,10 @@ class Engine:
         x = self._conv(pl, dn + ".conv_up4.0", cat4, pad=1, act=ACT_LEAKY)
         hid_d = self._conv(pl, dn + ".conv_up4.2", x, pad=1, act=ACT_LEAKY)
         raw7 = pl.buf("raw7", (1, Hp, Wp, 8), torch.float32, zero=True)
-        self._conv(pl, dn + ".conv_up4.4", hid_d, out=raw7[..., :7])
         P = Hp * Wp
         extras = pl.bufs["extras"]
         out7 = pl.buf("out7", (P, 8), torch.float32)
-        ops.fba_head(raw7, 8, self.dtype, extras, P, out7, cat4[..., 72:73], cat4.stride(2))
+        ops.head_conv_fba(hid_d, *self.w.head[dn + ".conv_up4.4"], raw7, extras, P, out7, cat4[..., 72:73], cat4.stride(2))
         # refinement (FBA/models.py:417-435)
         r = "NET.refine"
         x = self._ws_gn(pl, r + ".conv1.0", r + ".conv1.1", cat4, act=ACT_LEAKY, pad=1)
@@ -798,9 +804,8 @@ class Engine:
         x = self._conv(pl, r + ".pred.0", x, pad=1, act=ACT_LEAKY)
         hid = self._conv(pl, r + ".pred.2", x, "hid", pad=1, act=ACT_LEAKY)
         raw10 = pl.buf("raw10", (1, Hp, Wp, 12), torch.float32, zero=True)
-        self._conv(pl, r + ".pred.4", hid, out=raw10[..., :10])
         fused = pl.buf("fused", (P, 8), torch.float32)
-        ops.fba_head(raw10, 12, self.dtype, extras, P, fused)
+        ops.head_conv_fba(hid, *self.w.head[r + ".pred.4"], raw10, extras, P, fused)
         return dict(raw7=raw7, out7=out7, raw10=raw10, fused=fused, hid=hid, conv5=conv5)
 
     # ---- one frame (EvalModel.forward with tri=None, tri_gt=None) ------------------------------------

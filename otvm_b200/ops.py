@@ -343,6 +343,16 @@ def fba_head(raw, raw_ld, dtype, extras, P, out7, alpha_dst=None, alpha_ld=0):
                           _p(alpha_dst), alpha_ld, _stream()), "otvm_fba_head"))
 
 
+def head_conv_fba(x, w, bias, raw, extras, P, out7, alpha_dst=None, alpha_ld=0):
+    """1x1 head convolution (x [1,H,W,16] -> raw [..][8 or 12] fp32, w [Cout,16] fp32) + clamp / sigmoid / fba_fusion"""
+    if DRY:
+        return None
+    lib = _lib.load()
+    _timed("glue", lambda: check(
+        lib.otvm_head_conv_fba(_p(x), _ld(x), _dt(x), _p(w), _p(bias), w.shape[0], _p(raw), raw.shape[-1], _p(extras), P,
+                               _p(out7), _p(alpha_dst), alpha_ld, _stream()), "otvm_head_conv_fba"))
+
+
 def frame_outputs(raw10, raw_ld, fused, hid, extras, Hp, Wp, H, W, pad_top, pad_left, mean_std, mem_in,
                   alpha_out, trimap_out):
     if DRY:

@@ -615,6 +615,35 @@ def test_conv2d_fused_groupnorm_channel_slices(nslice, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("Cout,ld", [(7, 8), (10, 12)])
+def test_head_conv_fba(Cout, ld, dtype):
+    """the 1x1 head convolution + clamp / sigmoid / fba_fusion in one pointwise kernel against F.conv2d + the oracle's
+    fusion (FBA/models.py:279-288, 347, 383-390, 415) on the stored activations"""
+    import otvm_oracle as O
+    ops = _ops()
+    H, W = 24, 40
+    g = torch.Generator().manual_seed(Cout)
+    x = torch.randn(1, 16, H, W, generator=g)
+    w = torch.randn(Cout, 16, 1, 1, generator=g) / 3
+    b = torch.randn(Cout, generator=g) / 3
+    img = torch.rand(1, 3, H, W, generator=g)
+    raw_want = F.conv2d(rnd(dtype, x), w, b)
+    fused_want = O._head(raw_want[:, :7], img)                                   # [1,7,H,W]: alpha, F, B
+    P = H * W
+    extras = torch.zeros(P, 8, device=DEV); extras[:, :3] = img[0].permute(1, 2, 0).reshape(P, 3).to(DEV)
+    raw = torch.full((1, H, W, ld), 7.0, device=DEV)
+    out7 = torch.zeros(P, 8, device=DEV)
+    cat = zeros((1, H, W, 80), dtype)
+    ops.head_conv_fba(nhwc(x, dtype), w.view(Cout, 16).to(DEV), b.to(DEV), raw, extras, P, out7, cat[..., 72:73], cat.stride(2))
+    torch.cuda.synchronize()
+    tol = 1e-2 if dtype == torch.bfloat16 else 1e-5
+    assert rel_err(raw[0, ..., :Cout].permute(2, 0, 1).cpu(), raw_want[0]) < 1e-5
+    assert float(raw[..., Cout:].abs().max()) == 0.0                             # the pad columns of a quad are zeroed
+    assert rel_err(out7[:, :7].t().reshape(7, H, W).cpu(), fused_want[0]) < 1e-5
+    assert rel_err(nchw(cat[..., 72:73])[0, 0], fused_want[0, 0]) < tol
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("s", [1, 2, 3, 6])
 def test_conv1x1_on_ppm_cells(s, dtype):
     """the pyramid-pooling 1x1 convs run on s*s pixels (small-M kernel) with fused GroupNorm statistics"""
