@@ -84,6 +84,37 @@ def test_weight_packing_matches_torch_semantics():
     assert float((got - want).abs().max()) < 1e-4
 
 
+@pytest.mark.parametrize("planes", [1, 2])
+def test_encoder_pair_weights_and_heads(planes):
+    """the grouped Encoder_Q / Encoder_M launches read ONE pair tensor per layer whose halves ARE the per-encoder entries
+    (views, no copy, same values as a stand-alone packing), and the 1x1 heads keep their fp32 weights"""
+    from otvm_b200.engine import PackedWeights
+    from otvm_b200.fixtures import make_state_dict
+    from otvm_b200.split import split_planes
+    sd = make_state_dict("default")
+    pw = PackedWeights(sd, torch.bfloat16, "cpu", planes=planes)
+    q, m = "trimap.model.Encoder_Q", "trimap.model.Encoder_M"
+    assert len(pw.pair) == 3 * 3 + 4 * 3 + 6 * 3 + 3            # 13 bottlenecks x 3 convolutions + 3 downsample branches
+    for sfx, (wp, bp) in pw.pair.items():
+        (wq, bq), (wm, bm) = pw.conv[q + sfx], pw.conv[m + sfx]
+        cout = wq.shape[-4]
+        assert wp.shape[-4] == 2 * cout and bp.numel() == 2 * cout
+        half = (lambda t, i: t[:, i * cout:(i + 1) * cout]) if planes > 1 else (lambda t, i: t[i * cout:(i + 1) * cout])
+        assert torch.equal(half(wp, 0), wq) and torch.equal(half(wp, 1), wm)
+        assert torch.equal(bp[:cout], bq) and torch.equal(bp[cout:], bm)
+        assert wq.untyped_storage().data_ptr() == wp.untyped_storage().data_ptr()      # a view of the pair tensor
+    # values: the same BN-folded weights a single-plane fp32 packing gives, rounded / split
+    ref = PackedWeights(sd, torch.float32, "cpu")
+    name = q + ".res3.1.conv2"
+    w32 = ref.conv[name][0]
+    want = split_planes(w32, planes) if planes > 1 else w32.to(torch.bfloat16)
+    assert torch.equal(pw.conv[name][0], want)
+    for name, cout in (("NET.decoder.conv_up4.4", 7), ("NET.refine.pred.4", 10)):
+        w, b = pw.head[name]
+        assert w.dtype == torch.float32 and tuple(w.shape) == (cout, 16) and torch.equal(w, sd[name + ".weight"].view(cout, 16))
+        assert torch.equal(b, sd[name + ".bias"])
+
+
 def _reference_policy(events, max_n):
     """models/alpha/model.py:472-493 on a list of frame ids"""
     mem = None
