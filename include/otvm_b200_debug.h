@@ -13,6 +13,9 @@ void otvm_debug_set_conv_halo(int mode);
  * number of times it has been launched (tests assert that the variant under test really ran) */
 void otvm_debug_set_conv_persist(int mode);
 long long otvm_debug_conv_persist_launches(void);
+/* launches that took the cluster split-K path (K slices of a tile as a thread-block cluster, partial tiles through
+ * distributed shared memory; env OTVM_CONV_CLUSTER_K=0 disables it) */
+long long otvm_debug_conv_cluster_launches(void);
 /* K-chunks per barrier pair on one-wave grids, 1 or 2 (env OTVM_CONV_KSUB); ring budget of multi-wave grids in KB (0 = default) */
 void otvm_debug_set_conv_ksub(int n);
 void otvm_debug_set_conv_budget_kb(int kb);

@@ -226,6 +226,21 @@ inline cudaError_t launch_k(void (*kernel)(Params...), dim3 grid, dim3 block, si
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
 }
 
+// same, as thread-block clusters of (1, 1, cluster_z) CTAs (grid.z must be a multiple of cluster_z)
+template <typename... Params, typename... Args>
+inline cudaError_t launch_k_cluster(void (*kernel)(Params...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                    unsigned cluster_z, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = cluster_z;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
 // number of SMs of the CURRENT device (cached per device: several devices may be used from one process)
 int sm_count();
 int current_device();                        // cudaGetDevice, -1 on failure

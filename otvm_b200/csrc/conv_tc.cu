@@ -43,6 +43,8 @@ struct ConvTcArgs {
   uint32_t tiles_x_magic, tiles_y_magic;   // ceil(2^32 / d) for the tile-coordinate divisions (0: d == 1)
   int KC, nchunk, nstage, ksub; // nstage ring groups of ksub K-chunks each
   int k_per_split;             // K iterations per blockIdx.z slice (split-K); == num_k without split
+  int cluster_k;               // > 1 (CLUSTER kernels): the blockIdx.z slices of a tile form a thread-block cluster; CTA 0 adds
+                               // the other slices' fp32 partial tiles through distributed shared memory and runs the epilogue
   int64_t split_stride;        // elements between the fp32 partial outputs of consecutive K slices
   uint32_t aux_off;            // barriers / tmem slot / stats / bias live after max(pipeline, staging) bytes
   uint32_t a_bytes, b_bytes, sbo, layout_type;
@@ -162,7 +164,7 @@ __device__ __forceinline__ void gn_reduce_columns(const float* sred, int e, int 
   if (live && sub == 0) atomicAdd(&gn_stats[((n0 + slot * cgc) / cg) * 2 + which], (double)acc);
 }
 
-template <int BN, int GN, int EPI, bool HALO>
+template <int BN, int GN, int EPI, bool HALO, bool CLUSTER = false>
 __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) conv_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB,
                                                                const __grid_constant__ CUtensorMap tmO,
@@ -443,6 +445,11 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     else mma_loop(std::integral_constant<int, 1>{});
   }
 }
+  // Cluster split-K (CLUSTER kernels, a.cluster_k CTAs along blockIdx.z): every thread of every CTA of the cluster passes two
+  // cluster barriers: #1 once the partial accumulators of ranks 1.. are parked in their shared memory, #2 once rank 0 has
+  // read them.  A template parameter, not a run-time switch: the extra branches cost every epilogue 1.3 % when they were.
+  const uint32_t crank = CLUSTER ? blockIdx.z : 0u;
+  if constexpr (CLUSTER) { if (warp < 2) { __syncwarp(); cluster_sync_all(); } }
   if (warp >= 2) {
     // ===== epilogue: warps 2..5 (and 6..9 when the block has a second group) own TMEM lanes 32*(warp%4) .. +31 =====
     // Compile-time variants (EPI) keep the per-element instruction count low: the three store paths and the
@@ -515,6 +522,23 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
 #pragma unroll
         for (int j = 0; j < CH; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(raw2[j]));
       }
+      if constexpr (CLUSTER) {
+        if (crank == 0) {                                      // + the K slices of the other CTAs of the cluster
+          const uint32_t poff = (((uint32_t)c >> 2) * 128u + (uint32_t)r) * 16u;
+#pragma unroll 1
+          for (uint32_t pr = 1; pr < (uint32_t)a.cluster_k; ++pr) {
+            const uint32_t rem = dsmem_addr(base, pr) + poff;
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
+              const float4 t = ld_dsmem_f4(rem + (uint32_t)j * (128u * 16u));
+              raw[4 * j] = __float_as_uint(__uint_as_float(raw[4 * j]) + t.x);
+              raw[4 * j + 1] = __float_as_uint(__uint_as_float(raw[4 * j + 1]) + t.y);
+              raw[4 * j + 2] = __float_as_uint(__uint_as_float(raw[4 * j + 2]) + t.z);
+              raw[4 * j + 3] = __float_as_uint(__uint_as_float(raw[4 * j + 3]) + t.w);
+            }
+          }
+        }
+      }
     };
     auto stats_chunk = [&](const float (&qv)[CH], int c) {
       const int slot0 = c / cgc;
@@ -528,7 +552,26 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
       }
     };
 
-    if (!idle) {                                             // (whole warps: a second group on a single-chunk tile does nothing)
+    if constexpr (CLUSTER) {
+      // partial tile of a rank >= 1 CTA: fp32 [BN/4 column quads][128 rows][4] at the start of its (drained) ring, so that
+      // a warp's 16-byte accesses are contiguous on both sides
+      if (crank != 0 && !idle) {
+        mbar_wait(accum_bar, 0);
+        tcgen05_after_sync();
+#pragma unroll 1
+        for (int c = c_lo; c < c_hi; c += CH) {
+          uint32_t raw[CH];
+          load_acc(c, raw);
+          uint8_t* pp = smem + (((uint32_t)c >> 2) * 128u + (uint32_t)r) * 16u;
+#pragma unroll
+          for (int j = 0; j < CH / 4; ++j)
+            *reinterpret_cast<uint4*>(pp + (size_t)j * (128 * 16)) = make_uint4(raw[4 * j], raw[4 * j + 1], raw[4 * j + 2], raw[4 * j + 3]);
+        }
+      }
+      __syncwarp();
+      cluster_sync_all();                                    // #1
+    }
+    if (!idle && crank == 0) {                               // (whole warps: a second group on a single-chunk tile does nothing)
     // bias (a constant: no PDL dependency, and warp 2 -- weight / patch producer first -- has waited anyway)
     for (int i = e; i < BN; i += nthr) sbias[i] = (a.bias && n0 + i < a.Cout) ? a.bias[wrow + i] : 0.f;
     if (n0 + c_lo < a.Cout) load_res(n0 + c_lo);             // in flight while the last MMAs finish
@@ -768,6 +811,7 @@ __global__ void __launch_bounds__(kConvThreadsMax, ((EPI & 4) != 0 ? 1 : 2)) con
     }
     tcgen05_before_sync();
   }
+  if constexpr (CLUSTER) { __syncwarp(); cluster_sync_all(); }   // #2: rank 0 has read every partial tile
   __syncthreads();
   if (dbg && threadIdx.x == 0) { dbg[7] = clock64(); dbg[12] = gtime_ns(); }
   if (warp == 1) {
@@ -1167,6 +1211,7 @@ static int conv_ksub_mode() {
   return g_conv_ksub;
 }
 static long long g_conv_persist_launches = 0;
+static long long g_conv_cluster_launches = 0;
 static int g_conv_persist = -2;           // -2 unset, -1 auto (default), 0 off, 1 whenever the shape allows
 static int conv_persist_mode() {
   if (g_conv_persist == -2) { const char* e = getenv("OTVM_CONV_PERSIST"); g_conv_persist = e ? atoi(e) : -1; }
@@ -1257,8 +1302,22 @@ static int conv_threads() {
 }
 
 template <int BN, int GN, int EPI, bool HALO>
+static int launch_conv_tc_cluster(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
+                                  const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s) {
+  OTVM_CUDA_CHECK((ensure_dynamic_smem<conv_tc_kernel<BN, GN, EPI, HALO, true>>(220 * 1024)));
+  launch_k_cluster(conv_tc_kernel<BN, GN, EPI, HALO, true>, grid, conv_threads<BN>(), smem, s, (unsigned)a.cluster_k, tmA, tmB,
+                   tmO, tmR, a);
+  OTVM_LAUNCH_CHECK();
+  ++g_conv_cluster_launches;
+  return OTVM_OK;
+}
+
+template <int BN, int GN, int EPI, bool HALO>
 static int launch_conv_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO,
                           const CUtensorMap& tmR, const ConvTcArgs& a, dim3 grid, size_t smem, cudaStream_t s, bool dry_run) {
+  if constexpr (GN == GN_NONE && (EPI & EPI_DIRECT) == 0 && BN >= 64) {
+    if (a.cluster_k > 1) return dry_run ? OTVM_OK : launch_conv_tc_cluster<BN, GN, EPI, HALO>(tmA, tmB, tmO, tmR, a, grid, smem, s);
+  }
   OTVM_CUDA_CHECK((ensure_dynamic_smem<conv_tc_kernel<BN, GN, EPI, HALO>>(220 * 1024)));
   if constexpr (GN == GN_FUSED) {
     // the grid barrier needs every CTA resident at once.  (cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for
@@ -1504,6 +1563,20 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     if (nsplit > 16) nsplit = 16;
     while (nsplit > 1 && (int64_t)nsplit * Mtot * p->Cout * 4 > p->workspace_bytes) --nsplit;
   }
+  // Cluster split-K for the layers too short for the workspace route (< 48 K iterations) whose grid leaves at least half
+  // of the SMs idle: the K slices (blockIdx.z) of a tile form a thread-block cluster and meet in rank 0 through distributed
+  // shared memory -- no workspace, no finish kernel, the epilogue stays in the kernel.  Plain / residual / second-output
+  // epilogues of >= 64-channel tiles only (the STM encoders' and decoder's 1/16-resolution layers: 256 -> 256 3x3 at 32^2,
+  // 36 iterations on 32 or 64 CTAs).  OTVM_CONV_CLUSTER_K=0 disables.
+  static const int cluster_on = getenv("OTVM_CONV_CLUSTER_K") ? atoi(getenv("OTVM_CONV_CLUSTER_K")) : 1;
+  a.cluster_k = 1;
+  if (cluster_on && nsplit == 1 && !a.halo && bn >= 64 && !p->gn_stats && !p->out_f32 && p->out_cs == 1 &&
+      ctas * 2 <= sm_count() && num_k >= 16 && conv_tc_epi(p, bn) >= 0 && !(conv_tc_epi(p, bn) & EPI_DIRECT)) {
+    int cs = (int)(sm_count() / ctas);
+    if (cs > 8) cs = 8;                                    // portable cluster size
+    if (cs > num_k / 8) cs = num_k / 8;                    // >= 8 K iterations per slice
+    if (cs > 1) { nsplit = cs; a.cluster_k = cs; }
+  }
   if (a.halo) {                            // halo mode slices whole K-chunks (9 taps each)
     const int cps = ceil_div(a.nchunk, nsplit);
     a.k_per_split = cps * 9;
@@ -1511,6 +1584,8 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     a.k_per_split = ceil_div(num_k, nsplit);
   }
   nsplit = ceil_div(num_k, a.k_per_split);
+  if (a.cluster_k > 1) a.cluster_k = nsplit;               // (no empty slice)
+  const bool clustered = a.cluster_k > 1;
   a.split_stride = Mtot * p->Cout;
   if (a.k_per_split < 4) ksub = 1;
   a.ksub = ksub;
@@ -1585,7 +1660,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
     }
   }
   dim3 grid(a.tiles_x * a.tiles_y * p->N, ceil_div(p->Cout, bn), nsplit);
-  if (nsplit > 1) {
+  if (nsplit > 1 && !clustered) {
     ConvTcArgs b = a;                       // raw fp32 partial tiles into the workspace, epilogue deferred
     b.bias = nullptr; b.out = p->workspace; b.out_ps = p->Cout; b.out_cs = 1; b.res = nullptr; b.out_relu = nullptr;
     b.act = OTVM_ACT_NONE; b.out_f32 = 1; b.gn_stats = nullptr;
@@ -1616,6 +1691,7 @@ int conv2d_tc(const otvm_conv_params* p, cudaStream_t s, bool dry_run) {
   const size_t staging = (size_t)128 * bn * 2 * (p->out_relu ? 2 : 1) * a.planes;
   size_t need = tma_store ? staging : 0;
   if (p->gn_stats) need += (size_t)64 * 129 * sizeof(float);  // GroupNorm row partials (sred)
+  if (clustered && need < (size_t)128 * bn * 4) need = (size_t)128 * bn * 4;   // fp32 partial tile of a rank >= 1 CTA
   if (need > pipe) pipe = need;           // the epilogue tile reuses the drained stages
   const size_t smem = pipe + 1024 + 16 * 8 + 128 + 16 + 16 + (2 * 128 + 128) * sizeof(float) + (size_t)num_k * 16;
   a.aux_off = (uint32_t)pipe;
@@ -1692,6 +1768,7 @@ extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_ksub(
 // dev hook: persistent patch-mode kernel (-1 auto, 0 off, 1 whenever the shape allows; env OTVM_CONV_PERSIST)
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_persist(int mode) { otvm::g_conv_persist = mode; }
 extern "C" __attribute__((visibility("default"))) long long otvm_debug_conv_persist_launches() { return otvm::g_conv_persist_launches; }
+extern "C" __attribute__((visibility("default"))) long long otvm_debug_conv_cluster_launches() { return otvm::g_conv_cluster_launches; }
 // dev hook: 3x3 halo-patch mode on/off (default on; env OTVM_CONV_HALO=0)
 extern "C" __attribute__((visibility("default"))) void otvm_debug_set_conv_halo(int enabled) {
   otvm::g_conv_halo = enabled;              // -1 auto, 0 off, 1 forced on

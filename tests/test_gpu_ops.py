@@ -576,6 +576,46 @@ def test_conv2d_grouped_pair(case, dtype):
     assert rel_err(nchw(out), nchw(single)) < (4e-3 if dtype == torch.bfloat16 else 1e-5)
 
 
+CLUSTER_CASES = [
+    # Cin, Cout, k, N, H, W, with_res, relu2     (short grids with 16..47 K iterations: STM res4 / decoder layers at 1/16)
+    (256, 256, 3, 1, 32, 32, False, False), (256, 256, 3, 2, 32, 32, False, False), (1024, 256, 1, 2, 32, 32, False, False),
+    (256, 256, 3, 1, 32, 32, True, True), (1024, 1024, 1, 1, 16, 16, True, False), (1024, 256, 1, 1, 24, 40, False, True),
+]
+
+
+@pytest.mark.parametrize("dtype", TC_DTYPES)
+@pytest.mark.parametrize("case", CLUSTER_CASES)
+def test_conv2d_cluster_split_k(case, dtype):
+    """cluster split-K: the K slices of a tile run as a thread-block cluster, ranks >= 1 park fp32 partial tiles in shared
+    memory and rank 0 adds them through distributed shared memory inside its normal epilogue (bias, residual, activation,
+    second ReLU output) == fp32 convolution on the stored operands"""
+    import ctypes
+    from otvm_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    lib.otvm_debug_conv_cluster_launches.restype = ctypes.c_longlong
+    Cin, Cout, k, N, H, W, with_res, relu2 = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(N, Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)
+    b = torch.randn(N, Cout, generator=g)
+    res = torch.randn(N, Cout, H, W, generator=g)
+    want = torch.cat([F.conv2d(rnd(dtype, x[i:i + 1]), rnd(dtype, w[i]), b[i], 1, k // 2) for i in range(N)])
+    if with_res:
+        want = want + rnd(dtype, res)
+    wd = [wpack(w[i], dtype) for i in range(N)]
+    wp = torch.cat(wd, dim=1 if wd[0].dim() == 5 else 0).contiguous() if N > 1 else wd[0]
+    out, outr = zeros((N, H, W, Cout), dtype), zeros((N, H, W, Cout), dtype)
+    n0 = lib.otvm_debug_conv_cluster_launches()
+    ops.conv2d(nhwc(x, dtype), wp, b.reshape(-1).to(DEV), out, pad=k // 2, res=nhwc(res, dtype) if with_res else None,
+               out_relu=outr if relu2 else None, groups=N)
+    torch.cuda.synchronize()
+    assert lib.otvm_debug_conv_cluster_launches() == n0 + 1, "the cluster split-K path was not taken"
+    assert rel_err(nchw(out), want) < TOL[dtype]
+    if relu2:
+        assert rel_err(nchw(outr), F.relu(want)) < TOL[dtype]
+
+
 @pytest.mark.parametrize("dtype", TC_DTYPES)
 @pytest.mark.parametrize("nslice", [2, 4])
 def test_conv2d_fused_groupnorm_channel_slices(nslice, dtype):
