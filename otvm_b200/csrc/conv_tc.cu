@@ -21,9 +21,12 @@
 // swizzle, which is exactly the K-major canonical UMMA layout, so the MMA warp issues tcgen05.mma straight
 // from it.  Weights [Cout][KH*KW*Cin] are the K-major B operand through a 2-D tensor map.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> bias / GroupNorm statistics / residual / activation -> swizzled
-// shared-memory tile that reuses the drained pipeline stages -> TMA tensor store, which also clips ragged tiles).
+// Warp roles (192 or 320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 (+ 6..9 for tiles of >= 64 channels: two groups split the tile's columns) = epilogue (TMEM -> registers ->
+// bias / GroupNorm statistics / residual, which arrives as a TMA tile / activation -> swizzled shared-memory tile that
+// reuses the drained pipeline stages -> TMA tensor store per 64-column sub-tile, which also clips ragged tiles).
+// Variants: GroupNorm statistics or the whole GroupNorm in the epilogue (grid barrier), split-K through a workspace or
+// through a thread-block cluster (CLUSTER), grouped filter banks (one launch for the two STM encoders).
 // Ring of NSTAGE {A,B} stages with full/empty mbarriers; tcgen05.commit releases stages and publishes the
 // accumulator.  Up to two CTAs per SM (<= 113 KB smem, <= 128 TMEM columns each) so one CTA's epilogue overlaps
 // another's main loop.
