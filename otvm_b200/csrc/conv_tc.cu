@@ -1140,8 +1140,13 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
     sstat[threadIdx.x & 31][0] = 0.0; sstat[threadIdx.x & 31][1] = 0.0;
     __syncthreads();
   }
+  // channel-major destinations (the value bank, out_cs = row length): consecutive threads take consecutive PIXELS of one
+  // channel quad, so their 2-byte stores are contiguous (pixel-fastest threads scattered them a row apart: 16 vs 5 us)
+  const bool pix_fast = out_cs != 1;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = idx / c4n; const int c = (int)(idx - p * c4n) * 4;
+    int64_t p; int c;
+    if (pix_fast) { const int64_t q = idx / M; p = idx - q * M; c = (int)q * 4; }
+    else { p = idx / c4n; c = (int)(idx - p * c4n) * 4; }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int z = 0; z < S; ++z) {
       const float4 t = *reinterpret_cast<const float4*>(ws + ((int64_t)z * M + p) * Cout + c);
